@@ -1,0 +1,56 @@
+"""ctypes binding of csrc/liblecb.so (the C ABI declared in include/lecb.h).
+
+There is no fallback of any kind: if the library is missing the import fails, and if a compute entry
+point is called without a CUDA device it returns LECB_ERR_CUDA, surfaced here as RuntimeError."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "liblecb.so")
+
+c_void_p, c_int, c_i64, c_uint, c_float = C.c_void_p, C.c_int, C.c_int64, C.c_uint, C.c_float
+
+# name -> (restype, argtypes); mirrors include/lecb.h one to one (tests/test_abi.py checks the header)
+SIGNATURES = {
+    "lecb_abi_version": (c_int, []),
+    "lecb_last_error": (C.c_char_p, []),
+    "lecb_launch_count": (C.c_ulonglong, []),
+    "lecb_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int,
+                               c_uint, c_void_p]),
+    "lecb_conv3x3_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                  c_uint, c_void_p]),
+}
+
+EPI_RELU, EPI_QUICKGELU, EPI_OUT_F32 = 1, 2, 4
+
+
+class LecbError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). lecb200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here == header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(status: int, what: str = ""):
+    if status != 0:
+        msg = lib.lecb_last_error()
+        raise LecbError(f"{what or 'lecb'} failed with status {status}: {msg.decode() if msg else ''}")
+
+
+def launch_count() -> int:
+    return int(lib.lecb_launch_count())

@@ -1,0 +1,381 @@
+// Persistent warp-specialised bf16 GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+//
+//   out[M,N] = epi( A[M,K] · W[N,K]^T + bias (+ residual) )
+//
+// A tiles (128 x BK) and W tiles (BN x BK) are staged in shared memory by TMA in the canonical
+// K-major swizzled layout (BK*2 bytes per row: 128B or 64B swizzle), multiplied by tcgen05.mma
+// (one elected thread, M=128, N=BN, K=16 per instruction) into a double-buffered fp32 accumulator in
+// TMEM, and drained by four epilogue warps with tcgen05.ld (thread == output row) that apply
+// bias / residual / ReLU / QuickGELU and store bf16 or fp32.  In CONV mode the A producer issues
+// TMA *im2col* loads over the NHWC activation tensor — one (tap, channel-block) per K step, padding
+// and row/image wrap handled by the TMA unit — so a 3x3 convolution is the same GEMM with K = 9*Cin.
+//
+// Roles (192 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 TMA producer,
+// warp 5 MMA issuer + TMEM owner.  Three mbarrier rings: smem full/empty, TMEM full/empty.
+#include <stdio.h>
+
+#include "lecb_common.cuh"
+#include "lecb_host.h"
+
+namespace lecb {
+
+constexpr int kTileM = 128;
+constexpr int kNumThreads = 192;
+
+template <int BN, int BK>
+struct GemmCfg {
+  static constexpr int kABytes = kTileM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmParams {
+  const float* bias;
+  const __nv_bfloat16* residual;
+  void* out;
+  float* row_sumsq;
+  int64_t M;
+  int N;
+  int num_kb;        // K / BK
+  int num_m_tiles;
+  int num_n_tiles;
+  unsigned flags;
+  // conv mode
+  int H, W, kb_per_tap;
+};
+
+template <int BN, int BK, bool kConv>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BN, BK>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* tfull = bars + 2 * kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ------------------------------- TMA producer -------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.num_n_tiles;
+        const int n_blk = tile - m_blk * p.num_n_tiles;
+        int pw = 0, ph = 0, pn = 0;
+        if (kConv) {
+          const int64_t m0 = static_cast<int64_t>(m_blk) * kTileM;
+          const int hw = p.H * p.W;
+          pn = static_cast<int>(m0 / hw);
+          const int rem = static_cast<int>(m0 - static_cast<int64_t>(pn) * hw);
+          ph = rem / p.W;
+          pw = rem - ph * p.W;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+          if (kConv) {
+            const int tap = kb / p.kb_per_tap;
+            const int cb = kb - tap * p.kb_per_tap;
+            const int ky = tap / 3, kx = tap - ky * 3;
+            tma_load_im2col_4d(&tmA, &full[stage], sA + stage * Cfg::kABytes, cb * BK, pw - 1, ph - 1, pn,
+                               static_cast<uint16_t>(kx), static_cast<uint16_t>(ky));
+          } else {
+            tma_load_2d(&tmA, &full[stage], sA + stage * Cfg::kABytes, kb * BK, m_blk * kTileM);
+          }
+          tma_load_2d(&tmB, &full[stage], sB + stage * Cfg::kBBytes, kb * BK, n_blk * BN);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------- MMA issuer ---------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BN, true);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = make_kmajor_desc(smem_u32(sA + stage * Cfg::kABytes), BK * 2);
+          const uint64_t bdesc = make_kmajor_desc(smem_u32(sB + stage * Cfg::kBBytes), BK * 2);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_f16(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                     (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------- epilogue (warps 0-3) -----------------------
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool relu = p.flags & LECB_EPI_RELU;
+    const bool gelu = p.flags & LECB_EPI_QUICKGELU;
+    const bool out_f32 = p.flags & LECB_EPI_OUT_F32;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.num_n_tiles;
+      const int n_blk = tile - m_blk * p.num_n_tiles;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int64_t row = static_cast<int64_t>(m_blk) * kTileM + warp * 32 + lane;
+      const bool row_ok = row < p.M;
+      float ssq = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(acc * BN + c * 32), r);
+        tmem_ld_wait();
+        const int n0 = n_blk * BN + c * 32;
+        if (n0 >= p.N) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (n0 + j < p.N) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          }
+        }
+        if (p.residual != nullptr && row_ok) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row * p.N + n0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (n0 + q * 8 < p.N) {
+              const uint4 u = __ldg(rp + q);
+              float2 f;
+              f = unpack_bf16(u.x); v[q * 8 + 0] += f.x; v[q * 8 + 1] += f.y;
+              f = unpack_bf16(u.y); v[q * 8 + 2] += f.x; v[q * 8 + 3] += f.y;
+              f = unpack_bf16(u.z); v[q * 8 + 4] += f.x; v[q * 8 + 5] += f.y;
+              f = unpack_bf16(u.w); v[q * 8 + 6] += f.x; v[q * 8 + 7] += f.y;
+            }
+          }
+        }
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (gelu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+        }
+        if (row_ok) {
+          if (out_f32) {
+            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + row * p.N + n0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (n0 + q * 4 < p.N) {
+                op[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                if (p.row_sumsq != nullptr)
+                  ssq += v[q * 4] * v[q * 4] + v[q * 4 + 1] * v[q * 4 + 1] + v[q * 4 + 2] * v[q * 4 + 2] +
+                         v[q * 4 + 3] * v[q * 4 + 3];
+              }
+            }
+          } else {
+            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + row * p.N + n0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (n0 + q * 8 < p.N) {
+                uint4 u;
+                u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+                u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+                u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+                u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+                op[q] = u;
+                if (p.row_sumsq != nullptr) {
+                  float2 f;
+                  f = unpack_bf16(u.x); ssq += f.x * f.x + f.y * f.y;
+                  f = unpack_bf16(u.y); ssq += f.x * f.x + f.y * f.y;
+                  f = unpack_bf16(u.z); ssq += f.x * f.x + f.y * f.y;
+                  f = unpack_bf16(u.w); ssq += f.x * f.x + f.y * f.y;
+                }
+              }
+            }
+          }
+        }
+      }
+      if (p.row_sumsq != nullptr && row_ok) atomicAdd(p.row_sumsq + row, ssq);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN, int BK, bool kConv>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, BK>;
+  static bool configured = false;
+  auto kern = gemm_kernel<BN, BK, kConv>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return fail(LECB_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+    configured = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int sms = sm_count();
+  if (sms <= 0) return fail(LECB_ERR_CUDA, "no CUDA device");
+  const int grid = tiles < sms ? tiles : sms;
+  kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  count_launch();
+  return check_launch("gemm_kernel");
+}
+
+static int pick_bn(int N) {
+  if (N <= 32) return 32;
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  return 256;
+}
+
+}  // namespace lecb
+
+using namespace lecb;
+
+extern "C" int lecb_gemm_bf16(const void* A, const void* W, const float* bias, const void* residual, void* out,
+                              float* row_sumsq, int64_t M, int N, int K, unsigned flags, void* stream) {
+  LECB_CHECK_ARG(A && W && out, "lecb_gemm_bf16: null pointer");
+  LECB_CHECK_ARG(M > 0 && N > 0 && K > 0, "lecb_gemm_bf16: empty problem M=%lld N=%d K=%d", (long long)M, N, K);
+  LECB_CHECK_ARG(K % 32 == 0, "lecb_gemm_bf16: K=%d must be a multiple of 32", K);
+  LECB_CHECK_ARG(N % 8 == 0, "lecb_gemm_bf16: N=%d must be a multiple of 8", N);
+  LECB_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                 "lecb_gemm_bf16: operands must be 16-byte aligned");
+  const int BK = (K % 64 == 0) ? 64 : 32;
+  int BN = pick_bn(N);
+  if (BK == 32 && BN > 64) BN = 64;
+  GemmParams p{};
+  p.bias = bias;
+  p.residual = static_cast<const __nv_bfloat16*>(residual);
+  p.out = out;
+  p.row_sumsq = row_sumsq;
+  p.M = M;
+  p.N = N;
+  p.num_kb = K / BK;
+  p.num_m_tiles = static_cast<int>((M + kTileM - 1) / kTileM);
+  p.num_n_tiles = (N + BN - 1) / BN;
+  p.flags = flags;
+  CUtensorMap tmA, tmB;
+  int st = encode_tiled_2d(&tmA, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), kTileM, BK);
+  if (st) return st;
+  st = encode_tiled_2d(&tmB, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), BN, BK);
+  if (st) return st;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (BK == 64) {
+    switch (BN) {
+      case 32: return launch_gemm<32, 64, false>(tmA, tmB, p, s);
+      case 64: return launch_gemm<64, 64, false>(tmA, tmB, p, s);
+      case 128: return launch_gemm<128, 64, false>(tmA, tmB, p, s);
+      default: return launch_gemm<256, 64, false>(tmA, tmB, p, s);
+    }
+  }
+  return BN == 32 ? launch_gemm<32, 32, false>(tmA, tmB, p, s) : launch_gemm<64, 32, false>(tmA, tmB, p, s);
+}
+
+extern "C" int lecb_conv3x3_bf16(const void* x, const void* w, const float* bias, void* out, int B, int H, int Wd,
+                                 int Cin, int Cout, unsigned flags, void* stream) {
+  LECB_CHECK_ARG(x && w && out, "lecb_conv3x3_bf16: null pointer");
+  LECB_CHECK_ARG(B > 0 && H > 0 && Wd > 0, "lecb_conv3x3_bf16: empty problem");
+  LECB_CHECK_ARG(Cin % 32 == 0, "lecb_conv3x3_bf16: Cin=%d must be a multiple of 32", Cin);
+  LECB_CHECK_ARG(Cout % 8 == 0, "lecb_conv3x3_bf16: Cout=%d must be a multiple of 8", Cout);
+  const int BK = (Cin % 64 == 0) ? 64 : 32;
+  int BN = pick_bn(Cout);
+  if (BK == 32 && BN > 64) BN = 64;
+  const int64_t M = static_cast<int64_t>(B) * H * Wd;
+  GemmParams p{};
+  p.bias = bias;
+  p.residual = nullptr;
+  p.out = out;
+  p.row_sumsq = nullptr;
+  p.M = M;
+  p.N = Cout;
+  p.kb_per_tap = Cin / BK;
+  p.num_kb = 9 * p.kb_per_tap;
+  p.num_m_tiles = static_cast<int>((M + kTileM - 1) / kTileM);
+  p.num_n_tiles = (Cout + BN - 1) / BN;
+  p.flags = flags;
+  p.H = H;
+  p.W = Wd;
+  CUtensorMap tmA, tmB;
+  int st = encode_im2col_3x3(&tmA, x, B, H, Wd, Cin, BK, kTileM);
+  if (st) return st;
+  st = encode_tiled_2d(&tmB, w, static_cast<uint64_t>(Cout), static_cast<uint64_t>(9) * Cin, BN, BK);
+  if (st) return st;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (BK == 64) {
+    switch (BN) {
+      case 32: return launch_gemm<32, 64, true>(tmA, tmB, p, s);
+      case 64: return launch_gemm<64, 64, true>(tmA, tmB, p, s);
+      case 128: return launch_gemm<128, 64, true>(tmA, tmB, p, s);
+      default: return launch_gemm<256, 64, true>(tmA, tmB, p, s);
+    }
+  }
+  return BN == 32 ? launch_gemm<32, 32, true>(tmA, tmB, p, s) : launch_gemm<64, 32, true>(tmA, tmB, p, s);
+}

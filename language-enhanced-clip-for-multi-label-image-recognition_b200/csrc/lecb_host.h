@@ -1,0 +1,29 @@
+// Host-side plumbing shared by the C-ABI translation units: error slot, launch counter, TMA encoders.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/lecb.h"
+
+namespace lecb {
+
+int fail(int status, const char* fmt, ...);          // records the thread-local message, returns status
+void count_launch(unsigned n = 1);
+int sm_count();                                       // SMs of the current device (cached per device)
+int check_launch(const char* what);                   // cudaGetLastError -> status
+
+// cuTensorMapEncode* resolved at run time through cudaGetDriverEntryPoint (no link-time libcuda).
+// 2-D row-major bf16 matrix [rows, cols]; box = box_rows x box_cols elements; swizzle = box_cols*2 bytes.
+int encode_tiled_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                    uint32_t box_cols);
+// NHWC bf16 tensor, 3x3 / pad 1 / stride 1 im2col window; box = `pixels` x `channels`.
+int encode_im2col_3x3(CUtensorMap* out, const void* base, int B, int H, int W, int C, uint32_t channels,
+                      uint32_t pixels);
+
+}  // namespace lecb
+
+#define LECB_CHECK_ARG(cond, ...) \
+  do {                            \
+    if (!(cond)) return ::lecb::fail(LECB_ERR_ARG, __VA_ARGS__); \
+  } while (0)

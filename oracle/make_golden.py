@@ -1,0 +1,201 @@
+"""Generate tests/golden/* by RUNNING THE REFERENCE'S OWN CLASSES (build container only).
+
+    python -m oracle.make_golden            # needs /root/reference; ~2-3 min on 8 CPU threads
+
+The reference ships no tests, golden vectors or fixtures for this path, so these
+reference-generated outputs are what pins both `oracle/restatement.py` and the CUDA path.  Inputs and
+weights are regenerated from seeds (oracle/synth.py) on the consuming side; each fixture stores
+checksums of them so RNG drift is caught instead of silently comparing different inputs.
+
+Fixtures written:
+  prompt_tokens_coco80.npz   reference tokenizer output for "X X ... X <class>." (n_ctx 16) + class names
+  head_rn50_224.npz          cfg 1: DenseCLIP.forward(image, if_test=True), RN50 224² B=8, evidence off/on
+  head_rn101_448.npz         cfg 2 shape at B=2 (deviation 1: T:447 literal 1024 -> 512)
+  head_tiny.npz              toy ModifiedResNet (width 8, 64² images) for fast CPU tests
+  head_small.npz             width-64, one-block-per-stage ModifiedResNet at 128² (GPU kernel tests)
+  train_rn50.npz             DenseCLIP.forward(None, captions) B=4 + ranking/ASL losses + prompt grads
+  train_tiny.npz             same on the toy arch, B=6
+  losses.npz                 ranking_loss / ASL_loss / dualcoop_loss values + grads on [16,80]
+  map.npz                    reference numpy mAP on synthetic scores/labels
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+from . import ref_extract as RX
+from . import synth
+
+GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+TINY_CLASSES = ["person", "dog", "traffic light", "cup", "potted plant", "tv"]
+
+
+def checksum(t: torch.Tensor) -> np.ndarray:
+    t = t.detach().double().flatten()
+    w = torch.arange(1, t.numel() + 1, dtype=torch.float64) % 97 + 1
+    return np.array([t.sum().item(), (t * w).sum().item(), t.abs().max().item()], dtype=np.float64)
+
+
+def state_checksum(sd) -> np.ndarray:
+    acc = np.zeros(3)
+    for k, v in sd.items():
+        if v.dtype.is_floating_point:
+            acc += checksum(v)
+    return acc
+
+
+def build_dense_clip(arch, sd, classnames, n_ctx, use_evidence, bank, seed, csc=False):
+    ns = RX.trainer_classes(bank, arch.embed_dim)
+    clip_model = RX.build_reference_clip(arch, sd)
+    cfg = RX.make_cfg(arch.image_resolution, n_ctx=n_ctx, csc=csc, use_evidence=use_evidence)
+    model = ns["DenseCLIP"](cfg, classnames, clip_model)
+    w = arch.transformer_width
+    with torch.no_grad():
+        for name, tag in (("ctx", "pos"), ("ctx_double", "neg"), ("ctx_evidence", "evi")):
+            getattr(model.prompt_learner, name).copy_(synth.prompt_ctx(n_ctx, w, seed, tag))
+    model.copy_params()
+    for name, p in model.named_parameters():
+        if "prompt_learner" not in name:
+            p.requires_grad_(False)          # T:763-765
+    return model
+
+
+def golden_tokens(classnames):
+    clip_pkg = RX.clip_package()
+    prefix = " ".join(["X"] * 16)
+    toks = torch.cat([clip_pkg.clip.tokenize(prefix + " " + n.replace("_", " ") + ".", truncate=True) for n in classnames])
+    toks_nocls = torch.cat([clip_pkg.clip.tokenize(prefix + ".", truncate=True) for _ in classnames])
+    tiny = torch.cat([clip_pkg.clip.tokenize(" ".join(["X"] * 4) + " " + n + ".", truncate=True) for n in TINY_CLASSES])
+    np.savez_compressed(os.path.join(GOLD, "prompt_tokens_coco80.npz"),
+                        tokens=toks.numpy(), tokens_nocls=toks_nocls.numpy(), n_ctx=np.int64(16),
+                        classnames=np.array(classnames), tiny_tokens=tiny.numpy(),
+                        tiny_classnames=np.array(TINY_CLASSES), tiny_n_ctx=np.int64(4))
+    return toks, tiny
+
+
+def golden_head(tag, arch, batch, classnames, n_ctx, bank_rows, seed, evidence_modes=(False, True)):
+    sd = synth.clip_state_dict(arch, seed=0)
+    img = synth.images(batch, arch.image_resolution, seed)
+    bank = synth.caption_bank(bank_rows, arch.embed_dim, seed)
+    out = {"image_checksum": checksum(img), "state_checksum": state_checksum(sd),
+           "bank_checksum": checksum(bank.float()), "batch": np.int64(batch), "seed": np.int64(seed),
+           "bank_rows": np.int64(bank_rows), "n_ctx": np.int64(n_ctx)}
+    for ev in evidence_modes:
+        t0 = time.time()
+        model = build_dense_clip(arch, sd, classnames, n_ctx, ev, bank, seed)
+        with torch.no_grad():
+            r = model(img, if_test=True)
+        sfx = "_ev" if ev else ""
+        for name, t in zip(("logits", "logits_local", "neg_map", "pos_map", "topk_scores"), r):
+            out[name + sfx] = t.float().numpy()
+        # cached, normalised prompt features (T:421-439): handy intermediate for kernel debugging
+        for k, v in model.prompt_text_features.items():
+            out[k + sfx] = v.float().numpy()
+        print(f"[{tag}] evidence={ev}: {time.time() - t0:.1f}s  logits absmax={r[0].abs().max():.4f} "
+              f"local absmax={r[1].abs().max():.4f}", flush=True)
+    np.savez_compressed(os.path.join(GOLD, f"head_{tag}.npz"), **out)
+
+
+def golden_train(tag, arch, batch, classnames, n_ctx, seed):
+    sd = synth.clip_state_dict(arch, seed=0)
+    caps = synth.captions(batch, seed, vocab=arch.vocab_size)
+    y = synth.labels(batch, len(classnames), seed)
+    L = RX.loss_functions()
+    out = {"caption_checksum": checksum(caps.float()), "state_checksum": state_checksum(sd),
+           "label_checksum": checksum(y), "batch": np.int64(batch), "seed": np.int64(seed), "n_ctx": np.int64(n_ctx)}
+    for ev in (False, True):
+        for loss_name in ("ranking", "asl"):
+            model = build_dense_clip(arch, sd, classnames, n_ctx, ev, None, seed)
+            r = model(None, caps)
+            logits, logits_local = r[0], r[1]
+            if loss_name == "ranking":       # T:806-808
+                loss = L["ranking_loss"](logits, y, scale_=1.0, margin_=1) + \
+                       L["ranking_loss"](logits_local, y, scale_=1.0, margin_=1)
+            else:
+                loss = L["ASL_loss"](logits, y) + L["ASL_loss"](logits_local, y)
+            loss.backward()
+            sfx = ("_ev" if ev else "") + "_" + loss_name
+            out["loss" + sfx] = np.float64(loss.item())
+            pl = model.prompt_learner
+            for pname in ("ctx", "ctx_double", "ctx_evidence"):
+                g = getattr(pl, pname).grad
+                out[f"grad_{pname}" + sfx] = (torch.zeros_like(getattr(pl, pname)) if g is None else g).numpy()
+                out[f"gradnone_{pname}" + sfx] = np.bool_(g is None)
+            if loss_name == "ranking":
+                s2 = "_ev" if ev else ""
+                out["logits" + s2] = logits.detach().numpy()
+                out["logits_local" + s2] = logits_local.detach().numpy()
+                out["seq_feats" + s2] = r[2].detach().numpy()[:, :2]      # [L,2,D] slice keeps the file small
+                out["text_features" + s2] = r[3].detach().numpy()
+            print(f"[train_{tag}] evidence={ev} loss={loss_name}: {loss.item():.6f}", flush=True)
+    np.savez_compressed(os.path.join(GOLD, f"train_{tag}.npz"), **out)
+
+
+def golden_losses():
+    L = RX.loss_functions()
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn((16, 80), generator=g) * 2.0
+    y = (torch.rand((16, 80), generator=g) < 0.06).float()
+    y[0, 3] = 1.0
+    y_partial = y.clone()
+    y_partial[torch.rand((16, 80), generator=g) < 0.3] = 0.0
+    y_partial[(y == 0) & (y_partial == 0) & (torch.rand((16, 80), generator=g) < 0.5)] = -1.0
+    out = {"x": x.numpy(), "y": y.numpy(), "y_partial": y_partial.numpy()}
+    for name, fn in (("ranking_s1", lambda a: L["ranking_loss"](a, y, scale_=1.0, margin_=1)),
+                     ("ranking_s2", lambda a: L["ranking_loss"](a, y)),
+                     ("asl", lambda a: L["ASL_loss"](a, y)),
+                     ("dualcoop", lambda a: L["dualcoop_loss"](a, None, y_partial))):
+        a = x.clone().requires_grad_(True)
+        b = a * 1.0          # ranking_loss scales its argument in place (U:86): give it a non-leaf copy
+        loss = fn(b)
+        loss.backward()
+        out["loss_" + name] = np.float64(loss.item())
+        out["grad_" + name] = a.grad.numpy()
+        print(f"[losses] {name}: {loss.item():.6f}", flush=True)
+    np.savez_compressed(os.path.join(GOLD, "losses.npz"), **out)
+
+
+def golden_map():
+    ref_map = RX.mAP_function()
+    g = torch.Generator().manual_seed(5)
+    scores = torch.randn((64, 80), generator=g).numpy()
+    targs = (torch.rand((64, 80), generator=g) < 0.1).float().numpy()
+    targs[0, :] = 1.0          # every class has at least one positive
+    np.savez_compressed(os.path.join(GOLD, "map.npz"), scores=scores, targets=targs,
+                        mAP=np.float64(ref_map(targs, scores)))
+    print("[map]", ref_map(targs, scores))
+
+
+def main(which=None):
+    assert RX.available(), "reference tree not found"
+    os.makedirs(GOLD, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_num_threads(os.cpu_count())
+    classnames = RX.coco_classnames()
+    assert len(classnames) == 80
+    steps = {
+        "tokens": lambda: golden_tokens(classnames),
+        "losses": golden_losses,
+        "map": golden_map,
+        "head_tiny": lambda: golden_head("tiny", synth.tiny_rn(), 3, TINY_CLASSES, 4, 64, 1240),
+        "train_tiny": lambda: golden_train("tiny", synth.tiny_rn(), 6, TINY_CLASSES, 4, 1241),
+        "head_small": lambda: golden_head("small", synth.small_rn(), 4, classnames, 16, 512, 1242),
+        "head_rn50": lambda: golden_head("rn50_224", synth.RN50(224), 8, classnames, 16, 5000, 1235),
+        "head_rn101": lambda: golden_head("rn101_448", synth.RN101(448), 2, classnames, 16, 2000, 1236, (True,)),
+        "train_rn50": lambda: golden_train("rn50", synth.RN50(224), 4, classnames, 16, 1238),
+    }
+    for name, fn in steps.items():
+        if which and name not in which:
+            continue
+        t0 = time.time()
+        fn()
+        print(f"== {name} done in {time.time() - t0:.1f}s", flush=True)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:] or None)

@@ -1,0 +1,88 @@
+"""tcgen05 GEMM / implicit-GEMM conv parity on the B200 (through the C ABI).
+
+Reference: fp32 torch matmul / conv2d on the same bf16-rounded operands; the kernel accumulates in
+fp32 so the only difference is summation order and the final bf16 rounding of the output:
+tolerance = 2^-8 relative to the output scale (one bf16 ulp) + small absolute slack."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).cuda()
+
+
+def _check(got, want, what):
+    got = got.float()
+    scale = want.abs().max().item() + 1e-6
+    err = (got - want).abs().max().item()
+    assert err <= scale * (2.0 ** -7), f"{what}: max err {err:.4g} vs scale {scale:.4g}"
+
+
+GEMM_SHAPES = [
+    # (M, N, K) : tile-aligned, ragged M, small N, N tail (240), K = 32-multiple, multi-wave
+    (128, 64, 64), (256, 128, 128), (200, 256, 512), (1000, 512, 2048), (333, 240, 512),
+    (128, 32, 96), (4096, 2048, 256), (777, 1024, 1024), (50176, 64, 256), (19000, 256, 64), (64, 8, 32),
+]
+
+
+@pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
+def test_gemm_plain(m, n, k):
+    from lecb200 import ops
+    a = _rand((m, k), 1).bfloat16()
+    w = _rand((n, k), 2, k ** -0.5).bfloat16()
+    out = ops.gemm(a, w)
+    torch.cuda.synchronize()
+    _check(out, a.float() @ w.float().t(), f"gemm {m}x{n}x{k}")
+
+
+@pytest.mark.parametrize("m,n,k", [(300, 256, 512), (1111, 64, 64), (515, 2048, 2048)])
+def test_gemm_epilogues(m, n, k):
+    from lecb200 import ops
+    a = _rand((m, k), 3).bfloat16()
+    w = _rand((n, k), 4, k ** -0.5).bfloat16()
+    bias = _rand((n,), 5)
+    res = _rand((m, n), 6).bfloat16()
+    base = a.float() @ w.float().t() + bias
+    _check(ops.gemm(a, w, bias), base, "bias")
+    _check(ops.gemm(a, w, bias, relu=True), base.relu(), "bias+relu")
+    _check(ops.gemm(a, w, bias, residual=res, relu=True), (base + res.float()).relu(), "bias+res+relu")
+    _check(ops.gemm(a, w, bias, quick_gelu=True), base * torch.sigmoid(1.702 * base), "quickgelu")
+    f32 = ops.gemm(a, w, bias, out_f32=True)
+    assert f32.dtype == torch.float32
+    assert (f32 - base).abs().max().item() <= 1e-3 * (base.abs().max().item() + 1)
+    ssq = torch.zeros((m,), device="cuda")
+    out = ops.gemm(a, w, bias, row_sumsq=ssq)
+    torch.cuda.synchronize()
+    want = out.float().pow(2).sum(-1)
+    assert ((ssq - want).abs() / (want + 1e-6)).max().item() < 1e-4
+
+
+CONV_SHAPES = [
+    # (B, H, W, Cin, Cout)
+    (2, 8, 8, 64, 64), (1, 14, 14, 512, 512), (3, 28, 28, 256, 256), (2, 56, 56, 128, 128),
+    (2, 32, 32, 32, 32), (1, 64, 64, 32, 64), (5, 7, 7, 512, 512), (2, 112, 112, 64, 64), (1, 5, 9, 64, 128),
+]
+
+
+@pytest.mark.parametrize("b,h,w,cin,cout", CONV_SHAPES)
+def test_conv3x3(b, h, w, cin, cout):
+    from lecb200 import ops
+    x = _rand((b, h, w, cin), 7).bfloat16()
+    wt = _rand((cout, 3, 3, cin), 8, (9 * cin) ** -0.5).bfloat16()
+    bias = _rand((cout,), 9, 0.1)
+    out = ops.conv3x3(x, wt, bias, relu=True)
+    torch.cuda.synchronize()
+    want = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), bias, padding=1)
+    want = want.relu().permute(0, 2, 3, 1)
+    _check(out, want, f"conv {b}x{h}x{w}x{cin}->{cout}")
+
+
+def test_gemm_rejects_bad_args():
+    from lecb200 import LecbError, ops
+    a = torch.zeros((16, 40), device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros((8, 40), device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(LecbError):
+        ops.gemm(a, w)          # K not a multiple of 32
