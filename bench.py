@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — headline metric of the dual-prompt scoring path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): multi-label images/sec, 80 classes, 448x448.  Workload at every N = BASELINE
+configs[1] per GPU: CLIP RN101 dual-prompt inference (pos/neg/evidence prompts, 80 COCO classes), synthetic
+448x448 images, batch 256 per GPU, bf16 operands / fp32 accumulation, random-init weights (weak scaling:
+per-GPU batch fixed, the packed logits all-gathered over NCCL inside the timed region).
+
+One JSON line on rank 0:
+  value       img/s with the input batch resident in HBM (CUDA events, max over ranks)
+  e2e         img/s through the public API with pinned HOST images: H2D copy of every step's input and D2H
+              read of its logits inside the timed region (double-buffered copy stream)
+  roofline    dominant kernel = the tcgen05 GEMM / implicit-GEMM conv kernel: algorithmic FLOPs per step /
+              its summed CUDA-event duration, vs the measured sustained bf16 peak
+  cpu_baseline / --impl reference: the CPU restatement of the reference path (oracle/restatement.py, kind
+              "port": /root/reference does not travel to the GPU box) on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOAD = "CLIP RN101 dual-prompt (pos/neg/evidence) inference, 80 classes, 448x448 synthetic images, batch 256 per GPU"
+METRIC = "multi_label_images_per_sec_80cls_448px"
+UNIT = "img/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_burst": p["bf16_tflops"], "bf16_sustained": p["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def load_tokens():
+    tk = np.load(os.path.join(ROOT, "tests", "golden", "prompt_tokens_coco80.npz"), allow_pickle=False)
+    return torch.from_numpy(tk["tokens"]), int(tk["n_ctx"]), [str(s) for s in tk["classnames"]]
+
+
+class Cfg(dict):
+    __getattr__ = dict.__getitem__
+
+
+def make_cfg(res, n_ctx, use_evidence):
+    return Cfg(TRAINER=Cfg(Caption=Cfg(N_CTX=n_ctx, CTX_INIT="", CSC=False, CLASS_TOKEN_POSITION="end",
+                                       use_evidence=use_evidence, PREC="fp32")),
+               INPUT=Cfg(SIZE=(res, res)),
+               TRAIN=Cfg(IF_LEARN_SCALE=False, IF_LEARN_spatial_SCALE=False, spatial_SCALE_text=50.0,
+                         spatial_SCALE_image=50.0, ema=False, momentum=0.995, LOSSFUNC="double_ranking"))
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.tmp = index, None, None
+
+    def start(self):
+        try:
+            self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.tmp.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            os.unlink(self.tmp.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=float(max(power)))
+        return out
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle restatement of the reference image path (text features cached like T:421-439)
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_rate(arch, steps, warmup, budget_s, threads=None):
+    from oracle import restatement as R
+    from oracle import synth
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    sd = synth.clip_state_dict(arch, 0)
+    toks, n_ctx, _ = load_tokens()
+    w = arch.transformer_width
+    # text features: computed once, untimed — the reference caches them after the first call (T:421-439);
+    # random unit rows stand in for them (their values do not change the timed image path's cost)
+    g = torch.Generator().manual_seed(0)
+    tfeat = [torch.nn.functional.normalize(torch.randn((toks.shape[0], arch.embed_dim), generator=g), dim=-1) for _ in range(3)]
+    heads = arch.vision_width * 32 // 64
+
+    def step(img):
+        with torch.no_grad():
+            feat = R.rn_trunk(sd, img, arch.vision_layers)
+            return R.head_test(R.attnpool_global(sd, feat, heads), R.local_features(sd, feat), tfeat[0], tfeat[1], tfeat[2])
+
+    probe = synth.images(1, arch.image_resolution, 99)
+    step(probe)
+    t0 = time.perf_counter()
+    step(probe)
+    t_img = time.perf_counter() - t0
+    total_steps = steps + warmup
+    per_step = max(1, min(8, int(budget_s / max(t_img, 1e-3) / max(total_steps, 1))))
+    imgs = synth.images(per_step, arch.image_resolution, 100)
+    for _ in range(warmup):
+        step(imgs)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step(imgs)
+    dt = time.perf_counter() - t0
+    return {"value": per_step * steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{steps} steps x {per_step} synthetic 448x448 images through oracle/restatement.py "
+                      f"(RN101 trunk + attnpool + dual-prompt head, fp32, torch CPU, prompt features cached)",
+            "ms_per_step": 1e3 * dt / steps, "images_per_step": per_step}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from oracle import synth
+    arch = synth.RN101(448)
+    r = cpu_reference_rate(arch, args.steps, args.warmup, budget_s=150.0)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "images_per_step": r["images_per_step"], "device": "host CPU"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# product arm
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="lecb200", choices=["lecb200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step (configs[1]: 256)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-entry-point timing table (JSON) here")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import lecb200
+    from lecb200 import synth
+    from lecb200.clip_model import CLIPParams
+    from lecb200.dense_clip import DenseCLIPB200
+    from lecb200.dist import all_gather_logits, pack_logits
+    from lecb200.prof import KernelTimer
+
+    arch = synth.RN101(448)
+    toks, n_ctx, names = load_tokens()
+    clip = CLIPParams(*arch.ctor_args())
+    clip.load_state_dict(synth.clip_state_dict(arch, 0), strict=False)
+    clip = clip.float().to(dev).eval()
+    model = DenseCLIPB200(make_cfg(448, n_ctx, True), names, clip, tokenized_prompts=toks).to(dev)
+    B = args.batch
+    K = len(names)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- HBM-resident throughput ----------------
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    images = torch.randn((B, 3, 448, 448), device=dev, generator=gen)        # 616 MB > L2: no flush needed
+
+    def step(img):
+        out = model(img, if_test=True)
+        return all_gather_logits(out[0], out[1])
+
+    for _ in range(args.warmup):
+        step(images)
+    barrier()
+    launches0 = lecb200.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res = step(images)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    launches = (lecb200.launch_count() - launches0) // args.steps
+    value = world * B / (ms * 1e-3)
+    assert torch.isfinite(res[0]).all() and torch.isfinite(res[1]).all()
+
+    # ---------------- end to end: pinned host images -> logits on the host ----------------
+    host_in = [torch.empty((B, 3, 448, 448), dtype=torch.float32).pin_memory() for _ in range(2)]
+    for h in host_in:
+        h.normal_()
+    dev_in = [torch.empty((B, 3, 448, 448), device=dev) for _ in range(2)]
+    host_out = torch.empty((B * world, 2 * K), dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_loop(n):
+        main_stream = torch.cuda.current_stream()
+        with torch.cuda.stream(copy_stream):
+            dev_in[0].copy_(host_in[0], non_blocking=True)
+            ready[0].record(copy_stream)
+        for i in range(n):
+            cur, nxt = i % 2, (i + 1) % 2
+            if i + 1 < n:
+                with torch.cuda.stream(copy_stream):
+                    if i >= 1:
+                        copy_stream.wait_event(consumed[nxt])
+                    dev_in[nxt].copy_(host_in[nxt], non_blocking=True)
+                    ready[nxt].record(copy_stream)
+            main_stream.wait_event(ready[cur])
+            lg, ll = step(dev_in[cur])
+            consumed[cur].record(main_stream)
+            host_out.copy_(pack_logits(lg, ll), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_loop(args.warmup)
+    barrier()
+    e0.record()
+    e2e_loop(args.steps)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    e2e = {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": world * B * 3 * 448 * 448 * 4,
+           "d2h_bytes_per_step": world * B * 2 * K * 4, "ms_per_step": ms_e2e}
+
+    # ---------------- roofline: per-entry-point CUDA events (instrumented replay, not the timed region) ----
+    roofline, table = None, None
+    if rank == 0:
+        pk = peaks()
+        prof_steps = 2
+        with KernelTimer() as kt:
+            for _ in range(prof_steps):
+                model(images, if_test=True)
+        table = kt.summary(prof_steps)
+        gemm_ms = sum(table[n]["ms"] for n in ("lecb_gemm_bf16", "lecb_conv3x3_bf16") if n in table)
+        gemm_fl = sum(table[n]["flops"] for n in ("lecb_gemm_bf16", "lecb_conv3x3_bf16") if n in table)
+        gemm_n = sum(table[n]["launches"] for n in ("lecb_gemm_bf16", "lecb_conv3x3_bf16") if n in table)
+        total_ms = sum(d["ms"] for d in table.values())
+        achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12
+        roofline = {"kernel": "lecb::gemm_kernel<BN,BK,conv> (tcgen05 GEMM + TMA-im2col conv)", "bound": "tensor",
+                    "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
+                    "traffic": None, "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
+                    "launches_per_step": gemm_n, "avg_launch_us": 1e3 * gemm_ms / max(gemm_n, 1),
+                    "share_of_step": gemm_ms / total_ms, "algorithmic_gflop_per_step": gemm_fl / 1e9}
+        if args.profile_out:
+            with open(args.profile_out, "w") as f:
+                json.dump({"batch": B, "ms_per_step_events_sum": total_ms, "table": table}, f, indent=1)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_rate(arch, steps=2, warmup=1, budget_s=20.0)
+        cpu_baseline = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "global_batch": world * B, "per_gpu_batch": B, "classes": K,
+                           "parallelism": f"dp{world}", "l2_policy": "input batch (616 MB/GPU) larger than L2, no flush",
+                           "collective": "all_gather_into_tensor of packed [B,2K] fp32 logits per step" if world > 1 else "none"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "cpu_baseline": cpu_baseline}
+        if table is not None:
+            line["kernel_ms_per_step"] = {k: round(v["ms"], 4) for k, v in sorted(table.items(), key=lambda kv: -kv[1]["ms"])}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -38,6 +38,8 @@ enum lecb_status {
 #define LECB_EPI_RELU 1u        /* y = max(y, 0) after bias (+ residual)                     */
 #define LECB_EPI_QUICKGELU 2u   /* y = y * sigmoid(1.702 y)   (M:202-204)                    */
 #define LECB_EPI_OUT_F32 4u     /* store fp32 instead of bf16                                 */
+#define LECB_EPI_RES_F32 8u     /* `residual` is fp32 [M,N] instead of bf16                   */
+#define LECB_GEMM_F16_OPERANDS 16u /* A and W hold IEEE fp16 instead of bf16 (retrieval, T:445)  */
 
 int lecb_abi_version(void);
 const char* lecb_last_error(void);
@@ -61,6 +63,67 @@ int lecb_gemm_bf16(const void* A, const void* W, const float* bias, const void* 
  * conv2/conv3).  Requirements: Cin % 32 == 0, Cout % 8 == 0. */
 int lecb_conv3x3_bf16(const void* x, const void* w, const float* bias, void* out, int B, int H, int Wd,
                       int Cin, int Cout, unsigned flags, void* stream);
+
+/* ---- stem conv1: 3x3, stride 2, pad 1, 3 -> Cout channels, folded BN + ReLU (M:144-145,174-175) ----
+ * x: NCHW fp32 [B,3,H,W] (the reference's input layout, T:401); w: fp32 [27][Cout] with row index
+ * ci*9+ky*3+kx; out: NHWC bf16 [B,H/2,W/2,Cout].  Cout in {8, 32, 48}. */
+int lecb_stem_conv1(const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int Cout,
+                    void* stream);
+
+/* ---- 2x2 average pool, NHWC bf16 (M:150 stem avgpool, M:23,35 anti-aliased stride) ---- */
+int lecb_avgpool2x2(const void* x, void* out, int B, int H, int W, int C, void* stream);
+
+/* ---- mean over the P tokens of each image: x bf16 [B,P,C] -> bf16 and/or fp32 [B,C] (M:92) ---- */
+int lecb_token_mean(const void* x, void* out_bf16, float* out_f32, int B, int P, int C, void* stream);
+
+/* ---- row L2 normalisation y = x / ||x||, no epsilon (T:441-442, T:431-436, T:485-488) ---- */
+int lecb_l2norm_rows(const void* x, void* y, int64_t rows, int D, int in_is_bf16, int out_is_bf16, void* stream);
+
+/* ---- LayerNorm forward, fp32 statistics (M:193-199); x fp32 [rows,D] -> bf16 and/or fp32 y;
+ * optional per-row mean / rstd outputs for the backward ---- */
+int lecb_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
+                       float* mean, float* rstd, int64_t rows, int D, float eps, void* stream);
+
+/* ---- AttentionPool2d, if_pos=False, query = mean token only (M:89-127 via T:413) ----
+ * q fp32 [B,C] = q_proj(mean token) (unscaled); kmat, vmat bf16 [B*P,C] = k_proj / v_proj of the patch
+ * tokens; out bf16 [B,C] = attention output of token 0 before c_proj.  Head dim 64, heads % 8 == 0. */
+int lecb_attnpool_query0(const float* q, const void* kmat, const void* vmat, void* out, int B, int P, int C,
+                         int heads, void* stream);
+
+/* ---- causal multi-head self-attention forward (M:221-223 with the mask of M:364-370) ----
+ * qkv bf16 [N*L, 3W] (q | k | v), out bf16 [N*L, W]; head dim 64; L <= 128. */
+int lecb_causal_attn_fwd(const void* qkv, void* out, int N, int L, int W, int heads, void* stream);
+
+/* ---- dual-prompt head aggregation (T:456-470 test, T:496-514 train) ----
+ * dots fp32 [B*P, ldn]: raw dot products of the UN-normalised local features with the unit prompt
+ * features, columns [0,K) = positive, [K,2K) = negative, [2K,3K) = evidence (n_txt == 3);
+ * row_sumsq fp32 [B*P] (or NULL if rows are already unit) supplies 1/||feature||;
+ * row_mask u8 [B*P] (or NULL): 1 = padded caption token (T:491), skipped.
+ * -> logits_local fp32 [B,K]; optional neg_map / pos_map fp32 [P,B,K] (3rd/4th return values, T:472;
+ * neg_map is post winner-take-all when evidence is used, as in the reference). */
+int lecb_head_aggregate(const float* dots, int ldn, const float* row_sumsq, const uint8_t* row_mask,
+                        float* logits_local, float* neg_map, float* pos_map, int B, int P, int K, int n_txt,
+                        float logit_scale, float spatial_scale, void* stream);
+
+/* ---- global logits (T:448,453-455): out[b,k] = scale * <x_b, tpos_k>, x = g_unit or (g_unit+g_add)/2 ---- */
+int lecb_global_logits(const float* g_unit, const float* g_add, const float* tpos, float* out, int B, int D, int K,
+                       float scale, void* stream);
+
+/* ---- asymmetric loss forward + backward (U:126-173): loss (scalar, device) and dloss/dlogits ----
+ * partial != 0: -sum/B (dualcoop_loss, U:175-181); else -mean (ASL_loss, U:184-190). grad may be NULL. */
+int lecb_asl_fwd_bwd(const float* logits, const float* targets, float* grad, float* loss, int64_t B, int K,
+                     float gamma_neg, float gamma_pos, float clip, float eps, float thresh_pos, float thresh_neg,
+                     int partial, void* stream);
+
+/* ---- pairwise ranking hinge forward + backward (U:85-93), logits are NOT modified ---- */
+int lecb_ranking_fwd_bwd(const float* logits, const float* targets, float* grad, float* loss, int B, int K,
+                         float scale, float margin, void* stream);
+
+/* ---- caption retrieval helpers (T:444-448); the similarity matrix itself is lecb_gemm_bf16 with
+ * LECB_GEMM_F16_OPERANDS run twice (hi, lo halves of the query) against the fp16 bank ---- */
+int lecb_split_f16(const float* x, void* hi, void* lo, int64_t n, void* stream);   /* x = hi + lo, fp16 each */
+int lecb_topk10(const float* sim, int64_t ld, int B, int N, float* out_val, int* out_idx, void* stream);
+int lecb_gather_mean10(const void* bank, int bank_is_f16, const int* idx, float* out, int B, int D, void* stream);
 
 #ifdef __cplusplus
 }

@@ -21,9 +21,27 @@ SIGNATURES = {
                                c_uint, c_void_p]),
     "lecb_conv3x3_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_uint, c_void_p]),
+    "lecb_stem_conv1": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "lecb_avgpool2x2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "lecb_token_mean": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "lecb_l2norm_rows": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_void_p]),
+    "lecb_layernorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64,
+                                   c_int, c_float, c_void_p]),
+    "lecb_attnpool_query0": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "lecb_causal_attn_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "lecb_head_aggregate": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                    c_int, c_int, c_float, c_float, c_void_p]),
+    "lecb_global_logits": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p]),
+    "lecb_asl_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_float, c_float, c_float,
+                                 c_float, c_float, c_float, c_int, c_void_p]),
+    "lecb_ranking_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float,
+                                     c_void_p]),
+    "lecb_split_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
+    "lecb_topk10": (c_int, [c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "lecb_gather_mean10": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
 }
 
-EPI_RELU, EPI_QUICKGELU, EPI_OUT_F32 = 1, 2, 4
+EPI_RELU, EPI_QUICKGELU, EPI_OUT_F32, EPI_RES_F32, GEMM_F16_OPERANDS = 1, 2, 4, 8, 16
 
 
 class LecbError(RuntimeError):

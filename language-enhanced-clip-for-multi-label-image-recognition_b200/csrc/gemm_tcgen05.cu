@@ -130,7 +130,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp == 5) {
     // ------------------------------- MMA issuer ---------------------------------
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(BN, true);
+      const uint32_t idesc = make_idesc_f16(BN, (p.flags & LECB_GEMM_F16_OPERANDS) == 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -168,6 +168,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const bool relu = p.flags & LECB_EPI_RELU;
     const bool gelu = p.flags & LECB_EPI_QUICKGELU;
     const bool out_f32 = p.flags & LECB_EPI_OUT_F32;
+    const bool res_f32 = p.flags & LECB_EPI_RES_F32;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.num_n_tiles;
       const int n_blk = tile - m_blk * p.num_n_tiles;
@@ -195,7 +196,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         }
-        if (p.residual != nullptr && row_ok) {
+        if (p.residual != nullptr && row_ok && res_f32) {
+          const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + row * p.N + n0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (n0 + q * 4 < p.N) {
+              const float4 f = __ldg(rp + q);
+              v[q * 4 + 0] += f.x; v[q * 4 + 1] += f.y; v[q * 4 + 2] += f.z; v[q * 4 + 3] += f.w;
+            }
+          }
+        } else if (p.residual != nullptr && row_ok) {
           const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row * p.N + n0);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {

@@ -1,0 +1,145 @@
+// Caption retrieval (T:444-448): sim = g_unit · bankᵀ, top-10 per image, mean of the selected bank rows.
+// The similarity GEMM runs on tcgen05 through lecb_gemm_f16 with the fp32 query split into an exact
+// fp16 (hi, lo) pair, so the ranking matches the reference's fp32 matmul against the fp16 bank; these
+// kernels do the split, the per-row top-k selection and the gather-mean.
+#include "lecb_common.cuh"
+#include "lecb_host.h"
+
+namespace lecb {
+
+__global__ void __launch_bounds__(256)
+split_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  const __half h = __float2half_rn(v);
+  hi[i] = h;
+  lo[i] = __float2half_rn(v - __half2float(h));
+}
+
+constexpr int kTopK = 10;
+
+__device__ __forceinline__ void topk_insert(float (&val)[kTopK], int (&idx)[kTopK], float v, int i) {
+  if (v <= val[kTopK - 1]) return;
+  int pos = kTopK - 1;
+#pragma unroll
+  for (int j = kTopK - 2; j >= 0; --j) {
+    if (v > val[j]) {
+      val[j + 1] = val[j];
+      idx[j + 1] = idx[j];
+      pos = j;
+    }
+  }
+  val[pos] = v;
+  idx[pos] = i;
+}
+
+// One CTA per query row: per-thread sorted top-10 over a strided slice, then 10 rounds of block arg-max.
+__global__ void __launch_bounds__(256)
+topk10_kernel(const float* __restrict__ sim, int64_t ld, int N, float* __restrict__ out_val,
+              int* __restrict__ out_idx) {
+  __shared__ float s_val[256 * kTopK];
+  __shared__ int s_idx[256 * kTopK];
+  __shared__ float r_val[8];
+  __shared__ int r_slot[8];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const float* row = sim + static_cast<int64_t>(b) * ld;
+  float val[kTopK];
+  int idx[kTopK];
+#pragma unroll
+  for (int j = 0; j < kTopK; ++j) {
+    val[j] = -INFINITY;
+    idx[j] = -1;
+  }
+  for (int i = t; i < N; i += 256) topk_insert(val, idx, __ldg(row + i), i);
+#pragma unroll
+  for (int j = 0; j < kTopK; ++j) {
+    s_val[t * kTopK + j] = val[j];
+    s_idx[t * kTopK + j] = idx[j];
+  }
+  __syncthreads();
+  int head = 0;     // each thread's list is sorted: only its current head can be the global maximum
+  for (int r = 0; r < kTopK; ++r) {
+    float v = head < kTopK ? s_val[t * kTopK + head] : -INFINITY;
+    int slot = t;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int os = __shfl_xor_sync(0xffffffffu, slot, o);
+      if (ov > v || (ov == v && os < slot)) {
+        v = ov;
+        slot = os;
+      }
+    }
+    if ((t & 31) == 0) {
+      r_val[t >> 5] = v;
+      r_slot[t >> 5] = slot;
+    }
+    __syncthreads();
+    float bv = r_val[0];
+    int bs = r_slot[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      if (r_val[w] > bv || (r_val[w] == bv && r_slot[w] < bs)) {
+        bv = r_val[w];
+        bs = r_slot[w];
+      }
+    }
+    if (t == bs) {
+      out_val[b * kTopK + r] = bv;
+      out_idx[b * kTopK + r] = s_idx[t * kTopK + head];
+      ++head;
+    }
+    __syncthreads();
+  }
+}
+
+// g_add[b,:] = mean of the 10 selected bank rows, rounded to the bank's dtype like the reference's
+// `caption_text_feats[idx].view(-1, topk, D).mean(1)` on an fp16 tensor.
+template <typename TBank>
+__global__ void __launch_bounds__(256)
+gather_mean_kernel(const TBank* __restrict__ bank, const int* __restrict__ idx, float* __restrict__ out, int D) {
+  const int b = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < kTopK; ++j) {
+      const int r = idx[b * kTopK + j];
+      if constexpr (sizeof(TBank) == 2) s += __half2float(bank[static_cast<int64_t>(r) * D + d]);
+      else s += bank[static_cast<int64_t>(r) * D + d];
+    }
+    s *= 1.0f / kTopK;
+    if constexpr (sizeof(TBank) == 2) s = __half2float(__float2half_rn(s));
+    out[static_cast<int64_t>(b) * D + d] = s;
+  }
+}
+
+}  // namespace lecb
+
+using namespace lecb;
+
+extern "C" int lecb_split_f16(const float* x, void* hi, void* lo, int64_t n, void* stream) {
+  LECB_CHECK_ARG(x && hi && lo && n > 0, "lecb_split_f16: bad argument");
+  split_f16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__half*>(hi), static_cast<__half*>(lo), n);
+  count_launch();
+  return check_launch("split_f16_kernel");
+}
+
+extern "C" int lecb_topk10(const float* sim, int64_t ld, int B, int N, float* out_val, int* out_idx, void* stream) {
+  LECB_CHECK_ARG(sim && out_val && out_idx, "lecb_topk10: null pointer");
+  LECB_CHECK_ARG(B > 0 && N >= kTopK && ld >= N, "lecb_topk10: need N >= 10 and ld >= N (N=%d)", N);
+  topk10_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(sim, ld, N, out_val, out_idx);
+  count_launch();
+  return check_launch("topk10_kernel");
+}
+
+extern "C" int lecb_gather_mean10(const void* bank, int bank_is_f16, const int* idx, float* out, int B, int D,
+                                  void* stream) {
+  LECB_CHECK_ARG(bank && idx && out && B > 0 && D > 0, "lecb_gather_mean10: bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (bank_is_f16) gather_mean_kernel<__half><<<B, 256, 0, s>>>(static_cast<const __half*>(bank), idx, out, D);
+  else gather_mean_kernel<float><<<B, 256, 0, s>>>(static_cast<const float*>(bank), idx, out, D);
+  count_launch();
+  return check_launch("gather_mean_kernel");
+}

@@ -1,0 +1,64 @@
+"""Multi-GPU plumbing for the scoring path: one process per GPU, torch.distributed (NCCL over NVLink).
+
+Inference shards by image batch: every rank scores its own contiguous slice with replicated frozen
+weights, then ONE all-gather of a packed [B_local, 2K] fp32 tile (global logits | local logits)
+assembles the global result — the only exchange on the path (the reference itself never
+shards inference, §2a).  Prompt tuning shards by caption batch and all-reduces (averages) one flat
+prompt-gradient buffer, the semantics of the reference's DDP wrapper (T:786-787)."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world: int):
+    """Contiguous, balanced slice [lo, hi) of n_items for `rank` (first n_items % world ranks get one more)."""
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def pack_logits(logits: torch.Tensor, logits_local: torch.Tensor) -> torch.Tensor:
+    return torch.cat([logits, logits_local], dim=1).contiguous()
+
+
+def unpack_logits(packed: torch.Tensor):
+    k = packed.shape[1] // 2
+    return packed[:, :k], packed[:, k:]
+
+
+def all_gather_logits(logits, logits_local, group=None):
+    """-> (logits [G*B,K], logits_local [G*B,K]) in rank order; equal B on every rank."""
+    packed = pack_logits(logits, logits_local)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return unpack_logits(packed)
+    world = dist.get_world_size(group)
+    out = torch.empty((world * packed.shape[0], packed.shape[1]), device=packed.device, dtype=packed.dtype)
+    dist.all_gather_into_tensor(out, packed, group=group)
+    return unpack_logits(out)
+
+
+def flat_grads(params):
+    """One flat fp32 buffer holding every prompt-parameter gradient (zeros where a grad is None: the
+    reference needs find_unused_parameters=True for ctx_evidence / the scalars)."""
+    chunks = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in params]
+    return torch.cat(chunks)
+
+
+def allreduce_mean_grads(params, group=None):
+    """DDP semantics (T:787): average the prompt gradients over ranks with a single all-reduce."""
+    params = [p for p in params if p.requires_grad]
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    flat = flat_grads(params)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat /= dist.get_world_size(group)
+    off = 0
+    for p in params:
+        n = p.numel()
+        g = flat[off:off + n].view_as(p).to(p.dtype)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        off += n

@@ -1,0 +1,143 @@
+"""B200 execution engines for the two frozen CLIP towers.
+
+`VisualRN`  — CLIP ModifiedResNet trunk + dense/global pooling (reference: T:385-413, M:10-190).
+`TextTower` — CLIP text transformer (reference: T:72-101, M:207-239).
+
+Data layout in HBM: activations are NHWC bf16, i.e. row-major [B*H*W, C] matrices, so every 1x1
+convolution / linear layer is one `lecb_gemm_bf16` launch and every 3x3 convolution one
+`lecb_conv3x3_bf16` launch (TMA im2col) with eval-BatchNorm folded into the bf16 weights and an fp32
+bias, ReLU / residual-add fused in the epilogue.  Weights are packed once at construction.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+def _fold_bn(sd, conv_key, bn_prefix, eps=1e-5):
+    """eval BatchNorm folded into the preceding conv (BN is always in eval mode: SURVEY §3.3)."""
+    w = sd[conv_key].float()
+    scale = sd[bn_prefix + ".weight"].float() / torch.sqrt(sd[bn_prefix + ".running_var"].float() + eps)
+    bias = sd[bn_prefix + ".bias"].float() - sd[bn_prefix + ".running_mean"].float() * scale
+    return w * scale.view(-1, 1, 1, 1), bias.contiguous()
+
+
+def _w1x1(w):
+    return w.reshape(w.shape[0], w.shape[1]).to(torch.bfloat16).contiguous()
+
+
+def _w3x3(w):
+    return w.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()          # [Cout,3,3,Cin]
+
+
+class VisualRN:
+    def __init__(self, sd, layers, width, heads, embed_dim, device):
+        sd = {k: v.detach().to(device) for k, v in sd.items() if k.startswith("visual.")}
+        self.layers, self.width, self.heads, self.embed_dim, self.device = tuple(layers), width, heads, embed_dim, device
+        w, b = _fold_bn(sd, "visual.conv1.weight", "visual.bn1")
+        self.stem1 = (w.permute(1, 2, 3, 0).reshape(27, -1).contiguous(), b)          # fp32 [27,Cout]
+        w, b = _fold_bn(sd, "visual.conv2.weight", "visual.bn2")
+        self.stem2 = (_w3x3(w), b)
+        w, b = _fold_bn(sd, "visual.conv3.weight", "visual.bn3")
+        self.stem3 = (_w3x3(w), b)
+        self.blocks = []
+        for li, nblk in enumerate(self.layers, start=1):
+            for bi in range(nblk):
+                p = f"visual.layer{li}.{bi}"
+                blk = {"stride": 2 if (li > 1 and bi == 0) else 1}
+                w, b = _fold_bn(sd, p + ".conv1.weight", p + ".bn1")
+                blk["c1"] = (_w1x1(w), b)
+                w, b = _fold_bn(sd, p + ".conv2.weight", p + ".bn2")
+                blk["c2"] = (_w3x3(w), b)
+                w, b = _fold_bn(sd, p + ".conv3.weight", p + ".bn3")
+                blk["c3"] = (_w1x1(w), b)
+                if (p + ".downsample.0.weight") in sd:
+                    w, b = _fold_bn(sd, p + ".downsample.0.weight", p + ".downsample.1")
+                    blk["ds"] = (_w1x1(w), b)
+                self.blocks.append(blk)
+        ap = "visual.attnpool."
+        self.proj = {n: (sd[ap + n + ".weight"].to(torch.bfloat16).contiguous(), sd[ap + n + ".bias"].float().contiguous())
+                     for n in ("q_proj", "k_proj", "v_proj", "c_proj")}
+
+    # ---- T:385-399 encode_image ----
+    def trunk(self, image):
+        """image fp32 NCHW [B,3,H,W] (cuda) -> layer4 features, NHWC bf16 [B,H/32,W/32,Cv]."""
+        x = ops.stem_conv1(image.contiguous(), *self.stem1)
+        x = ops.conv3x3(x, *self.stem2)
+        x = ops.conv3x3(x, *self.stem3)
+        x = ops.avgpool2x2(x)
+        for blk in self.blocks:
+            x = self._bottleneck(x, blk)
+        return x
+
+    @staticmethod
+    def _bottleneck(x, blk):
+        b, h, w, c = x.shape
+        y = ops.gemm(x.view(-1, c), *blk["c1"], relu=True)
+        y = ops.conv3x3(y.view(b, h, w, -1), *blk["c2"])
+        idn = x
+        if blk["stride"] > 1:
+            y = ops.avgpool2x2(y)
+            idn = ops.avgpool2x2(x)
+            h, w = h // 2, w // 2
+        if "ds" in blk:
+            idn = ops.gemm(idn.view(-1, c), *blk["ds"])
+        out = ops.gemm(y.view(b * h * w, -1), *blk["c3"], residual=idn.view(b * h * w, -1), relu=True)
+        return out.view(b, h, w, -1)
+
+    # ---- T:405-413: per-patch value->output path + single-query attention pool ----
+    def pooled(self, feat):
+        """feat NHWC bf16 [B,h,w,Cv] -> (local bf16 [B*P,D] un-normalised, row_sumsq fp32 [B*P], g fp32 [B,D])."""
+        b, h, w, c = feat.shape
+        p = h * w
+        x2 = feat.view(b * p, c)
+        v = ops.gemm(x2, *self.proj["v_proj"])                         # shared by local path and attnpool values
+        ssq = torch.zeros((b * p,), device=feat.device, dtype=torch.float32)
+        local = ops.gemm(v, *self.proj["c_proj"], row_sumsq=ssq)
+        k = ops.gemm(x2, *self.proj["k_proj"])
+        mean_tok = ops.token_mean(feat.view(b, p, c))
+        q = ops.gemm(mean_tok, *self.proj["q_proj"], out_f32=True)
+        o = ops.attnpool_query0(q, k, v, b, p, self.heads)
+        g = ops.gemm(o, *self.proj["c_proj"], out_f32=True)
+        return local, ssq, g
+
+
+class TextTower:
+    def __init__(self, sd, width, heads, layers, embed_dim, device):
+        g = lambda k: sd[k].detach().to(device)
+        self.width, self.heads, self.nlayers, self.embed_dim, self.device = width, heads, layers, embed_dim, device
+        self.pos = g("positional_embedding").float().contiguous()
+        self.tok = g("token_embedding.weight").float().contiguous()
+        self.blocks = []
+        for i in range(layers):
+            p = f"transformer.resblocks.{i}"
+            self.blocks.append({
+                "ln1": (g(p + ".ln_1.weight").float().contiguous(), g(p + ".ln_1.bias").float().contiguous()),
+                "ln2": (g(p + ".ln_2.weight").float().contiguous(), g(p + ".ln_2.bias").float().contiguous()),
+                "qkv": (g(p + ".attn.in_proj_weight").to(torch.bfloat16).contiguous(), g(p + ".attn.in_proj_bias").float().contiguous()),
+                "out": (g(p + ".attn.out_proj.weight").to(torch.bfloat16).contiguous(), g(p + ".attn.out_proj.bias").float().contiguous()),
+                "fc": (g(p + ".mlp.c_fc.weight").to(torch.bfloat16).contiguous(), g(p + ".mlp.c_fc.bias").float().contiguous()),
+                "proj": (g(p + ".mlp.c_proj.weight").to(torch.bfloat16).contiguous(), g(p + ".mlp.c_proj.bias").float().contiguous()),
+            })
+        self.ln_final = (g("ln_final.weight").float().contiguous(), g("ln_final.bias").float().contiguous())
+        self.text_proj_t = g("text_projection").t().to(torch.bfloat16).contiguous()      # [D, W] K-major
+
+    def forward(self, x, eot_index=None, sequence=False):
+        """T:82-101.  x fp32 [N,L,W] = embeddings + positional embedding.  -> fp32 [N,D] at `eot_index`
+        (int64 [N]) or fp32 [N,L,D] when `sequence`."""
+        n, l, w = x.shape
+        x = x.reshape(n * l, w).contiguous()
+        for blk in self.blocks:
+            h, _, _, _ = ops.layernorm(x, *blk["ln1"])
+            qkv = ops.gemm(h, *blk["qkv"])
+            a = ops.causal_attn(qkv, n, l, w, self.heads)
+            x = ops.gemm_f32res(a, *blk["out"], x)
+            h, _, _, _ = ops.layernorm(x, *blk["ln2"])
+            u = ops.gemm(h, *blk["fc"], quick_gelu=True)
+            x = ops.gemm_f32res(u, *blk["proj"], x)
+        h, _, _, _ = ops.layernorm(x, *self.ln_final)
+        if sequence:
+            return ops.gemm(h, self.text_proj_t, out_f32=True).view(n, l, -1)
+        rows = h.view(n, l, w)[torch.arange(n, device=h.device), eot_index].contiguous()
+        return ops.gemm(rows, self.text_proj_t, out_f32=True)

@@ -60,3 +60,141 @@ def conv3x3(x, w, bias=None, relu=True, out=None):
     check(lib.lecb_conv3x3_bf16(_ptr(x), _ptr(w), _ptr(bias), _ptr(out), b, h, wd, cin, cout,
                                 EPI_RELU if relu else 0, _stream()), "lecb_conv3x3_bf16")
     return out
+
+
+def gemm_f32res(a, w, bias, residual_f32, out=None):
+    """fp32 residual stream update: out_f32 = a @ w^T + bias + residual_f32 (text-tower blocks, M:226-227)."""
+    _need(a, torch.bfloat16, "a")
+    _need(w, torch.bfloat16, "w")
+    _need(residual_f32, torch.float32, "residual")
+    m, k = a.shape
+    n = w.shape[0]
+    if out is None:
+        out = torch.empty((m, n), device=a.device, dtype=torch.float32)
+    check(lib.lecb_gemm_bf16(_ptr(a), _ptr(w), _ptr(bias), _ptr(residual_f32), _ptr(out), 0, m, n, k,
+                             EPI_OUT_F32 | _lib.EPI_RES_F32, _stream()), "lecb_gemm_bf16")
+    return out
+
+
+def stem_conv1(x, w27, bias):
+    """x NCHW fp32 [B,3,H,W]; w27 fp32 [27,Cout]; -> NHWC bf16 [B,H/2,W/2,Cout] (conv+BN+ReLU)."""
+    _need(x, torch.float32, "x")
+    _need(w27, torch.float32, "w27")
+    _need(bias, torch.float32, "bias")
+    b, c, h, w = x.shape
+    assert c == 3
+    cout = w27.shape[1]
+    out = torch.empty((b, h // 2, w // 2, cout), device=x.device, dtype=torch.bfloat16)
+    check(lib.lecb_stem_conv1(_ptr(x), _ptr(w27), _ptr(bias), _ptr(out), b, h, w, cout, _stream()), "lecb_stem_conv1")
+    return out
+
+
+def avgpool2x2(x):
+    _need(x, torch.bfloat16, "x")
+    b, h, w, c = x.shape
+    out = torch.empty((b, h // 2, w // 2, c), device=x.device, dtype=torch.bfloat16)
+    check(lib.lecb_avgpool2x2(_ptr(x), _ptr(out), b, h, w, c, _stream()), "lecb_avgpool2x2")
+    return out
+
+
+def token_mean(x, want_f32=False):
+    """x bf16 [B,P,C] -> bf16 [B,C] (and fp32 copy if asked)."""
+    _need(x, torch.bfloat16, "x")
+    b, p, c = x.shape
+    ob = torch.empty((b, c), device=x.device, dtype=torch.bfloat16)
+    of = torch.empty((b, c), device=x.device, dtype=torch.float32) if want_f32 else None
+    check(lib.lecb_token_mean(_ptr(x), _ptr(ob), _ptr(of), b, p, c, _stream()), "lecb_token_mean")
+    return (ob, of) if want_f32 else ob
+
+
+def l2norm_rows(x, out_dtype=None):
+    """y = x / ||x||_2 along the last dim (no epsilon, like the reference)."""
+    assert x.dtype in (torch.float32, torch.bfloat16) and x.is_cuda and x.is_contiguous()
+    out_dtype = out_dtype or x.dtype
+    d = x.shape[-1]
+    rows = x.numel() // d
+    y = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    check(lib.lecb_l2norm_rows(_ptr(x), _ptr(y), rows, d, int(x.dtype == torch.bfloat16),
+                               int(out_dtype == torch.bfloat16), _stream()), "lecb_l2norm_rows")
+    return y
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out_bf16=True, out_f32=False, save_stats=False):
+    _need(x, torch.float32, "x")
+    d = x.shape[-1]
+    rows = x.numel() // d
+    yb = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if out_bf16 else None
+    yf = torch.empty(x.shape, device=x.device, dtype=torch.float32) if out_f32 else None
+    mean = torch.empty((rows,), device=x.device, dtype=torch.float32) if save_stats else None
+    rstd = torch.empty((rows,), device=x.device, dtype=torch.float32) if save_stats else None
+    check(lib.lecb_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(yb), _ptr(yf), _ptr(mean), _ptr(rstd), rows, d,
+                                 float(eps), _stream()), "lecb_layernorm_fwd")
+    return yb, yf, mean, rstd
+
+
+def attnpool_query0(q, kmat, vmat, b, p, heads):
+    _need(q, torch.float32, "q")
+    _need(kmat, torch.bfloat16, "kmat")
+    _need(vmat, torch.bfloat16, "vmat")
+    c = q.shape[-1]
+    out = torch.empty((b, c), device=q.device, dtype=torch.bfloat16)
+    check(lib.lecb_attnpool_query0(_ptr(q), _ptr(kmat), _ptr(vmat), _ptr(out), b, p, c, heads, _stream()),
+          "lecb_attnpool_query0")
+    return out
+
+
+def causal_attn(qkv, n, l, w, heads):
+    _need(qkv, torch.bfloat16, "qkv")
+    out = torch.empty((n * l, w), device=qkv.device, dtype=torch.bfloat16)
+    check(lib.lecb_causal_attn_fwd(_ptr(qkv), _ptr(out), n, l, w, heads, _stream()), "lecb_causal_attn_fwd")
+    return out
+
+
+def head_aggregate(dots, b, p, k, n_txt, row_sumsq=None, row_mask=None, logit_scale=4.0, spatial_scale=50.0,
+                   want_maps=True):
+    """dots fp32 [B*P, ldn] -> logits_local [B,K] (+ neg_map, pos_map [P,B,K])."""
+    _need(dots, torch.float32, "dots")
+    ldn = dots.shape[-1]
+    out = torch.empty((b, k), device=dots.device, dtype=torch.float32)
+    neg = torch.empty((p, b, k), device=dots.device, dtype=torch.float32) if want_maps else None
+    pos = torch.empty((p, b, k), device=dots.device, dtype=torch.float32) if want_maps else None
+    if row_mask is not None:
+        _need(row_mask, torch.uint8, "row_mask")
+    check(lib.lecb_head_aggregate(_ptr(dots), ldn, _ptr(row_sumsq), _ptr(row_mask), _ptr(out), _ptr(neg), _ptr(pos),
+                                  b, p, k, n_txt, float(logit_scale), float(spatial_scale), _stream()),
+          "lecb_head_aggregate")
+    return out, neg, pos
+
+
+def global_logits(g_unit, tpos, g_add=None, scale=4.0):
+    _need(g_unit, torch.float32, "g_unit")
+    _need(tpos, torch.float32, "tpos")
+    b, d = g_unit.shape
+    k = tpos.shape[0]
+    out = torch.empty((b, k), device=g_unit.device, dtype=torch.float32)
+    check(lib.lecb_global_logits(_ptr(g_unit), _ptr(g_add), _ptr(tpos), _ptr(out), b, d, k, float(scale), _stream()),
+          "lecb_global_logits")
+    return out
+
+
+def asl_fwd_bwd(logits, targets, gamma_neg=2.0, gamma_pos=1.0, clip=0.05, eps=1e-8, thresh_pos=0.9, thresh_neg=0.9,
+                partial=False, want_grad=True):
+    _need(logits, torch.float32, "logits")
+    _need(targets, torch.float32, "targets")
+    b, k = logits.shape
+    grad = torch.empty_like(logits) if want_grad else None
+    loss = torch.empty((), device=logits.device, dtype=torch.float32)
+    check(lib.lecb_asl_fwd_bwd(_ptr(logits), _ptr(targets), _ptr(grad), _ptr(loss), b, k, gamma_neg, gamma_pos, clip,
+                               eps, thresh_pos, thresh_neg, int(partial), _stream()), "lecb_asl_fwd_bwd")
+    return loss, grad
+
+
+def ranking_fwd_bwd(logits, targets, scale=2.0, margin=1.0, want_grad=True):
+    _need(logits, torch.float32, "logits")
+    _need(targets, torch.float32, "targets")
+    b, k = logits.shape
+    grad = torch.empty_like(logits) if want_grad else None
+    loss = torch.empty((), device=logits.device, dtype=torch.float32)
+    check(lib.lecb_ranking_fwd_bwd(_ptr(logits), _ptr(targets), _ptr(grad), _ptr(loss), b, k, float(scale),
+                                   float(margin), _stream()), "lecb_ranking_fwd_bwd")
+    return loss, grad

@@ -1,0 +1,84 @@
+"""Per-entry-point CUDA-event timing of the C-ABI calls (used by bench.py for the roofline numbers).
+
+`with KernelTimer() as kt: step()` brackets every liblecb call with CUDA events on the launching
+stream and accumulates duration plus algorithmic FLOPs / bytes per entry point.  Instrumentation
+only: nothing here is active during the timed throughput region."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def _work(name, a):
+    """(flops, algorithmic HBM bytes) of one call from its C arguments."""
+    if name == "lecb_gemm_bf16":
+        m, n, k, flags = a[6], a[7], a[8], a[9]
+        out_b = 4 if flags & _lib.EPI_OUT_F32 else 2
+        res_b = 0 if not a[3] else (4 if flags & _lib.EPI_RES_F32 else 2)
+        return 2.0 * m * n * k, 2.0 * (m * k + n * k) + m * n * (out_b + res_b)
+    if name == "lecb_conv3x3_bf16":
+        b, h, w, ci, co = a[4], a[5], a[6], a[7], a[8]
+        return 2.0 * b * h * w * co * 9 * ci, 2.0 * (b * h * w * (ci + co) + 9 * ci * co)
+    if name == "lecb_avgpool2x2":
+        b, h, w, c = a[2], a[3], a[4], a[5]
+        return 1.0 * b * h * w * c, 2.0 * b * h * w * c * 1.25
+    if name == "lecb_stem_conv1":
+        b, h, w, co = a[4], a[5], a[6], a[7]
+        return 2.0 * b * (h // 2) * (w // 2) * co * 27, 4.0 * b * 3 * h * w + 2.0 * b * (h // 2) * (w // 2) * co
+    if name == "lecb_head_aggregate":
+        ldn, b, p, k, n_txt = a[1], a[7], a[8], a[9], a[10]
+        maps = 2 if a[5] else 0
+        return 20.0 * b * p * k, 4.0 * b * p * (n_txt * k + maps * k) + 4.0 * b * k
+    if name == "lecb_l2norm_rows":
+        rows, d = a[2], a[3]
+        return 3.0 * rows * d, rows * d * ((2 if a[4] else 4) + (2 if a[5] else 4))
+    if name == "lecb_asl_fwd_bwd":
+        return 25.0 * a[4] * a[5], 12.0 * a[4] * a[5]
+    return 0.0, 0.0
+
+
+class KernelTimer:
+    def __init__(self):
+        self.records = []          # (name, start_evt, end_evt, flops, bytes)
+        self._saved = {}
+
+    def __enter__(self):
+        lib = _lib.lib
+        for name in _lib.SIGNATURES:
+            if name in ("lecb_abi_version", "lecb_last_error", "lecb_launch_count"):
+                continue
+            fn = getattr(lib, name)
+            self._saved[name] = fn
+
+            def wrapped(*args, _fn=fn, _name=name):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                stream = torch.cuda.current_stream()
+                s.record(stream)
+                r = _fn(*args)
+                e.record(stream)
+                fl, by = _work(_name, args)
+                self.records.append((_name, s, e, fl, by))
+                return r
+
+            setattr(lib, name, wrapped)
+        return self
+
+    def __exit__(self, *exc):
+        for name, fn in self._saved.items():
+            setattr(_lib.lib, name, fn)
+        torch.cuda.synchronize()
+        return False
+
+    def summary(self, steps=1):
+        agg = {}
+        for name, s, e, fl, by in self.records:
+            d = agg.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+            d["ms"] += s.elapsed_time(e)
+            d["flops"] += fl
+            d["bytes"] += by
+            d["launches"] += 1
+        for d in agg.values():
+            for k in d:
+                d[k] /= steps
+        return agg

@@ -1,0 +1,147 @@
+"""DenseCLIPB200.forward(image, if_test=True) on the B200 vs the reference-generated goldens and the
+CPU oracle (through the C ABI end to end).  Gate: max abs logit error <= 1e-2, top-k label sets equal
+(up to ties inside the tolerance), mAP within +-0.05 — the north_star tolerances."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restatement as R
+
+from . import _cases as C
+from ._gpu_common import LOGIT_TOL, build_model, rel_err, topk_sets_match
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("tag", ["small", "rn50_224"])
+def test_trunk_and_pooling_match_oracle(tag):
+    c = C.head_case(tag)
+    model = build_model(c, use_evidence=False)
+    eng = model.visual_engine()
+    img = c["image"].cuda()
+    feat = eng.trunk(img)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref_feat = R.rn_trunk(c["sd"], c["image"], c["arch"].vision_layers)
+        ref_local = R.local_features(c["sd"], ref_feat)                                 # [P,B,D]
+        ref_g = R.attnpool_global(c["sd"], ref_feat, c["arch"].vision_width * 32 // 64)
+    # sanity bounds on intermediates (bf16 activations through up to 100 layers); the parity GATE is the
+    # logit tolerance in test_forward_test_matches_reference
+    e = rel_err(feat.permute(0, 3, 1, 2), ref_feat)
+    print(f"[{tag}] trunk rel err {e:.4f}")
+    assert e < 8e-2, f"trunk rel err {e}"
+    local, ssq, g = eng.pooled(feat)
+    b, p = ref_local.shape[1], ref_local.shape[0]
+    e = rel_err(local.view(b, p, -1).permute(1, 0, 2), ref_local)
+    print(f"[{tag}] local rel err {e:.4f}")
+    assert e < 8e-2, f"local rel err {e}"
+    e = rel_err(g, ref_g)
+    print(f"[{tag}] global rel err {e:.4f}")
+    assert e < 8e-2, f"global rel err {e}"
+    want = local.float().pow(2).sum(-1)
+    assert ((ssq - want).abs() / want).max().item() < 1e-3
+
+
+@pytest.mark.parametrize("tag", ["small", "rn50_224", "rn101_448"])
+def test_forward_test_matches_reference(tag):
+    c = C.head_case(tag)
+    g = c["gold"]
+    for ev in c["modes"]:
+        sfx = "_ev" if ev else ""
+        model = build_model(c, use_evidence=ev)
+        out = model(c["image"].cuda(), if_test=True)
+        torch.cuda.synchronize()
+        logits, logits_local, neg_map, pos_map, scores = [None if t is None else t.float().cpu() for t in out]
+        # retrieval off here (bank=None): compare logits_ with the oracle run without a bank
+        with torch.no_grad():
+            ref = R.dense_clip_test(c["sd"], c["arch"], c["image"], c["pl_state"], c["tokens"], use_evidence=ev, bank=None)
+        assert scores is None
+        print(f"[{tag}{sfx}] max abs err: logits_ {(logits - ref[0]).abs().max().item():.5f} "
+              f"logits_local {np.abs(logits_local.numpy() - g['logits_local' + sfx]).max():.5f} "
+              f"(range {np.abs(g['logits_local' + sfx]).max():.4f}) neg_map {np.abs(neg_map.numpy() - g['neg_map' + sfx]).max():.5f} "
+              f"pos_map {np.abs(pos_map.numpy() - g['pos_map' + sfx]).max():.5f}")
+        assert (logits - ref[0]).abs().max().item() <= LOGIT_TOL, f"{tag}{sfx}: logits_"
+        assert (logits_local.numpy() - g["logits_local" + sfx]).__abs__().max() <= LOGIT_TOL, f"{tag}{sfx}: logits_local"
+        assert np.abs(neg_map.numpy() - g["neg_map" + sfx]).max() <= LOGIT_TOL
+        assert np.abs(pos_map.numpy() - g["pos_map" + sfx]).max() <= LOGIT_TOL
+        # scale-free check: the local logits are tiny under evidence (WTA divides by ~K), so also bound the
+        # error relative to the output range
+        assert rel_err(logits_local, torch.from_numpy(g["logits_local" + sfx])) < 5e-2, f"{tag}{sfx}: local rel"
+        assert topk_sets_match(logits.numpy(), ref[0].numpy(), 5, 2 * LOGIT_TOL)
+        assert topk_sets_match(logits_local.numpy(), g["logits_local" + sfx], 5, 2 * LOGIT_TOL)
+
+
+@pytest.mark.parametrize("tag", ["small", "rn50_224"])
+def test_planted_prototypes_map_and_topk(tag):
+    """mAP / top-k parity on scores with a realistic spread.  Random-init prompts give near-tied class
+    scores (every cosine within ~1e-2 of the others), where rank metrics only measure rounding noise.
+    Here the class prompts are *planted* from the data: text feature k = the unit local feature of a
+    random (patch, image) taken from the ORACLE's fp32 features, loaded through the reference's own
+    `prompt_text_features` cache (T:421-426).  Cosines then span [-0.2, 1] and logits reach 4.0, so the
+    1e-2 logit tolerance, the top-k label sets and the +-0.05 mAP gate (EV:137-175) are all meaningful."""
+    c = C.head_case(tag)
+    arch = c["arch"]
+    with torch.no_grad():
+        feat = R.rn_trunk(c["sd"], c["image"], arch.vision_layers)
+        local = R.local_features(c["sd"], feat)                     # [P,B,D]
+        g_ref = R.attnpool_global(c["sd"], feat, arch.vision_width * 32 // 64)
+    p, b, d = local.shape
+    rng = np.random.default_rng(5)
+    unit = (local / local.norm(dim=-1, keepdim=True)).reshape(p * b, d)
+    k = 80
+    t_pos = unit[rng.choice(p * b, k, replace=False)].clone()
+    t_neg = unit[rng.choice(p * b, k, replace=False)].clone()
+    with torch.no_grad():
+        ref = R.head_test(g_ref, local, t_pos, t_neg, None, bank=None)
+    model = build_model(c, use_evidence=False)
+    model.prompt_text_features = {"text_features": t_pos.cuda(), "text_features_neg": t_neg.cuda()}
+    out = [t.float().cpu() for t in model(c["image"].cuda(), if_test=True)[:4]]
+    torch.cuda.synchronize()
+    errs = [(o - r).abs().max().item() for o, r in zip(out, ref[:4])]
+    print(f"[{tag}] planted: max abs err logits_ {errs[0]:.5f} logits_local {errs[1]:.5f} neg {errs[2]:.5f} pos {errs[3]:.5f}; "
+          f"ranges {ref[0].abs().max():.3f} {ref[1].abs().max():.3f}")
+    assert max(errs) <= LOGIT_TOL
+    assert topk_sets_match(out[0].numpy(), ref[0].numpy(), 5, 2 * LOGIT_TOL)
+    assert topk_sets_match(out[1].numpy(), ref[1].numpy(), 5, 2 * LOGIT_TOL)
+    # mAP over all (patch, image) rows of the positive-prompt map; labels = reference cosine in the class's
+    # top 15 %, with 10 % label noise so the reference mAP is not a degenerate 100
+    ref_rows, got_rows = ref[3].reshape(p * b, k).numpy(), out[3].reshape(p * b, k).numpy()
+    y = (ref_rows > np.quantile(ref_rows, 0.85, axis=0)).astype(np.float32)
+    flip = rng.random(y.shape) < 0.10
+    y = np.where(flip, 1 - y, y)
+    m_got, m_ref = R.mean_average_precision(y, got_rows), R.mean_average_precision(y, ref_rows)
+    print(f"[{tag}] planted: mAP over {p * b} rows: got {m_got:.4f} ref {m_ref:.4f}")
+    assert abs(m_got - m_ref) <= 0.05, (m_got, m_ref)
+
+
+@pytest.mark.parametrize("tag", ["small", "rn50_224", "rn101_448"])
+def test_forward_with_retrieval_matches_reference(tag):
+    """T:444-448 caption retrieval in the loop: logits_ and the top-10 scores vs the reference run."""
+    c = C.head_case(tag)
+    g = c["gold"]
+    ev = c["modes"][-1]
+    sfx = "_ev" if ev else ""
+    model = build_model(c, use_evidence=ev, bank=c["bank"].cuda())
+    out = model(c["image"].cuda(), if_test=True)
+    torch.cuda.synchronize()
+    logits, scores = out[0].float().cpu().numpy(), out[4].float().cpu().numpy()
+    e1, e2 = np.abs(logits - g["logits" + sfx]).max(), np.abs(scores - g["topk_scores" + sfx]).max()
+    print(f"[{tag}{sfx}] retrieval: logits_ err {e1:.5f} (range {np.abs(g['logits' + sfx]).max():.4f}) topk score err {e2:.5f}")
+    assert e1 <= LOGIT_TOL and e2 <= LOGIT_TOL
+    assert topk_sets_match(logits, g["logits" + sfx], 5, 2 * LOGIT_TOL)
+
+
+def test_prompt_features_match_reference():
+    c = C.head_case("small")
+    model = build_model(c, use_evidence=True)
+    tf = model._prompt_features(True)
+    g = c["gold"]
+    for k in ("text_features", "text_features_neg", "text_features_evidence"):
+        err = np.abs(tf[k].float().cpu().numpy() - g[k + "_ev"]).max()
+        assert err < 5e-3, f"{k}: {err}"        # unit vectors of dim 512: entries ~0.04, bf16 tower
+
+
+def test_no_cpu_path():
+    from lecb200 import LecbError, ops
+    with pytest.raises(LecbError):
+        ops.gemm(torch.zeros((128, 64), dtype=torch.bfloat16), torch.zeros((64, 64), dtype=torch.bfloat16))
