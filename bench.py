@@ -71,7 +71,7 @@ def make_cfg(res, n_ctx, use_evidence):
 # clocks
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
@@ -86,7 +86,9 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summarise the samples whose timestamp falls inside [t_begin, t_end] (time.time() values)."""
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -102,15 +104,18 @@ class ClockSampler:
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for line in self.tmp.read().splitlines():
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-                power.append(float(parts[2]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if t_begin is not None and not (t_begin - 0.05 <= ts <= t_end + 0.05):
+                    continue
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+                power.append(float(parts[3]))
             except ValueError:
                 continue
-            for n, v in zip(names, parts[3:7]):
+            for n, v in zip(names, parts[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         try:
@@ -187,7 +192,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="lecb200", choices=["lecb200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step (configs[1]: 256)")
@@ -245,20 +250,22 @@ def main():
         out = model(img, if_test=True)
         return all_gather_logits(out[0], out[1])
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                      # started before warm-up: nvidia-smi needs ~0.5 s to produce samples
     for _ in range(args.warmup):
         step(images)
     barrier()
     launches0 = lecb200.launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.time()
     e0.record()
     for _ in range(args.steps):
         res = step(images)
     e1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    t_end = time.time()
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     launches = (lecb200.launch_count() - launches0) // args.steps
     value = world * B / (ms * 1e-3)
@@ -324,7 +331,7 @@ def main():
                     "share_of_step": gemm_ms / total_ms, "algorithmic_gflop_per_step": gemm_fl / 1e9}
         if args.profile_out:
             with open(args.profile_out, "w") as f:
-                json.dump({"batch": B, "ms_per_step_events_sum": total_ms, "table": table}, f, indent=1)
+                json.dump({"batch": B, "ms_per_step_events_sum": total_ms, "table": table, "detail": kt.detail(prof_steps)}, f, indent=1)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

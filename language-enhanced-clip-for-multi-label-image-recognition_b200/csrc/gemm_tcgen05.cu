@@ -5,13 +5,21 @@
 // A tiles (128 x BK) and W tiles (BN x BK) are staged in shared memory by TMA in the canonical
 // K-major swizzled layout (BK*2 bytes per row: 128B or 64B swizzle), multiplied by tcgen05.mma
 // (one elected thread, M=128, N=BN, K=16 per instruction) into a double-buffered fp32 accumulator in
-// TMEM, and drained by four epilogue warps with tcgen05.ld (thread == output row) that apply
-// bias / residual / ReLU / QuickGELU and store bf16 or fp32.  In CONV mode the A producer issues
-// TMA *im2col* loads over the NHWC activation tensor — one (tap, channel-block) per K step, padding
-// and row/image wrap handled by the TMA unit — so a 3x3 convolution is the same GEMM with K = 9*Cin.
+// TMEM, and drained by four epilogue warps with tcgen05.ld (thread == output row).  In CONV mode the A
+// producer issues TMA *im2col* loads over the NHWC activation tensor — one (tap, channel-block) per K
+// step, padding and row/image wrap handled by the TMA unit — so a 3x3 convolution is the same GEMM
+// with K = 9*Cin.
 //
-// Roles (192 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 TMA producer,
-// warp 5 MMA issuer + TMEM owner.  Three mbarrier rings: smem full/empty, TMEM full/empty.
+// Epilogue (bf16 output): the tile leaves through shared memory in 64-column blocks.  A dedicated DMA
+// warp TMA-loads the bf16 residual block into a swizzled staging buffer ahead of time, the epilogue
+// warps add bias / residual, apply ReLU / QuickGELU, overwrite the block in place, and the DMA warp
+// TMA-stores it — every HBM access of the epilogue is a full-line bulk transfer, overlapped with the
+// next tile's MMAs.  fp32 outputs (small / final GEMMs) use direct vector stores instead.
+//
+// Roles (352 threads): warps 0-7 epilogue in two groups of four (TMEM lane quarter = warp id % 4; the
+// groups take alternate 64-column blocks so two blocks are always in flight per SM), warp 8 TMA producer,
+// warp 9 MMA issuer + TMEM owner, warp 10 epilogue DMA.  mbarrier rings: smem full/empty (operands),
+// TMEM full/empty (accumulators), staging free/full (epilogue blocks).
 #include <stdio.h>
 
 #include "lecb_common.cuh"
@@ -20,22 +28,26 @@
 namespace lecb {
 
 constexpr int kTileM = 128;
-constexpr int kNumThreads = 192;
+constexpr int kNumThreads = 352;
+constexpr int kWarpTma = 8, kWarpMma = 9, kWarpDma = 10;
 
-template <int BN, int BK>
+template <int BN, int BK, int NB>
 struct GemmCfg {
   static constexpr int kABytes = kTileM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
+  static constexpr int kCCols = BN >= 64 ? 64 : BN;               // columns per staged epilogue block
+  static constexpr int kCBlocks = BN / kCCols;
+  static constexpr int kCBytes = kTileM * kCCols * 2;             // 16 KB (8 KB for BN = 32)
+  static constexpr int kStagesRaw = (227 * 1024 - NB * kCBytes - 2048) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + NB * kCBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct GemmParams {
   const float* bias;
-  const __nv_bfloat16* residual;
+  const void* residual;
   void* out;
   float* row_sumsq;
   int64_t M;
@@ -44,31 +56,38 @@ struct GemmParams {
   int num_m_tiles;
   int num_n_tiles;
   unsigned flags;
+  int staged;        // bf16 output through smem + TMA store
   // conv mode
   int H, W, kb_per_tap;
 };
 
-template <int BN, int BK, bool kConv>
+template <int BN, int BK, int NB, bool kConv>
 __global__ void __launch_bounds__(kNumThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = GemmCfg<BN, BK>;
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
+  using Cfg = GemmCfg<BN, BK, NB>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int kCCols = Cfg::kCCols;
+  constexpr int kCBlocks = Cfg::kCBlocks;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* sC = smem + kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + NB * Cfg::kCBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kStages;
   uint64_t* tfull = bars + 2 * kStages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* cfree = tempty + 2;
+  uint64_t* cfull = cfree + NB;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cfull + NB);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == kWarpTma && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < kStages; ++i) {
@@ -77,11 +96,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      // staged path: both epilogue groups read every accumulator (8 warps) unless a tile is a single block,
+      // in which case the groups alternate tiles (4 warps); direct fp32 path: group 0 only
+      mbar_init(&tempty[i], (p.staged && kCBlocks > 1) ? 8 : 4);
+    }
+    for (int i = 0; i < NB; ++i) {
+      mbar_init(&cfree[i], 1);
+      mbar_init(&cfull[i], 4);
     }
     fence_barrier_init();
   }
-  if (warp == 5) {
+  if (warp == kWarpMma) {
     tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
@@ -90,7 +115,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == kWarpTma) {
     // ------------------------------- TMA producer -------------------------------
     if (lane == 0) {
       int stage = 0;
@@ -127,7 +152,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kWarpMma) {
     // ------------------------------- MMA issuer ---------------------------------
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(BN, (p.flags & LECB_GEMM_F16_OPERANDS) == 0);
@@ -161,74 +186,200 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (acc == 0) acc_phase ^= 1;
       }
     }
+  } else if (warp == kWarpDma) {
+    // ------------------------------- epilogue DMA (staged bf16 output) ----------
+    if (lane == 0 && p.staged) {
+      const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      const uint32_t total = static_cast<uint32_t>(my_tiles) * kCBlocks;
+      const bool has_res = p.residual != nullptr;
+      auto coords = [&](uint32_t g, int& m0, int& n0) {
+        const int i = static_cast<int>(g / kCBlocks), cb = static_cast<int>(g % kCBlocks);
+        const int tile = blockIdx.x + i * gridDim.x;
+        const int m_blk = tile / p.num_n_tiles;
+        const int n_blk = tile - m_blk * p.num_n_tiles;
+        m0 = m_blk * kTileM;
+        n0 = n_blk * BN + cb * kCCols;
+      };
+      auto make_free = [&](uint32_t g) {
+        const int buf = g % NB;
+        if (has_res) {
+          int m0, n0;
+          coords(g, m0, n0);
+          mbar_arrive_expect_tx(&cfree[buf], Cfg::kCBytes);
+          tma_load_2d(&tmR, &cfree[buf], sC + buf * Cfg::kCBytes, n0, m0);
+        } else {
+          mbar_arrive(&cfree[buf]);
+        }
+      };
+      for (uint32_t g = 0; g < NB && g < total; ++g) make_free(g);
+      for (uint32_t g = 0; g < total; ++g) {
+        const int buf = g % NB;
+        mbar_wait(&cfull[buf], (g / NB) & 1);
+        int m0, n0;
+        coords(g, m0, n0);
+        tma_store_2d(&tmC, sC + buf * Cfg::kCBytes, n0, m0);
+        tma_store_commit();
+        // recycle the buffer of the PREVIOUS block (its store had a whole block time to drain) so the lane
+        // never stalls on the store it has just issued
+        if (g >= 1 && g - 1 + NB < total) {
+          tma_store_wait_read1();
+          make_free(g - 1 + NB);
+        }
+      }
+      tma_store_wait_all();
+    }
   } else {
-    // ------------------------------- epilogue (warps 0-3) -----------------------
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    // ------------------------------- epilogue (warps 0-7) -----------------------
+    const int group = warp >> 2;                 // 0 or 1
+    const int quarter = warp & 3;                // TMEM lane quarter this warp may read
     const bool relu = p.flags & LECB_EPI_RELU;
     const bool gelu = p.flags & LECB_EPI_QUICKGELU;
-    const bool out_f32 = p.flags & LECB_EPI_OUT_F32;
     const bool res_f32 = p.flags & LECB_EPI_RES_F32;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const uint32_t erow = static_cast<uint32_t>(quarter * 32 + lane);   // row inside the tile == TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    int tile_seq = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_seq) {
       const int m_blk = tile / p.num_n_tiles;
       const int n_blk = tile - m_blk * p.num_n_tiles;
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
-      const int64_t row = static_cast<int64_t>(m_blk) * kTileM + warp * 32 + lane;
+      const int acc = tile_seq & 1;
+      const uint32_t acc_phase = (tile_seq >> 1) & 1;
+      const int64_t row = static_cast<int64_t>(m_blk) * kTileM + erow;
       const bool row_ok = row < p.M;
       float ssq = 0.f;
+      if (p.staged) {
+        // block g = tile_seq * kCBlocks + cb belongs to group g % 2
+        const uint32_t g0 = static_cast<uint32_t>(tile_seq) * kCBlocks;
+        int cb_first = (kCBlocks > 1) ? group : (((g0 & 1) == static_cast<uint32_t>(group)) ? 0 : kCBlocks);
+        if (cb_first >= kCBlocks) continue;       // single-block tile owned by the other group
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(acc * BN + c * 32), r);
-        tmem_ld_wait();
-        const int n0 = n_blk * BN + c * 32;
-        if (n0 >= p.N) continue;
-        float v[32];
+        for (int cb = cb_first; cb < kCBlocks; cb += 2) {
+          const uint32_t gblk = g0 + cb;
+          const int buf = gblk % NB;
+          uint8_t* cbuf = sC + buf * Cfg::kCBytes;
+          // both 32-column halves of the block are fetched from TMEM back to back, then one wait
+          uint32_t r[kCCols / 32][32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias != nullptr) {
+          for (int half = 0; half < kCCols / 32; ++half)
+            tmem_ld_32x32(tmem_base + lane_base + static_cast<uint32_t>(acc * BN + cb * kCCols + half * 32), r[half]);
+          tmem_ld_wait();
+          if (cb + 2 >= kCBlocks) {      // last TMEM read of this accumulator by this warp: hand it back early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          mbar_wait(&cfree[buf], (gblk / NB) & 1);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (n0 + j < p.N) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          for (int half = 0; half < kCCols / 32; ++half) {
+            const int n0 = n_blk * BN + cb * kCCols + half * 32;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[half][j]);
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                if (n0 + j < p.N) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                  v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                }
+              }
+            }
+            if (p.residual != nullptr) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 u = *reinterpret_cast<const uint4*>(cbuf + swizzled_chunk_offset(erow, half * 4 + q, kCCols * 2));
+                float2 f;
+                f = unpack_bf16(u.x); v[q * 8 + 0] += f.x; v[q * 8 + 1] += f.y;
+                f = unpack_bf16(u.y); v[q * 8 + 2] += f.x; v[q * 8 + 3] += f.y;
+                f = unpack_bf16(u.z); v[q * 8 + 4] += f.x; v[q * 8 + 5] += f.y;
+                f = unpack_bf16(u.w); v[q * 8 + 6] += f.x; v[q * 8 + 7] += f.y;
+              }
+            }
+            if (relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (gelu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 u;
+              u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+              u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+              u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+              u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+              *reinterpret_cast<uint4*>(cbuf + swizzled_chunk_offset(erow, half * 4 + q, kCCols * 2)) = u;
+              if (p.row_sumsq != nullptr && n0 + q * 8 < p.N) {
+                float2 f;
+                f = unpack_bf16(u.x); ssq += f.x * f.x + f.y * f.y;
+                f = unpack_bf16(u.y); ssq += f.x * f.x + f.y * f.y;
+                f = unpack_bf16(u.z); ssq += f.x * f.x + f.y * f.y;
+                f = unpack_bf16(u.w); ssq += f.x * f.x + f.y * f.y;
+              }
             }
           }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&cfull[buf]);
         }
-        if (p.residual != nullptr && row_ok && res_f32) {
-          const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + row * p.N + n0);
+      } else {
+        if (group != 0) continue;                 // direct fp32 stores: one group is plenty (small GEMMs)
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + lane_base + static_cast<uint32_t>(acc * BN + c * 32), r);
+          tmem_ld_wait();
+          const int n0 = n_blk * BN + c * 32;
+          if (n0 >= p.N) continue;
+          float v[32];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            if (n0 + q * 4 < p.N) {
-              const float4 f = __ldg(rp + q);
-              v[q * 4 + 0] += f.x; v[q * 4 + 1] += f.y; v[q * 4 + 2] += f.z; v[q * 4 + 3] += f.w;
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (n0 + j < p.N) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
             }
           }
-        } else if (p.residual != nullptr && row_ok) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row * p.N + n0);
+          if (p.residual != nullptr && row_ok && res_f32) {
+            const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + row * p.N + n0);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (n0 + q * 8 < p.N) {
-              const uint4 u = __ldg(rp + q);
-              float2 f;
-              f = unpack_bf16(u.x); v[q * 8 + 0] += f.x; v[q * 8 + 1] += f.y;
-              f = unpack_bf16(u.y); v[q * 8 + 2] += f.x; v[q * 8 + 3] += f.y;
-              f = unpack_bf16(u.z); v[q * 8 + 4] += f.x; v[q * 8 + 5] += f.y;
-              f = unpack_bf16(u.w); v[q * 8 + 6] += f.x; v[q * 8 + 7] += f.y;
+            for (int q = 0; q < 8; ++q) {
+              if (n0 + q * 4 < p.N) {
+                const float4 f = __ldg(rp + q);
+                v[q * 4 + 0] += f.x; v[q * 4 + 1] += f.y; v[q * 4 + 2] += f.z; v[q * 4 + 3] += f.w;
+              }
+            }
+          } else if (p.residual != nullptr && row_ok) {
+            const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + row * p.N + n0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (n0 + q * 8 < p.N) {
+                const uint4 u = __ldg(rp + q);
+                float2 f;
+                f = unpack_bf16(u.x); v[q * 8 + 0] += f.x; v[q * 8 + 1] += f.y;
+                f = unpack_bf16(u.y); v[q * 8 + 2] += f.x; v[q * 8 + 3] += f.y;
+                f = unpack_bf16(u.z); v[q * 8 + 4] += f.x; v[q * 8 + 5] += f.y;
+                f = unpack_bf16(u.w); v[q * 8 + 6] += f.x; v[q * 8 + 7] += f.y;
+              }
             }
           }
-        }
-        if (relu) {
+          if (relu) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (gelu) {
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (gelu) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
-        }
-        if (row_ok) {
-          if (out_f32) {
+            for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+          }
+          if (row_ok) {
             float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + row * p.N + n0);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -239,61 +390,50 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                          v[q * 4 + 3] * v[q * 4 + 3];
               }
             }
-          } else {
-            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + row * p.N + n0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (n0 + q * 8 < p.N) {
-                uint4 u;
-                u.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
-                u.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-                u.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
-                u.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-                op[q] = u;
-                if (p.row_sumsq != nullptr) {
-                  float2 f;
-                  f = unpack_bf16(u.x); ssq += f.x * f.x + f.y * f.y;
-                  f = unpack_bf16(u.y); ssq += f.x * f.x + f.y * f.y;
-                  f = unpack_bf16(u.z); ssq += f.x * f.x + f.y * f.y;
-                  f = unpack_bf16(u.w); ssq += f.x * f.x + f.y * f.y;
-                }
-              }
-            }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
       }
       if (p.row_sumsq != nullptr && row_ok) atomicAdd(p.row_sumsq + row, ssq);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kWarpMma) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int BN, int BK, bool kConv>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, BK>;
+template <int BN, int BK, int NB, bool kConv>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, BK, NB>;
   static bool configured = false;
-  auto kern = gemm_kernel<BN, BK, kConv>;
+  auto kern = gemm_kernel<BN, BK, NB, kConv>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return fail(LECB_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
     configured = true;
   }
+  CUtensorMap tmC = tmA, tmR = tmA;      // placeholders when the staged path is off
+  p.staged = (p.flags & LECB_EPI_OUT_F32) ? 0 : 1;
+  if (p.staged) {
+    int st = encode_tiled_2d(&tmC, p.out, static_cast<uint64_t>(p.M), static_cast<uint64_t>(p.N), kTileM, Cfg::kCCols);
+    if (st) return st;
+    if (p.residual != nullptr) {
+      if (p.flags & LECB_EPI_RES_F32) return fail(LECB_ERR_ARG, "fp32 residual requires LECB_EPI_OUT_F32");
+      st = encode_tiled_2d(&tmR, p.residual, static_cast<uint64_t>(p.M), static_cast<uint64_t>(p.N), kTileM, Cfg::kCCols);
+      if (st) return st;
+    }
+  }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int sms = sm_count();
   if (sms <= 0) return fail(LECB_ERR_CUDA, "no CUDA device");
   const int grid = tiles < sms ? tiles : sms;
-  kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmR, p);
   count_launch();
   return check_launch("gemm_kernel");
 }
@@ -303,6 +443,27 @@ static int pick_bn(int N) {
   if (N <= 64) return 64;
   if (N <= 128) return 128;
   return 256;
+}
+
+// NB = number of 16 KB epilogue staging buffers: 4 when the K loop is short (the tile is epilogue/HBM-bound and
+// deeper residual prefetch + store overlap matters more than operand stages), else 2.
+template <bool kConv, int NB>
+static int dispatch_nb(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t s) {
+  if (BK == 64) {
+    switch (BN) {
+      case 32: return launch_gemm<32, 64, NB, kConv>(tmA, tmB, p, s);
+      case 64: return launch_gemm<64, 64, NB, kConv>(tmA, tmB, p, s);
+      case 128: return launch_gemm<128, 64, NB, kConv>(tmA, tmB, p, s);
+      default: return launch_gemm<256, 64, NB, kConv>(tmA, tmB, p, s);
+    }
+  }
+  return BN == 32 ? launch_gemm<32, 32, NB, kConv>(tmA, tmB, p, s) : launch_gemm<64, 32, NB, kConv>(tmA, tmB, p, s);
+}
+
+template <bool kConv>
+static int dispatch(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t s) {
+  if (!kConv && p.num_kb <= 8) return dispatch_nb<kConv, 4>(BN, BK, tmA, tmB, p, s);
+  return dispatch_nb<kConv, 2>(BN, BK, tmA, tmB, p, s);
 }
 
 }  // namespace lecb
@@ -316,14 +477,14 @@ extern "C" int lecb_gemm_bf16(const void* A, const void* W, const float* bias, c
   LECB_CHECK_ARG(K % 32 == 0, "lecb_gemm_bf16: K=%d must be a multiple of 32", K);
   LECB_CHECK_ARG(N % 8 == 0, "lecb_gemm_bf16: N=%d must be a multiple of 8", N);
   LECB_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
-                     (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                     (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
                  "lecb_gemm_bf16: operands must be 16-byte aligned");
   const int BK = (K % 64 == 0) ? 64 : 32;
   int BN = pick_bn(N);
   if (BK == 32 && BN > 64) BN = 64;
   GemmParams p{};
   p.bias = bias;
-  p.residual = static_cast<const __nv_bfloat16*>(residual);
+  p.residual = residual;
   p.out = out;
   p.row_sumsq = row_sumsq;
   p.M = M;
@@ -337,16 +498,7 @@ extern "C" int lecb_gemm_bf16(const void* A, const void* W, const float* bias, c
   if (st) return st;
   st = encode_tiled_2d(&tmB, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), BN, BK);
   if (st) return st;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (BK == 64) {
-    switch (BN) {
-      case 32: return launch_gemm<32, 64, false>(tmA, tmB, p, s);
-      case 64: return launch_gemm<64, 64, false>(tmA, tmB, p, s);
-      case 128: return launch_gemm<128, 64, false>(tmA, tmB, p, s);
-      default: return launch_gemm<256, 64, false>(tmA, tmB, p, s);
-    }
-  }
-  return BN == 32 ? launch_gemm<32, 32, false>(tmA, tmB, p, s) : launch_gemm<64, 32, false>(tmA, tmB, p, s);
+  return dispatch<false>(BN, BK, tmA, tmB, p, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int lecb_conv3x3_bf16(const void* x, const void* w, const float* bias, void* out, int B, int H, int Wd,
@@ -355,6 +507,8 @@ extern "C" int lecb_conv3x3_bf16(const void* x, const void* w, const float* bias
   LECB_CHECK_ARG(B > 0 && H > 0 && Wd > 0, "lecb_conv3x3_bf16: empty problem");
   LECB_CHECK_ARG(Cin % 32 == 0, "lecb_conv3x3_bf16: Cin=%d must be a multiple of 32", Cin);
   LECB_CHECK_ARG(Cout % 8 == 0, "lecb_conv3x3_bf16: Cout=%d must be a multiple of 8", Cout);
+  LECB_CHECK_ARG((flags & (LECB_EPI_OUT_F32 | LECB_EPI_RES_F32 | LECB_GEMM_F16_OPERANDS)) == 0,
+                 "lecb_conv3x3_bf16: only LECB_EPI_RELU / LECB_EPI_QUICKGELU are supported");
   const int BK = (Cin % 64 == 0) ? 64 : 32;
   int BN = pick_bn(Cout);
   if (BK == 32 && BN > 64) BN = 64;
@@ -378,14 +532,5 @@ extern "C" int lecb_conv3x3_bf16(const void* x, const void* w, const float* bias
   if (st) return st;
   st = encode_tiled_2d(&tmB, w, static_cast<uint64_t>(Cout), static_cast<uint64_t>(9) * Cin, BN, BK);
   if (st) return st;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (BK == 64) {
-    switch (BN) {
-      case 32: return launch_gemm<32, 64, true>(tmA, tmB, p, s);
-      case 64: return launch_gemm<64, 64, true>(tmA, tmB, p, s);
-      case 128: return launch_gemm<128, 64, true>(tmA, tmB, p, s);
-      default: return launch_gemm<256, 64, true>(tmA, tmB, p, s);
-    }
-  }
-  return BN == 32 ? launch_gemm<32, 32, true>(tmA, tmB, p, s) : launch_gemm<64, 32, true>(tmA, tmB, p, s);
+  return dispatch<true>(BN, BK, tmA, tmB, p, static_cast<cudaStream_t>(stream));
 }

@@ -78,6 +78,29 @@ __device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap* m, uint64_
       : "memory");
 }
 
+// 2-D tiled store smem -> global (bulk async group of the issuing thread); OOB parts of the box are clipped.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk stores of this thread have finished READING shared memory
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// all but the most recent committed bulk store have finished reading shared memory
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// ... have completed entirely (writes visible)
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Byte offset of element (row, 16-byte chunk) inside a TMA-swizzled tile whose rows are `row_bytes` wide
+// (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B); tile base must be 1024-byte aligned.
+__device__ __forceinline__ uint32_t swizzled_chunk_offset(uint32_t row, uint32_t chunk, uint32_t row_bytes) {
+  const uint32_t off = row * row_bytes + chunk * 16u;
+  const uint32_t mask = row_bytes == 128 ? 7u : (row_bytes == 64 ? 3u : 1u);
+  return off ^ (((off >> 7) & mask) << 4);
+}
+
 // ------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ------------------------------------------------------------------------------------------

@@ -31,16 +31,36 @@ def _w3x3(w):
     return w.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()          # [Cout,3,3,Cin]
 
 
+def _pack_pixel_pairs(w, bias):
+    """Re-express a 3x3 / pad-1 conv over NHWC [B,H,W,Ci] as the same kind of conv over the *pixel-pair*
+    view [B,H,W/2,2*Ci] -> [B,H,W/2,2*Co] (identical memory).  Used for the Ci = 32 stem convolutions:
+    64-byte im2col rows and K steps of 32 leave the tensor pipe and the TMA unit badly under-fed; the pair
+    view gives 128-byte rows, BK = 64 and twice the MMA N at the price of 50 % structural zeros in the
+    (tiny) weight matrix.  w fp32 [Co,3,3,Ci] (ky,kx,ci) -> [2*Co,3,3,2*Ci]; output pixel 2j+o reads input
+    pixel 2j+o+kx-1 = pair j + floor((o+kx-1)/2), element (o+kx-1) mod 2."""
+    co, _, _, ci = w.shape
+    out = w.new_zeros((2, co, 3, 3, 2, ci))
+    for o in range(2):
+        for kx in range(3):
+            d = o + kx - 1
+            pt, ip = d // 2 + 1, d % 2
+            out[o, :, :, pt, ip, :] = w[:, :, kx, :]
+    return out.reshape(2 * co, 3, 3, 2 * ci), torch.cat([bias, bias]).contiguous()
+
+
 class VisualRN:
     def __init__(self, sd, layers, width, heads, embed_dim, device):
         sd = {k: v.detach().to(device) for k, v in sd.items() if k.startswith("visual.")}
         self.layers, self.width, self.heads, self.embed_dim, self.device = tuple(layers), width, heads, embed_dim, device
         w, b = _fold_bn(sd, "visual.conv1.weight", "visual.bn1")
         self.stem1 = (w.permute(1, 2, 3, 0).reshape(27, -1).contiguous(), b)          # fp32 [27,Cout]
-        w, b = _fold_bn(sd, "visual.conv2.weight", "visual.bn2")
-        self.stem2 = (_w3x3(w), b)
-        w, b = _fold_bn(sd, "visual.conv3.weight", "visual.bn3")
-        self.stem3 = (_w3x3(w), b)
+        self.stem_pairs = (width // 2) % 64 != 0          # Ci = 32 stem convs run on the pixel-pair view
+        for name, conv, bn in (("stem2", "visual.conv2.weight", "visual.bn2"), ("stem3", "visual.conv3.weight", "visual.bn3")):
+            w, b = _fold_bn(sd, conv, bn)
+            w = w.permute(0, 2, 3, 1).contiguous()                                    # [Co,3,3,Ci] fp32
+            if self.stem_pairs:
+                w, b = _pack_pixel_pairs(w, b)
+            setattr(self, name, (w.to(torch.bfloat16).contiguous(), b))
         self.blocks = []
         for li, nblk in enumerate(self.layers, start=1):
             for bi in range(nblk):
@@ -64,9 +84,15 @@ class VisualRN:
     def trunk(self, image):
         """image fp32 NCHW [B,3,H,W] (cuda) -> layer4 features, NHWC bf16 [B,H/32,W/32,Cv]."""
         x = ops.stem_conv1(image.contiguous(), *self.stem1)
+        b, h, w, c = x.shape
+        if self.stem_pairs:
+            x = x.view(b, h, w // 2, 2 * c)
+        from . import prof
+        prof.ALGO_FLOP_SCALE = 0.5 if self.stem_pairs else 1.0     # half of the packed MACs are structural zeros
         x = ops.conv3x3(x, *self.stem2)
         x = ops.conv3x3(x, *self.stem3)
-        x = ops.avgpool2x2(x)
+        prof.ALGO_FLOP_SCALE = 1.0
+        x = ops.avgpool2x2(x.view(b, h, w, -1))
         for blk in self.blocks:
             x = self._bottleneck(x, blk)
         return x

@@ -10,6 +10,21 @@ import torch
 from . import _lib
 
 
+# Set by callers whose launch carries structural zeros (pixel-pair packed stem convs: half the MACs of the
+# packed problem are zero weights): algorithmic FLOPs = launched FLOPs * ALGO_FLOP_SCALE.
+ALGO_FLOP_SCALE = 1.0
+
+
+def _sig(name, a):
+    if name == "lecb_gemm_bf16":
+        return f"M={a[6]} N={a[7]} K={a[8]} flags={a[9]} res={int(bool(a[3]))}"
+    if name == "lecb_conv3x3_bf16":
+        return f"B={a[4]} H={a[5]} W={a[6]} Cin={a[7]} Cout={a[8]}"
+    if name == "lecb_avgpool2x2":
+        return f"B={a[2]} H={a[3]} W={a[4]} C={a[5]}"
+    return ""
+
+
 def _work(name, a):
     """(flops, algorithmic HBM bytes) of one call from its C arguments."""
     if name == "lecb_gemm_bf16":
@@ -19,7 +34,7 @@ def _work(name, a):
         return 2.0 * m * n * k, 2.0 * (m * k + n * k) + m * n * (out_b + res_b)
     if name == "lecb_conv3x3_bf16":
         b, h, w, ci, co = a[4], a[5], a[6], a[7], a[8]
-        return 2.0 * b * h * w * co * 9 * ci, 2.0 * (b * h * w * (ci + co) + 9 * ci * co)
+        return 2.0 * b * h * w * co * 9 * ci * ALGO_FLOP_SCALE, 2.0 * (b * h * w * (ci + co) + 9 * ci * co)
     if name == "lecb_avgpool2x2":
         b, h, w, c = a[2], a[3], a[4], a[5]
         return 1.0 * b * h * w * c, 2.0 * b * h * w * c * 1.25
@@ -58,7 +73,7 @@ class KernelTimer:
                 r = _fn(*args)
                 e.record(stream)
                 fl, by = _work(_name, args)
-                self.records.append((_name, s, e, fl, by))
+                self.records.append((_name, s, e, fl, by, _sig(_name, args)))
                 return r
 
             setattr(lib, name, wrapped)
@@ -72,7 +87,7 @@ class KernelTimer:
 
     def summary(self, steps=1):
         agg = {}
-        for name, s, e, fl, by in self.records:
+        for name, s, e, fl, by, _ in self.records:
             d = agg.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
             d["ms"] += s.elapsed_time(e)
             d["flops"] += fl
@@ -82,3 +97,21 @@ class KernelTimer:
             for k in d:
                 d[k] /= steps
         return agg
+
+    def detail(self, steps=1):
+        """Per (entry point, shape) rows sorted by time: the launch list bench.py writes under profiles/."""
+        agg = {}
+        for name, s, e, fl, by, sig in self.records:
+            d = agg.setdefault((name, sig), {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+            d["ms"] += s.elapsed_time(e)
+            d["flops"] += fl
+            d["bytes"] += by
+            d["launches"] += 1
+        rows = []
+        for (name, sig), d in agg.items():
+            ms = d["ms"] / steps
+            rows.append({"op": name, "shape": sig, "ms_per_step": round(ms, 4), "launches_per_step": d["launches"] / steps,
+                         "tflops": round(d["flops"] / steps / max(ms, 1e-9) / 1e9, 1),
+                         "gbs": round(d["bytes"] / steps / max(ms, 1e-9) / 1e6, 1)})
+        rows.sort(key=lambda r: -r["ms_per_step"])
+        return rows
