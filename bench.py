@@ -198,6 +198,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step (configs[1]: 256)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-entry-point timing table (JSON) here")
+    ap.add_argument("--ncu-window", action="store_true",
+                    help="bracket the timed region with cudaProfilerStart/Stop (use with ncu --profile-from-start off)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -259,11 +261,15 @@ def main():
     launches0 = lecb200.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_begin = time.time()
+    if args.ncu_window:
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(args.steps):
         res = step(images)
     e1.record()
     barrier()
+    if args.ncu_window:
+        torch.cuda.profiler.stop()
     t_end = time.time()
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
