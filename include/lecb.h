@@ -125,6 +125,25 @@ int lecb_split_f16(const float* x, void* hi, void* lo, int64_t n, void* stream);
 int lecb_topk10(const float* sim, int64_t ld, int B, int N, float* out_val, int* out_idx, void* stream);
 int lecb_gather_mean10(const void* bank, int bank_is_f16, const int* idx, float* out, int B, int D, void* stream);
 
+/* ---- prompt-tuning backward (T:473-545 + loss.backward(); all CLIP weights frozen, T:763-765) ----
+ * data-gradient kernels only: the dgrad GEMMs are lecb_gemm_bf16 against pre-transposed weights. */
+int lecb_quick_gelu_fwd(const void* v, void* u, int64_t n, void* stream);                 /* bf16, M:202-204 */
+int lecb_quick_gelu_bwd(const void* du, const void* v, void* dv, int64_t n, void* stream);
+/* dx = dx_in + dLN/dx(dy); dy, x fp32 [rows,D]; outputs fp32 and/or bf16 (M:193-199, weights frozen) */
+int lecb_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                       const float* dx_in, float* dx_f32, void* dx_bf16, int64_t rows, int D, void* stream);
+/* causal attention backward: qkv, dqkv bf16 [N*L,3W]; dout bf16 [N*L,W]; L <= 96 (M:221-223) */
+int lecb_causal_attn_bwd(const void* qkv, const void* dout, void* dqkv, int N, int L, int W, int heads, void* stream);
+/* backward of y = x/||x|| on fp32 rows (T:487-488,503) */
+int lecb_l2norm_bwd(const float* x, const float* dy, float* dx, int64_t rows, int D, void* stream);
+/* gradient of logits_local w.r.t. the raw dot products (same operands as lecb_head_aggregate; T:496-514) */
+int lecb_head_aggregate_bwd(const float* dots, int ldn, const float* row_sumsq, const uint8_t* row_mask,
+                            const float* grad_local, float* d_dots, int B, int P, int K, int n_txt, float logit_scale,
+                            float spatial_scale, void* stream);
+/* out[J,D] (+)= alpha * sum_r a[r,J] * b[r,D]: prompt-feature gradients (a fp32 [R,lda], b bf16|fp32 [R,D]) */
+int lecb_tn_gemm_small(const float* a, int lda, const void* b, int b_is_bf16, float* out, int R, int J, int D,
+                       float alpha, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,6 +39,16 @@ SIGNATURES = {
     "lecb_split_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
     "lecb_topk10": (c_int, [c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "lecb_gather_mean10": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "lecb_quick_gelu_fwd": (c_int, [c_void_p, c_void_p, c_i64, c_void_p]),
+    "lecb_quick_gelu_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
+    "lecb_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_i64, c_int, c_void_p]),
+    "lecb_causal_attn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "lecb_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
+    "lecb_head_aggregate_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                        c_int, c_float, c_float, c_void_p]),
+    "lecb_tn_gemm_small": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_int,
+                                   c_void_p]),
 }
 
 EPI_RELU, EPI_QUICKGELU, EPI_OUT_F32, EPI_RES_F32, GEMM_F16_OPERANDS = 1, 2, 4, 8, 16

@@ -149,6 +149,55 @@ class TextTower:
         self.ln_final = (g("ln_final.weight").float().contiguous(), g("ln_final.bias").float().contiguous())
         self.text_proj_t = g("text_projection").t().to(torch.bfloat16).contiguous()      # [D, W] K-major
 
+    # ------------------------------------------------------------------ prompt-tuning (fwd with saves + bwd)
+    def _dgrad_weights(self):
+        """Transposed copies of the frozen weights for the data-gradient GEMMs (built on first use)."""
+        if getattr(self, "_wt", None) is None:
+            self._wt = [{k: blk[k][0].t().contiguous() for k in ("qkv", "out", "fc", "proj")} for blk in self.blocks]
+            self._text_proj = self.text_proj_t.t().contiguous()              # [W, D]: W-operand of d_rows = dT @ P^T
+        return self._wt
+
+    def forward_train(self, x, eot_index):
+        """Like forward(x, eot_index) but keeps what the backward needs.  x fp32 [N,L,W] -> (T_raw fp32 [N,D], saved)."""
+        n, l, w = x.shape
+        x = x.reshape(n * l, w).contiguous()
+        saved = {"n": n, "l": l, "w": w, "eot": eot_index, "layers": []}
+        for blk in self.blocks:
+            h, _, m1, r1 = ops.layernorm(x, *blk["ln1"], save_stats=True)
+            qkv = ops.gemm(h, *blk["qkv"])
+            a = ops.causal_attn(qkv, n, l, w, self.heads)
+            x1 = ops.gemm_f32res(a, *blk["out"], x)
+            h, _, m2, r2 = ops.layernorm(x1, *blk["ln2"], save_stats=True)
+            v = ops.gemm(h, *blk["fc"])                         # pre-activation kept for the QuickGELU backward
+            u = ops.quick_gelu_fwd(v)
+            x2 = ops.gemm_f32res(u, *blk["proj"], x1)
+            saved["layers"].append((x, m1, r1, qkv, x1, m2, r2, v))
+            x = x2
+        h, _, mf, rf = ops.layernorm(x, *self.ln_final, save_stats=True)
+        saved["final"] = (x, mf, rf)
+        rows = h.view(n, l, w)[torch.arange(n, device=h.device), eot_index].contiguous()
+        return ops.gemm(rows, self.text_proj_t, out_f32=True), saved
+
+    def backward(self, saved, d_out):
+        """d_out fp32 [N,D] = dL/dT_raw  ->  dL/dx fp32 [N,L,W] (x = prompt embeddings + positional embedding)."""
+        wt = self._dgrad_weights()
+        n, l, w = saved["n"], saved["l"], saved["w"]
+        d_rows = ops.gemm(d_out.to(torch.bfloat16).contiguous(), self._text_proj, out_f32=True)      # [N,W]
+        dh = torch.zeros((n, l, w), device=d_out.device, dtype=torch.float32)
+        dh[torch.arange(n, device=d_out.device), saved["eot"]] = d_rows                               # only EOT rows see the loss
+        xf, mf, rf = saved["final"]
+        dx, dxb = ops.layernorm_bwd(dh.view(n * l, w), xf, self.ln_final[0], mf, rf)
+        for blk, t, (x0, m1, r1, qkv, x1, m2, r2, v) in zip(reversed(self.blocks), reversed(wt), reversed(saved["layers"])):
+            du = ops.gemm(dxb, t["proj"])                                  # [M,4W] bf16
+            dv = ops.quick_gelu_bwd(du, v)
+            dh2 = ops.gemm(dv, t["fc"], out_f32=True)
+            dx1, dx1b = ops.layernorm_bwd(dh2, x1, blk["ln2"][0], m2, r2, dx_in=dx)
+            da = ops.gemm(dx1b, t["out"])
+            dqkv = ops.causal_attn_bwd(qkv, da, n, l, w, self.heads)
+            dh1 = ops.gemm(dqkv, t["qkv"], out_f32=True)
+            dx, dxb = ops.layernorm_bwd(dh1, x0, blk["ln1"][0], m1, r1, dx_in=dx1)
+        return dx.view(n, l, w)
+
     def forward(self, x, eot_index=None, sequence=False):
         """T:82-101.  x fp32 [N,L,W] = embeddings + positional embedding.  -> fp32 [N,D] at `eot_index`
         (int64 [N]) or fp32 [N,L,D] when `sequence`."""

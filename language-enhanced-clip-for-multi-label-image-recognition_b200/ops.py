@@ -198,3 +198,79 @@ def ranking_fwd_bwd(logits, targets, scale=2.0, margin=1.0, want_grad=True):
     check(lib.lecb_ranking_fwd_bwd(_ptr(logits), _ptr(targets), _ptr(grad), _ptr(loss), b, k, float(scale),
                                    float(margin), _stream()), "lecb_ranking_fwd_bwd")
     return loss, grad
+
+
+# ---------------------------------------------------------------------------------------------
+# prompt-tuning backward ops
+# ---------------------------------------------------------------------------------------------
+def quick_gelu_fwd(v):
+    _need(v, torch.bfloat16, "v")
+    u = torch.empty_like(v)
+    check(lib.lecb_quick_gelu_fwd(_ptr(v), _ptr(u), v.numel(), _stream()), "lecb_quick_gelu_fwd")
+    return u
+
+
+def quick_gelu_bwd(du, v):
+    _need(du, torch.bfloat16, "du")
+    _need(v, torch.bfloat16, "v")
+    dv = torch.empty_like(v)
+    check(lib.lecb_quick_gelu_bwd(_ptr(du), _ptr(v), _ptr(dv), v.numel(), _stream()), "lecb_quick_gelu_bwd")
+    return dv
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx_in=None, want_bf16=True):
+    """-> (dx fp32, dx bf16|None) with dx = dx_in + LN'(dy)."""
+    _need(dy, torch.float32, "dy")
+    _need(x, torch.float32, "x")
+    d = x.shape[-1]
+    rows = x.numel() // d
+    dxf = torch.empty_like(x)
+    dxb = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    check(lib.lecb_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx_in), _ptr(dxf),
+                                 _ptr(dxb), rows, d, _stream()), "lecb_layernorm_bwd")
+    return dxf, dxb
+
+
+def causal_attn_bwd(qkv, dout, n, l, w, heads):
+    _need(qkv, torch.bfloat16, "qkv")
+    _need(dout, torch.bfloat16, "dout")
+    dqkv = torch.empty_like(qkv)
+    check(lib.lecb_causal_attn_bwd(_ptr(qkv), _ptr(dout), _ptr(dqkv), n, l, w, heads, _stream()), "lecb_causal_attn_bwd")
+    return dqkv
+
+
+def l2norm_bwd(x, dy):
+    _need(x, torch.float32, "x")
+    _need(dy, torch.float32, "dy")
+    d = x.shape[-1]
+    dx = torch.empty_like(x)
+    check(lib.lecb_l2norm_bwd(_ptr(x), _ptr(dy), _ptr(dx), x.numel() // d, d, _stream()), "lecb_l2norm_bwd")
+    return dx
+
+
+def head_aggregate_bwd(dots, grad_local, b, p, k, n_txt, row_sumsq=None, row_mask=None, logit_scale=4.0,
+                       spatial_scale=50.0):
+    _need(dots, torch.float32, "dots")
+    _need(grad_local, torch.float32, "grad_local")
+    d_dots = torch.empty_like(dots)
+    if dots.shape[-1] > n_txt * k:
+        d_dots.zero_()
+    check(lib.lecb_head_aggregate_bwd(_ptr(dots), dots.shape[-1], _ptr(row_sumsq), _ptr(row_mask), _ptr(grad_local),
+                                      _ptr(d_dots), b, p, k, n_txt, float(logit_scale), float(spatial_scale), _stream()),
+          "lecb_head_aggregate_bwd")
+    return d_dots
+
+
+def tn_gemm_small(a, b, j, out=None, alpha=1.0, accumulate=False):
+    """out[J,D] (+)= alpha * a[:, :J]^T @ b;  a fp32 [R,lda], b bf16|fp32 [R,D]."""
+    _need(a, torch.float32, "a")
+    assert b.is_cuda and b.is_contiguous() and b.dtype in (torch.bfloat16, torch.float32)
+    r, lda = a.shape
+    d = b.shape[1]
+    assert b.shape[0] == r
+    if out is None:
+        out = torch.empty((j, d), device=a.device, dtype=torch.float32)
+        assert not accumulate
+    check(lib.lecb_tn_gemm_small(_ptr(a), lda, _ptr(b), int(b.dtype == torch.bfloat16), _ptr(out), r, j, d, float(alpha),
+                                 int(accumulate), _stream()), "lecb_tn_gemm_small")
+    return out

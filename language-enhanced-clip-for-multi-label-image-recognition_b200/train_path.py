@@ -1,0 +1,133 @@
+"""Text-only prompt-tuning forward/backward (reference: DenseCLIP.forward(None, captions), T:473-545).
+
+The caption branch (text-as-image features) is frozen and runs without saving anything.  The prompt
+branch — 2 or 3 x K prompt sequences through the text tower, L2 normalisation, the caption-by-class
+contraction, winner-take-all + token-softmax aggregation and the global logits — is one
+torch.autograd.Function whose backward is hand-written kernels end to end; torch autograd only carries the
+gradient from the [K,77,W] prompt embeddings back into `ctx` / `ctx_double` / `ctx_evidence` through the
+reference's own `torch.cat` / `expand` in PromptLearner.forward (T:199-242)."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+def _cfg(model, path, default=None):
+    from .dense_clip import _cfg_get
+    return _cfg_get(model.cfg, path, default)
+
+
+class _DualPromptHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pack, logit_scale_t, *prompts):
+        tower, tok_prompts, local, ssq, mask, g_unit, b, l, logit_scale, spatial = pack
+        n_txt = len(prompts)
+        k = prompts[0].shape[0]
+        x = (torch.cat([p.detach().float() for p in prompts], 0) + tower.pos).contiguous()        # [n*K, 77, W]
+        eot = tok_prompts.to(x.device).argmax(dim=-1).repeat(n_txt)
+        t_raw, saved = tower.forward_train(x, eot)                                                # [n*K, D] fp32
+        t_hat = ops.l2norm_rows(t_raw)
+        pad = (-t_hat.shape[0]) % 8
+        t_cat = t_hat if not pad else torch.cat([t_hat, t_hat.new_zeros((pad, t_hat.shape[1]))], 0)
+        dots = ops.gemm(local, t_cat.to(torch.bfloat16).contiguous(), out_f32=True)               # [B*L, n*K(+pad)]
+        logits_local, _, _ = ops.head_aggregate(dots, b, l, k, n_txt, row_sumsq=ssq, row_mask=mask,
+                                                logit_scale=logit_scale, spatial_scale=spatial, want_maps=False)
+        t_pos = t_hat[:k].contiguous()
+        logits = ops.global_logits(g_unit, t_pos, None, logit_scale)
+        ctx.pack = (tower, saved, t_raw, dots, local, ssq, mask, g_unit, b, l, k, n_txt, logit_scale, spatial)
+        ctx.save_for_backward(logits, logits_local)
+        ctx.learn_scale = logit_scale_t is not None and logit_scale_t.requires_grad
+        return logits, logits_local, t_pos
+
+    @staticmethod
+    def backward(ctx, d_logits, d_local, d_tpos):
+        tower, saved, t_raw, dots, local, ssq, mask, g_unit, b, l, k, n_txt, logit_scale, spatial = ctx.pack
+        logits, logits_local = ctx.saved_tensors
+        dev = dots.device
+        d_logits = torch.zeros((b, k), device=dev) if d_logits is None else d_logits.float().contiguous()
+        d_local = torch.zeros((b, k), device=dev) if d_local is None else d_local.float().contiguous()
+        d_dots = ops.head_aggregate_bwd(dots, d_local, b, l, k, n_txt, row_sumsq=ssq, row_mask=mask,
+                                        logit_scale=logit_scale, spatial_scale=spatial)
+        d_that = ops.tn_gemm_small(d_dots, local, n_txt * k)                                       # [n*K, D]
+        ops.tn_gemm_small(d_logits, g_unit, k, out=d_that, alpha=logit_scale, accumulate=True)     # rows [0,K) = positive prompts
+        if d_tpos is not None:
+            d_that[:k] += d_tpos.float()
+        d_traw = ops.l2norm_bwd(t_raw, d_that)
+        dx = tower.backward(saved, d_traw)                                                          # [n*K, 77, W]
+        grads = tuple(dx[i * k:(i + 1) * k] for i in range(n_txt))
+        d_scale = None
+        if ctx.learn_scale:          # logits = exp(temperature) * (...)  =>  dL/dtemperature = sum(dlogits * logits)
+            d_scale = (d_logits * logits).sum() + (d_local * logits_local).sum()
+        ctx.pack = None
+        return (None, d_scale) + grads
+
+
+@torch.no_grad()
+def _caption_branch(model, captions):
+    """T:474-477,485-486,491: per-token caption features (frozen path)."""
+    tw = model.text_encoder.tower()
+    b, l = captions.shape
+    x = (tw.tok[captions] + tw.pos).contiguous()
+    n, _, w = x.shape
+    xs = x.reshape(n * l, w)
+    for blk in tw.blocks:
+        h, _, _, _ = ops.layernorm(xs, *blk["ln1"])
+        qkv = ops.gemm(h, *blk["qkv"])
+        a = ops.causal_attn(qkv, n, l, w, tw.heads)
+        xs = ops.gemm_f32res(a, *blk["out"], xs)
+        h, _, _, _ = ops.layernorm(xs, *blk["ln2"])
+        u = ops.gemm(h, *blk["fc"], quick_gelu=True)
+        xs = ops.gemm_f32res(u, *blk["proj"], xs)
+    h, _, _, _ = ops.layernorm(xs, *tw.ln_final)
+    ssq = torch.zeros((b * l,), device=x.device, dtype=torch.float32)
+    local = ops.gemm(h, tw.text_proj_t, row_sumsq=ssq)                       # bf16 [B*L, D] + row sum of squares
+    eot = captions.argmax(dim=-1)
+    g = local.view(b, l, -1)[torch.arange(b, device=x.device), eot].float().contiguous()
+    g_unit = ops.l2norm_rows(g)
+    mask = (captions == 0).to(torch.uint8).reshape(-1).contiguous()          # token id 0 = padding (T:491)
+    return local, ssq, mask, g_unit
+
+
+def _prompt_logits_nograd(model, learner, local, ssq, mask, g_unit, b, l, logit_scale, spatial, use_evidence):
+    """EMA twin branch (T:516-541): same math, no saves."""
+    prompts, prompts_double, prompts_evidence, _, _, _ = learner()
+    tok = model.tokenized_prompts
+    feats = [ops.l2norm_rows(model.text_encoder(p, tok)) for p in
+             ((prompts, prompts_double, prompts_evidence) if use_evidence else (prompts, prompts_double))]
+    k = feats[0].shape[0]
+    cat = torch.cat(feats, 0)
+    pad = (-cat.shape[0]) % 8
+    if pad:
+        cat = torch.cat([cat, cat.new_zeros((pad, cat.shape[1]))], 0)
+    dots = ops.gemm(local, cat.to(torch.bfloat16).contiguous(), out_f32=True)
+    logits_local, _, _ = ops.head_aggregate(dots, b, l, k, len(feats), row_sumsq=ssq, row_mask=mask,
+                                            logit_scale=logit_scale, spatial_scale=spatial, want_maps=False)
+    return ops.global_logits(g_unit, feats[0], None, logit_scale), logits_local
+
+
+def forward_train(model, captions):
+    """-> (logits_, logits_local, image_features [L,B,D], text_features [K,D], logits_m_|None, logits_local_m|None)."""
+    use_evidence = bool(_cfg(model, "TRAINER.Caption.use_evidence", False))
+    if bool(_cfg(model, "TRAIN.IF_LEARN_spatial_SCALE", False)):
+        raise NotImplementedError("lecb200: a learnable spatial scale is not supported on the prompt-tuning path "
+                                  "(every shipped config fixes TRAIN.spatial_SCALE_text)")
+    captions = captions.to(model.text_encoder.positional_embedding.device)
+    b, l = captions.shape
+    local, ssq, mask, g_unit = _caption_branch(model, captions)
+    prompts, prompts_double, prompts_evidence, temperature, spatial_T, _ = model.prompt_learner()
+    learn = bool(_cfg(model, "TRAIN.IF_LEARN_SCALE", False))
+    logit_scale = float(temperature.exp()) if learn else 4.0
+    spatial = float(_cfg(model, "TRAIN.spatial_SCALE_text"))
+    pack = (model.text_encoder.tower(), model.tokenized_prompts, local, ssq, mask, g_unit, b, l, logit_scale, spatial)
+    plist = (prompts, prompts_double, prompts_evidence) if use_evidence else (prompts, prompts_double)
+    logits, logits_local, text_features = _DualPromptHead.apply(pack, temperature if learn else None, *plist)
+    with torch.no_grad():
+        image_features = ops.l2norm_rows(local, out_dtype=torch.float32).view(b, l, -1).permute(1, 0, 2)
+    logits_m, logits_local_m = None, None
+    if bool(_cfg(model, "TRAIN.ema", False)):
+        with torch.no_grad():
+            model._momentum_update()
+            logits_m, logits_local_m = _prompt_logits_nograd(model, model.prompt_learner_m, local, ssq, mask, g_unit, b, l,
+                                                             logit_scale, spatial, use_evidence)
+    return logits, logits_local, image_features, text_features, logits_m, logits_local_m
