@@ -1,0 +1,77 @@
+"""Host-side multi-rank logic on CPU (gloo, world_size 2): batch sharding, packed-logits all-gather order,
+prompt-gradient averaging with DDP semantics (T:786-787).  The GPU path uses the same functions over NCCL."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, fn_name):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        globals()[fn_name](rank, world)
+    finally:
+        dist.destroy_process_group()
+
+
+def _load_dist_module():
+    # loaded by path: the package __init__ needs liblecb.so, this module is pure torch.distributed plumbing
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "language-enhanced-clip-for-multi-label-image-recognition_b200", "dist.py")
+    spec = importlib.util.spec_from_file_location("_lecb200_dist", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _check_gather(rank, world):
+    D = _load_dist_module()
+    n_total, k = 10, 6
+    full = torch.arange(n_total * k, dtype=torch.float32).view(n_total, k)
+    lo, hi = D.shard_range(n_total, rank, world)
+    assert hi - lo == n_total // world
+    lg, ll = D.all_gather_logits(full[lo:hi].clone(), -full[lo:hi].clone())
+    assert torch.equal(lg, full) and torch.equal(ll, -full)
+
+
+def _check_grad_mean(rank, world):
+    D = _load_dist_module()
+    torch.manual_seed(0)
+    p1 = torch.nn.Parameter(torch.zeros(3, 4))
+    p2 = torch.nn.Parameter(torch.zeros(5))         # "unused" parameter: grad None on every rank
+    p3 = torch.nn.Parameter(torch.zeros(()))
+    p1.grad = torch.full((3, 4), float(rank + 1))
+    p3.grad = torch.tensor(float(10 * (rank + 1))) if rank == 0 else None
+    D.allreduce_mean_grads([p1, p2, p3])
+    assert torch.allclose(p1.grad, torch.full((3, 4), sum(range(1, world + 1)) / world))
+    assert torch.equal(p2.grad, torch.zeros(5))
+    assert torch.allclose(p3.grad, torch.tensor(10.0 / world))
+
+
+@pytest.mark.parametrize("fn", ["_check_gather", "_check_grad_mean"])
+def test_two_rank_gloo(fn):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), fn), nprocs=world, join=True)
+
+
+def test_shard_range_covers_everything():
+    D = _load_dist_module()
+    for n in (0, 1, 7, 256, 1000):
+        for world in (1, 2, 3, 8):
+            spans = [D.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
