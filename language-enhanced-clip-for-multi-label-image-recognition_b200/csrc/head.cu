@@ -32,25 +32,44 @@ head_aggregate_kernel(const float* __restrict__ dots, int ldn, const float* __re
     ssum[j] = 0.f;
     acc[j] = 0.f;
   }
-  for (int p = warp; p < P; p += kAggWarps) {
+  // Software-pipelined row loop: the raw dot products of the NEXT row of this warp are requested before the
+  // shuffle / exp chain of the current row starts, so the DRAM latency hides under the reductions.
+  auto live_row = [&](int p) { return p < P && !(row_mask != nullptr && row_mask[static_cast<int64_t>(b) * P + p]); };
+  auto fetch = [&](int p, float (&rp)[kJ], float (&rneg)[kJ], float (&re)[kJ], float& rn) {
     const int64_t row = static_cast<int64_t>(b) * P + p;
-    if (row_mask != nullptr && row_mask[row]) continue;   // padded token: weight underflows to exactly 0 (T:491-498)
-    const float rn = row_sumsq != nullptr ? rsqrtf(__ldg(row_sumsq + row)) : 1.0f;
     const float* dp = dots + row * ldn;
-    float pos[kJ], neg[kJ], evi[kJ];
-    float mx = -INFINITY;
+    rn = row_sumsq != nullptr ? __ldg(row_sumsq + row) : 1.0f;
 #pragma unroll
     for (int j = 0; j < kJ; ++j) {
       const int k = lane + 32 * j;
       if (k < K) {
-        pos[j] = __ldg(dp + k) * rn;
-        neg[j] = __ldg(dp + K + k) * rn;
-        evi[j] = evidence ? __ldg(dp + 2 * K + k) * rn : 0.f;
-        mx = fmaxf(mx, neg[j]);
+        rp[j] = __ldcs(dp + k);
+        rneg[j] = __ldcs(dp + K + k);
+        re[j] = evidence ? __ldcs(dp + 2 * K + k) : 0.f;
       } else {
-        pos[j] = neg[j] = evi[j] = 0.f;
+        rp[j] = rneg[j] = re[j] = 0.f;
       }
     }
+  };
+  int p = warp;
+  while (p < P && !live_row(p)) p += kAggWarps;       // padded token: weight underflows to exactly 0 (T:491-498)
+  float npos[kJ], nneg[kJ], nevi[kJ], nrn = 1.f;
+  if (p < P) fetch(p, npos, nneg, nevi, nrn);
+  while (p < P) {
+    float pos[kJ], neg[kJ], evi[kJ];
+    const float rn = row_sumsq != nullptr ? rsqrtf(nrn) : 1.0f;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kJ; ++j) {
+      pos[j] = npos[j] * rn;
+      neg[j] = nneg[j] * rn;
+      evi[j] = nevi[j] * rn;
+      if (lane + 32 * j < K) mx = fmaxf(mx, neg[j]);
+    }
+    const int pcur = p;
+    p += kAggWarps;
+    while (p < P && !live_row(p)) p += kAggWarps;
+    if (p < P) fetch(p, npos, nneg, nevi, nrn);          // prefetch the next live row
     float t[kJ];
     if (evidence) {
       mx = warp_max(mx);
@@ -69,7 +88,7 @@ head_aggregate_kernel(const float* __restrict__ dots, int ldn, const float* __re
         den += z[j];
       }
       den = warp_sum(den);
-      const float inv = 1.0f / den;
+      const float inv = __fdividef(1.0f, den);
 #pragma unroll
       for (int j = 0; j < kJ; ++j) {
         neg[j] *= z[j] * inv;
@@ -80,14 +99,14 @@ head_aggregate_kernel(const float* __restrict__ dots, int ldn, const float* __re
       for (int j = 0; j < kJ; ++j) t[j] = spatial_scale * neg[j];
     }
     if (neg_map != nullptr) {
-      float* np = neg_map + (static_cast<int64_t>(p) * B + b) * K;
-      float* pp = pos_map + (static_cast<int64_t>(p) * B + b) * K;
+      float* np = neg_map + (static_cast<int64_t>(pcur) * B + b) * K;
+      float* pp = pos_map + (static_cast<int64_t>(pcur) * B + b) * K;
 #pragma unroll
       for (int j = 0; j < kJ; ++j) {
         const int k = lane + 32 * j;
         if (k < K) {
-          np[k] = neg[j];
-          pp[k] = pos[j];
+          __stcs(np + k, neg[j]);
+          __stcs(pp + k, pos[j]);
         }
       }
     }

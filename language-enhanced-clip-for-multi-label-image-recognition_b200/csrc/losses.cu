@@ -20,48 +20,77 @@ __device__ __forceinline__ float pow_gamma(float base, float g) {
   return powf(base, g);
 }
 
+template <bool kFastGamma>
 __device__ __forceinline__ void asl_elem(float x, float y, const AslParams& p, float& loss, float& grad) {
-  const float s = 1.0f / (1.0f + __expf(-x));
+  const float e = __expf(-x);
+  const float s = __fdividef(1.0f, 1.0f + e);
   const float sneg_raw = 1.0f - s + p.clip;
   const bool clipped = (p.clip > 0.f) && (sneg_raw > 1.0f);
   const float sneg = (p.clip > 0.f) ? fminf(sneg_raw, 1.0f) : (1.0f - s);
-  const float ypos = y > p.thresh_pos ? 1.f : 0.f;
-  const float yneg = y < p.thresh_neg ? 1.f : 0.f;
-  const float lp = __logf(fmaxf(s, p.eps));
-  const float ln = __logf(fmaxf(sneg, p.eps));
-  float w = 1.0f;
-  if (p.gamma_neg > 0.f || p.gamma_pos > 0.f) {
-    const float pt = s * ypos + sneg * yneg;
-    w = pow_gamma(1.0f - pt, p.gamma_pos * ypos + p.gamma_neg * yneg);
+  const bool pos = y > p.thresh_pos, neg = y < p.thresh_neg;
+  // only one of the two log terms is live for binary targets: evaluate a single log on the selected probability
+  const float lp = pos ? __logf(fmaxf(s, p.eps)) : 0.f;
+  const float ln = neg ? __logf(fmaxf(sneg, p.eps)) : 0.f;
+  const float ypos = pos ? 1.f : 0.f, yneg = neg ? 1.f : 0.f;
+  const float pt = s * ypos + sneg * yneg;
+  const float base = 1.0f - pt;
+  float w;
+  if (kFastGamma) {                       // gamma_pos = 1, gamma_neg = 2 (ASL_loss / dualcoop_loss, U:179,188)
+    w = pos ? base : 1.0f;
+    w = neg ? (pos ? w * base * base : base * base) : w;
+  } else {
+    w = (p.gamma_neg > 0.f || p.gamma_pos > 0.f) ? pow_gamma(base, p.gamma_pos * ypos + p.gamma_neg * yneg) : 1.0f;
   }
-  loss = -(ypos * lp + yneg * ln) * w * p.inv_denom;
-  const float dpos = (s >= p.eps) ? (1.0f - s) : 0.f;                              // d log(sigmoid)/dx
-  const float dneg = (!clipped && sneg >= p.eps) ? (-s * (1.0f - s) / sneg) : 0.f;  // d log(1-s+clip)/dx
-  grad = -(ypos * dpos + yneg * dneg) * w * p.inv_denom;
+  loss = -(lp + ln) * w * p.inv_denom;
+  const float dpos = (pos && s >= p.eps) ? (1.0f - s) : 0.f;                              // d log(sigmoid)/dx
+  const float dneg = (neg && !clipped && sneg >= p.eps) ? __fdividef(-s * (1.0f - s), sneg) : 0.f;   // d log(1-s+clip)/dx
+  grad = -(dpos + dneg) * w * p.inv_denom;
 }
 
+template <bool kFastGamma>
 __global__ void __launch_bounds__(256)
 asl_fwd_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ grad,
                    float* __restrict__ loss_out, int64_t n, AslParams p) {
   float acc = 0.f;
   const int64_t nvec = n / 4;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
-    const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + i);
-    const float4 yv = __ldg(reinterpret_cast<const float4*>(y) + i);
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  const float4* y4 = reinterpret_cast<const float4*>(y);
+  int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // two independent 128-bit load pairs in flight per thread
+  for (; i + stride < nvec; i += 2 * stride) {
+    const float4 xa = __ldcs(x4 + i), ya = __ldcs(y4 + i);
+    const float4 xb = __ldcs(x4 + i + stride), yb = __ldcs(y4 + i + stride);
+    float4 ga, gb;
+    float l;
+    asl_elem<kFastGamma>(xa.x, ya.x, p, l, ga.x); acc += l;
+    asl_elem<kFastGamma>(xa.y, ya.y, p, l, ga.y); acc += l;
+    asl_elem<kFastGamma>(xa.z, ya.z, p, l, ga.z); acc += l;
+    asl_elem<kFastGamma>(xa.w, ya.w, p, l, ga.w); acc += l;
+    asl_elem<kFastGamma>(xb.x, yb.x, p, l, gb.x); acc += l;
+    asl_elem<kFastGamma>(xb.y, yb.y, p, l, gb.y); acc += l;
+    asl_elem<kFastGamma>(xb.z, yb.z, p, l, gb.z); acc += l;
+    asl_elem<kFastGamma>(xb.w, yb.w, p, l, gb.w); acc += l;
+    if (grad) {
+      __stcs(reinterpret_cast<float4*>(grad) + i, ga);
+      __stcs(reinterpret_cast<float4*>(grad) + i + stride, gb);
+    }
+  }
+  for (; i < nvec; i += stride) {
+    const float4 xv = __ldcs(x4 + i), yv = __ldcs(y4 + i);
     float4 g;
     float l;
-    asl_elem(xv.x, yv.x, p, l, g.x); acc += l;
-    asl_elem(xv.y, yv.y, p, l, g.y); acc += l;
-    asl_elem(xv.z, yv.z, p, l, g.z); acc += l;
-    asl_elem(xv.w, yv.w, p, l, g.w); acc += l;
-    if (grad) reinterpret_cast<float4*>(grad)[i] = g;
+    asl_elem<kFastGamma>(xv.x, yv.x, p, l, g.x); acc += l;
+    asl_elem<kFastGamma>(xv.y, yv.y, p, l, g.y); acc += l;
+    asl_elem<kFastGamma>(xv.z, yv.z, p, l, g.z); acc += l;
+    asl_elem<kFastGamma>(xv.w, yv.w, p, l, g.w); acc += l;
+    if (grad) __stcs(reinterpret_cast<float4*>(grad) + i, g);
   }
-  for (int64_t i = nvec * 4 + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+  for (int64_t t = nvec * 4 + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += stride) {
     float l, g;
-    asl_elem(x[i], y[i], p, l, g);
+    asl_elem<kFastGamma>(x[t], y[t], p, l, g);
     acc += l;
-    if (grad) grad[i] = g;
+    if (grad) grad[t] = g;
   }
   __shared__ float s_part[8];
   acc = warp_sum(acc);
@@ -129,7 +158,10 @@ extern "C" int lecb_asl_fwd_bwd(const float* logits, const float* targets, float
   const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
   if (blocks < 1) blocks = 1;
   if (blocks > cap) blocks = cap;
-  asl_fwd_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(logits, targets, grad, loss, n, p);
+  if (gamma_pos == 1.0f && gamma_neg == 2.0f)
+    asl_fwd_bwd_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, s>>>(logits, targets, grad, loss, n, p);
+  else
+    asl_fwd_bwd_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, s>>>(logits, targets, grad, loss, n, p);
   count_launch();
   return check_launch("asl_fwd_bwd_kernel");
 }

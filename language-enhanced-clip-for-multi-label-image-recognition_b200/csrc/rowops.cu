@@ -13,7 +13,7 @@ template <int CO>
 __global__ void __launch_bounds__(128) stem_conv1_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias,
                                                          __nv_bfloat16* __restrict__ out, int B, int H, int W) {
-  __shared__ float sw[27 * CO];   // [tap(ci,ky,kx)][co]
+  __shared__ __align__(16) float sw[27 * CO];   // [tap(ci,ky,kx)][co]
   __shared__ float sb[CO];
   for (int i = threadIdx.x; i < 27 * CO; i += blockDim.x) sw[i] = w[i];
   for (int i = threadIdx.x; i < CO; i += blockDim.x) sb[i] = bias[i];
@@ -47,8 +47,13 @@ __global__ void __launch_bounds__(128) stem_conv1_kernel(const float* __restrict
     for (int j = 0; j < 8; ++j) acc[j] = sb[c0 + j];
 #pragma unroll
     for (int t = 0; t < 27; ++t) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(in[t], sw[t * CO + c0 + j], acc[j]);
+      // weights are warp-uniform: two 128-bit shared-memory broadcasts feed 8 FMAs
+      const float4 w0 = *reinterpret_cast<const float4*>(&sw[t * CO + c0]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&sw[t * CO + c0 + 4]);
+      acc[0] = fmaf(in[t], w0.x, acc[0]); acc[1] = fmaf(in[t], w0.y, acc[1]);
+      acc[2] = fmaf(in[t], w0.z, acc[2]); acc[3] = fmaf(in[t], w0.w, acc[3]);
+      acc[4] = fmaf(in[t], w1.x, acc[4]); acc[5] = fmaf(in[t], w1.y, acc[5]);
+      acc[6] = fmaf(in[t], w1.z, acc[6]); acc[7] = fmaf(in[t], w1.w, acc[7]);
     }
     uint4 u;
     u.x = pack_bf16(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
