@@ -21,6 +21,7 @@
 // warp 9 MMA issuer + TMEM owner, warp 10 epilogue DMA.  mbarrier rings: smem full/empty (operands),
 // TMEM full/empty (accumulators), staging free/full (epilogue blocks).
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "lecb_common.cuh"
 #include "lecb_host.h"
@@ -39,10 +40,11 @@ struct GemmCfg {
   static constexpr int kCCols = BN >= 64 ? 64 : BN;               // columns per staged epilogue block
   static constexpr int kCBlocks = BN / kCCols;
   static constexpr int kCBytes = kTileM * kCCols * 2;             // 16 KB (8 KB for BN = 32)
-  static constexpr int kStagesRaw = (227 * 1024 - NB * kCBytes - 2048) / kStageBytes;
+  static constexpr int kStagesRaw = (227 * 1024 - NB * kCBytes - 2560) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);
-  static constexpr int kSmemBytes = kStages * kStageBytes + NB * kCBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + NB * kCBytes + 1024 /*align slack*/ + 512 /*barriers*/;
+  static_assert(kStages >= 2, "need at least a double-buffered operand ring");
 };
 
 struct GemmParams {
@@ -57,6 +59,8 @@ struct GemmParams {
   int num_n_tiles;
   unsigned flags;
   int staged;        // bf16 output through smem + TMA store
+  int b_resident;    // all K blocks of the (single) W tile stay in smem for the CTA's lifetime; A ring gets the rest
+  int res_stages;    // A-ring depth in b_resident mode
   // conv mode
   int H, W, kb_per_tap;
 };
@@ -81,7 +85,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tempty = tfull + 2;
   uint64_t* cfree = tempty + 2;
   uint64_t* cfull = cfree + NB;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cfull + NB);
+  uint64_t* bres = cfull + NB;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres + 1);
+  // b_resident: [ W k-blocks (num_kb * kBBytes) | A ring (res_stages * kABytes) ] inside the operand region
+  const int nstages = p.b_resident ? p.res_stages : kStages;
+  uint8_t* sA_ring = p.b_resident ? smem + p.num_kb * Cfg::kBBytes : sA;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -104,6 +112,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&cfree[i], 1);
       mbar_init(&cfull[i], 4);
     }
+    mbar_init(bres, 1);
     fence_barrier_init();
   }
   if (warp == kWarpMma) {
@@ -120,6 +129,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if (p.b_resident && blockIdx.x < num_tiles) {      // the whole W tile once per CTA
+        mbar_arrive_expect_tx(bres, static_cast<uint32_t>(p.num_kb) * Cfg::kBBytes);
+        for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(&tmB, bres, smem + kb * Cfg::kBBytes, kb * BK, 0);
+      }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / p.num_n_tiles;
         const int n_blk = tile - m_blk * p.num_n_tiles;
@@ -134,18 +147,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+          mbar_arrive_expect_tx(&full[stage], p.b_resident ? Cfg::kABytes : Cfg::kStageBytes);
           if (kConv) {
             const int tap = kb / p.kb_per_tap;
             const int cb = kb - tap * p.kb_per_tap;
             const int ky = tap / 3, kx = tap - ky * 3;
-            tma_load_im2col_4d(&tmA, &full[stage], sA + stage * Cfg::kABytes, cb * BK, pw - 1, ph - 1, pn,
+            tma_load_im2col_4d(&tmA, &full[stage], sA_ring + stage * Cfg::kABytes, cb * BK, pw - 1, ph - 1, pn,
                                static_cast<uint16_t>(kx), static_cast<uint16_t>(ky));
           } else {
-            tma_load_2d(&tmA, &full[stage], sA + stage * Cfg::kABytes, kb * BK, m_blk * kTileM);
+            tma_load_2d(&tmA, &full[stage], sA_ring + stage * Cfg::kABytes, kb * BK, m_blk * kTileM);
           }
-          tma_load_2d(&tmB, &full[stage], sB + stage * Cfg::kBBytes, kb * BK, n_blk * BN);
-          if (++stage == kStages) {
+          if (!p.b_resident) tma_load_2d(&tmB, &full[stage], sB + stage * Cfg::kBBytes, kb * BK, n_blk * BN);
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
@@ -160,6 +173,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (p.b_resident && blockIdx.x < num_tiles) mbar_wait(bres, 0);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -167,8 +181,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint64_t adesc = make_kmajor_desc(smem_u32(sA + stage * Cfg::kABytes), BK * 2);
-          const uint64_t bdesc = make_kmajor_desc(smem_u32(sB + stage * Cfg::kBBytes), BK * 2);
+          const uint64_t adesc = make_kmajor_desc(smem_u32(sA_ring + stage * Cfg::kABytes), BK * 2);
+          const uint64_t bdesc = make_kmajor_desc(
+              smem_u32(p.b_resident ? smem + kb * Cfg::kBBytes : sB + stage * Cfg::kBBytes), BK * 2);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the (addr >> 4) field
@@ -176,7 +191,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                      (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty[stage]);
-          if (++stage == kStages) {
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
@@ -429,6 +444,19 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
       if (st) return st;
     }
   }
+  // Small weight matrices (e.g. the 64-channel 3x3 convs: 9 x 8 KB) stay resident in shared memory: the mainloop
+  // then streams only A tiles, removing a third of the L2 -> SM fill traffic those layers are bound by.
+  p.b_resident = 0;
+  if (p.num_n_tiles == 1 && p.num_kb >= 2) {
+    const int region = Cfg::kStages * Cfg::kStageBytes;
+    const int wbytes = p.num_kb * Cfg::kBBytes;
+    int ring = (region - wbytes) / Cfg::kABytes;
+    if (ring > Cfg::kStages) ring = Cfg::kStages;
+    if (wbytes <= 96 * 1024 && ring >= 4) {
+      p.b_resident = 1;
+      p.res_stages = ring;
+    }
+  }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int sms = sm_count();
   if (sms <= 0) return fail(LECB_ERR_CUDA, "no CUDA device");
@@ -460,9 +488,15 @@ static int dispatch_nb(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap
   return BN == 32 ? launch_gemm<32, 32, NB, kConv>(tmA, tmB, p, s) : launch_gemm<64, 32, NB, kConv>(tmA, tmB, p, s);
 }
 
+// The staging-buffer count trades operand stages for epilogue depth: with a short K loop the tile is bound by
+// the residual read + output write, and the number of 16 KB residual blocks that can be in flight per SM
+// (each buffer cycles free -> TMA load -> add -> TMA store -> drain) sets the achievable HBM bandwidth.
 template <bool kConv>
 static int dispatch(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t s) {
-  if (!kConv && p.num_kb <= 8) return dispatch_nb<kConv, 4>(BN, BK, tmA, tmB, p, s);
+  if (kConv) return dispatch_nb<kConv, 2>(BN, BK, tmA, tmB, p, s);
+  if (p.num_kb <= 2) return dispatch_nb<kConv, 8>(BN, BK, tmA, tmB, p, s);
+  if (p.num_kb <= 4) return dispatch_nb<kConv, 5>(BN, BK, tmA, tmB, p, s);
+  if (p.num_kb <= 8) return dispatch_nb<kConv, 4>(BN, BK, tmA, tmB, p, s);
   return dispatch_nb<kConv, 2>(BN, BK, tmA, tmB, p, s);
 }
 
@@ -482,6 +516,7 @@ extern "C" int lecb_gemm_bf16(const void* A, const void* W, const float* bias, c
   const int BK = (K % 64 == 0) ? 64 : 32;
   int BN = pick_bn(N);
   if (BK == 32 && BN > 64) BN = 64;
+  if (getenv("LECB_EXP_BN128") && N == 256 && K >= 512 && residual == nullptr) BN = 128;   // experiment knob
   GemmParams p{};
   p.bias = bias;
   p.residual = residual;

@@ -13,19 +13,23 @@ template <int CO>
 __global__ void __launch_bounds__(128) stem_conv1_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias,
                                                          __nv_bfloat16* __restrict__ out, int B, int H, int W) {
+  // One thread = TWO horizontally adjacent output pixels x CO channels: the 5x3x3 input patch is shared and
+  // every 128-bit weight broadcast from shared memory feeds 8 FMAs (the kernel is FMA-issue bound).
   __shared__ __align__(16) float sw[27 * CO];   // [tap(ci,ky,kx)][co]
   __shared__ float sb[CO];
   for (int i = threadIdx.x; i < 27 * CO; i += blockDim.x) sw[i] = w[i];
   for (int i = threadIdx.x; i < CO; i += blockDim.x) sb[i] = bias[i];
   __syncthreads();
-  const int HO = H / 2, WO = W / 2;
-  const int64_t total = static_cast<int64_t>(B) * HO * WO;
+  const int HO = H / 2, WO = W / 2, WP = (WO + 1) / 2;
+  const int64_t total = static_cast<int64_t>(B) * HO * WP;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int wo = static_cast<int>(idx % WO);
-  const int ho = static_cast<int>((idx / WO) % HO);
-  const int b = static_cast<int>(idx / (static_cast<int64_t>(WO) * HO));
-  float in[27];
+  const int wp = static_cast<int>(idx % WP);
+  const int ho = static_cast<int>((idx / WP) % HO);
+  const int b = static_cast<int>(idx / (static_cast<int64_t>(WP) * HO));
+  const int wo = 2 * wp;
+  const bool second = wo + 1 < WO;
+  float in[3][3][5];
 #pragma unroll
   for (int ci = 0; ci < 3; ++ci) {
     const float* xp = x + (static_cast<int64_t>(b) * 3 + ci) * H * W;
@@ -33,34 +37,46 @@ __global__ void __launch_bounds__(128) stem_conv1_kernel(const float* __restrict
     for (int ky = 0; ky < 3; ++ky) {
       const int hi = 2 * ho - 1 + ky;
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int wi = 2 * wo - 1 + kx;
-        in[ci * 9 + ky * 3 + kx] = (hi >= 0 && hi < H && wi >= 0 && wi < W) ? __ldg(xp + static_cast<int64_t>(hi) * W + wi) : 0.f;
+      for (int c = 0; c < 5; ++c) {
+        const int wi = 2 * wo - 1 + c;
+        in[ci][ky][c] = (hi >= 0 && hi < H && wi >= 0 && wi < W) ? __ldg(xp + static_cast<int64_t>(hi) * W + wi) : 0.f;
       }
     }
   }
-  __nv_bfloat16* op = out + idx * CO;
+  __nv_bfloat16* op = out + ((static_cast<int64_t>(b) * HO + ho) * WO + wo) * CO;
 #pragma unroll
   for (int c0 = 0; c0 < CO; c0 += 8) {
-    float acc[8];
+    float a0[8], a1[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = sb[c0 + j];
+    for (int j = 0; j < 8; ++j) a0[j] = a1[j] = sb[c0 + j];
 #pragma unroll
-    for (int t = 0; t < 27; ++t) {
-      // weights are warp-uniform: two 128-bit shared-memory broadcasts feed 8 FMAs
-      const float4 w0 = *reinterpret_cast<const float4*>(&sw[t * CO + c0]);
-      const float4 w1 = *reinterpret_cast<const float4*>(&sw[t * CO + c0 + 4]);
-      acc[0] = fmaf(in[t], w0.x, acc[0]); acc[1] = fmaf(in[t], w0.y, acc[1]);
-      acc[2] = fmaf(in[t], w0.z, acc[2]); acc[3] = fmaf(in[t], w0.w, acc[3]);
-      acc[4] = fmaf(in[t], w1.x, acc[4]); acc[5] = fmaf(in[t], w1.y, acc[5]);
-      acc[6] = fmaf(in[t], w1.z, acc[6]); acc[7] = fmaf(in[t], w1.w, acc[7]);
-    }
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int t = ci * 9 + ky * 3 + kx;
+          const float4 w0 = *reinterpret_cast<const float4*>(&sw[t * CO + c0]);
+          const float4 w1 = *reinterpret_cast<const float4*>(&sw[t * CO + c0 + 4]);
+          const float p0 = in[ci][ky][kx], p1 = in[ci][ky][kx + 2];
+          a0[0] = fmaf(p0, w0.x, a0[0]); a0[1] = fmaf(p0, w0.y, a0[1]); a0[2] = fmaf(p0, w0.z, a0[2]); a0[3] = fmaf(p0, w0.w, a0[3]);
+          a0[4] = fmaf(p0, w1.x, a0[4]); a0[5] = fmaf(p0, w1.y, a0[5]); a0[6] = fmaf(p0, w1.z, a0[6]); a0[7] = fmaf(p0, w1.w, a0[7]);
+          a1[0] = fmaf(p1, w0.x, a1[0]); a1[1] = fmaf(p1, w0.y, a1[1]); a1[2] = fmaf(p1, w0.z, a1[2]); a1[3] = fmaf(p1, w0.w, a1[3]);
+          a1[4] = fmaf(p1, w1.x, a1[4]); a1[5] = fmaf(p1, w1.y, a1[5]); a1[6] = fmaf(p1, w1.z, a1[6]); a1[7] = fmaf(p1, w1.w, a1[7]);
+        }
     uint4 u;
-    u.x = pack_bf16(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
-    u.y = pack_bf16(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
-    u.z = pack_bf16(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
-    u.w = pack_bf16(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+    u.x = pack_bf16(fmaxf(a0[0], 0.f), fmaxf(a0[1], 0.f));
+    u.y = pack_bf16(fmaxf(a0[2], 0.f), fmaxf(a0[3], 0.f));
+    u.z = pack_bf16(fmaxf(a0[4], 0.f), fmaxf(a0[5], 0.f));
+    u.w = pack_bf16(fmaxf(a0[6], 0.f), fmaxf(a0[7], 0.f));
     *reinterpret_cast<uint4*>(op + c0) = u;
+    if (second) {
+      u.x = pack_bf16(fmaxf(a1[0], 0.f), fmaxf(a1[1], 0.f));
+      u.y = pack_bf16(fmaxf(a1[2], 0.f), fmaxf(a1[3], 0.f));
+      u.z = pack_bf16(fmaxf(a1[4], 0.f), fmaxf(a1[5], 0.f));
+      u.w = pack_bf16(fmaxf(a1[6], 0.f), fmaxf(a1[7], 0.f));
+      *reinterpret_cast<uint4*>(op + CO + c0) = u;
+    }
   }
 }
 
@@ -257,7 +273,7 @@ extern "C" int lecb_stem_conv1(const float* x, const float* w, const float* bias
                                int Cout, void* stream) {
   LECB_CHECK_ARG(x && w && bias && out, "lecb_stem_conv1: null pointer");
   LECB_CHECK_ARG(B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "lecb_stem_conv1: H, W must be even and positive");
-  const int64_t total = static_cast<int64_t>(B) * (H / 2) * (W / 2);
+  const int64_t total = static_cast<int64_t>(B) * (H / 2) * ((W / 2 + 1) / 2);     // two output pixels per thread
   const unsigned grid = static_cast<unsigned>((total + 127) / 128);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (Cout == 32)

@@ -25,7 +25,7 @@ class _DualPromptHead(torch.autograd.Function):
         n_txt = len(prompts)
         k = prompts[0].shape[0]
         x = (torch.cat([p.detach().float() for p in prompts], 0) + tower.pos).contiguous()        # [n*K, 77, W]
-        eot = tok_prompts.to(x.device).argmax(dim=-1).repeat(n_txt)
+        eot = tok_prompts.repeat(n_txt)          # EOT index per prompt sequence, already on the device
         t_raw, saved = tower.forward_train(x, eot)                                                # [n*K, D] fp32
         t_hat = ops.l2norm_rows(t_raw)
         pad = (-t_hat.shape[0]) % 8
@@ -119,7 +119,9 @@ def forward_train(model, captions):
     learn = bool(_cfg(model, "TRAIN.IF_LEARN_SCALE", False))
     logit_scale = float(temperature.exp()) if learn else 4.0
     spatial = float(_cfg(model, "TRAIN.spatial_SCALE_text"))
-    pack = (model.text_encoder.tower(), model.tokenized_prompts, local, ssq, mask, g_unit, b, l, logit_scale, spatial)
+    if getattr(model, "_eot_dev", None) is None or model._eot_dev.device != local.device:
+        model._eot_dev = model.tokenized_prompts.argmax(dim=-1).to(local.device)      # cached: keeps the step graph-capturable
+    pack = (model.text_encoder.tower(), model._eot_dev, local, ssq, mask, g_unit, b, l, logit_scale, spatial)
     plist = (prompts, prompts_double, prompts_evidence) if use_evidence else (prompts, prompts_double)
     logits, logits_local, text_features = _DualPromptHead.apply(pack, temperature if learn else None, *plist)
     with torch.no_grad():
