@@ -94,6 +94,14 @@ int lecb_attnpool_query0(const float* q, const void* kmat, const void* vmat, voi
  * qkv bf16 [N*L, 3W] (q | k | v), out bf16 [N*L, W]; head dim 64; L <= 128. */
 int lecb_causal_attn_fwd(const void* qkv, void* out, int N, int L, int W, int heads, void* stream);
 
+/* ---- multi-head self-attention forward on tcgen05 tensor cores, head dim 64 ----
+ * The ViT visual encoder's attention (nn.MultiheadAttention inside ResidualAttentionBlock, M:207-228, called
+ * from VisionTransformer.forward M:259-276) and, with causal != 0, the text transformer's masked attention.
+ * qkv bf16 [B*T, 3W] (q | k | v per token, head h = columns h*64..h*64+63 of each third); out bf16 [B*T, W].
+ * Only the first `q_rows` query rows of every sequence are computed and stored (q_rows == T: all of them;
+ * q_rows == 1: the class token only, used by the dense last block); other rows of `out` are left untouched. */
+int lecb_attn_fwd(const void* qkv, void* out, int B, int T, int W, int heads, int q_rows, int causal, void* stream);
+
 /* ---- dual-prompt head aggregation (T:456-470 test, T:496-514 train) ----
  * dots fp32 [B*P, ldn]: raw dot products of the UN-normalised local features with the unit prompt
  * features, columns [0,K) = positive, [K,2K) = negative, [2K,3K) = evidence (n_txt == 3);

@@ -83,6 +83,23 @@ int encode_tiled_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t 
   return LECB_OK;
 }
 
+int encode_tiled_3d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t batches,
+                    uint32_t box_cols, uint32_t box_rows) {
+  static EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(driver_entry("cuTensorMapEncodeTiled"));
+  if (!fn) return fail(LECB_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  const cuuint64_t dims[3] = {cols, rows, batches};
+  const cuuint64_t strides[2] = {cols * 2, rows * cols * 2};
+  const cuuint32_t box[3] = {box_cols, box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(box_cols * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(LECB_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed (%d) cols=%llu rows=%llu batches=%llu", (int)r,
+                (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)batches);
+  return LECB_OK;
+}
+
 int encode_im2col_3x3(CUtensorMap* out, const void* base, int B, int H, int W, int C, uint32_t channels,
                       uint32_t pixels) {
   static EncodeIm2colFn fn = reinterpret_cast<EncodeIm2colFn>(driver_entry("cuTensorMapEncodeIm2col"));

@@ -150,6 +150,17 @@ def causal_attn(qkv, n, l, w, heads):
     return out
 
 
+def attn_fwd(qkv, b, t, w, heads, q_rows=None, causal=False, out=None):
+    """Multi-head attention on tcgen05: qkv bf16 [B*T,3W] -> bf16 [B*T,W] (rows >= q_rows of each sequence untouched)."""
+    _need(qkv, torch.bfloat16, "qkv")
+    assert tuple(qkv.shape) == (b * t, 3 * w), (qkv.shape, b, t, w)
+    if out is None:
+        out = torch.empty((b * t, w), device=qkv.device, dtype=torch.bfloat16)
+    check(lib.lecb_attn_fwd(_ptr(qkv), _ptr(out), b, t, w, heads, t if q_rows is None else q_rows, int(causal),
+                            _stream()), "lecb_attn_fwd")
+    return out
+
+
 def head_aggregate(dots, b, p, k, n_txt, row_sumsq=None, row_mask=None, logit_scale=4.0, spatial_scale=50.0,
                    want_maps=True):
     """dots fp32 [B*P, ldn] -> logits_local [B,K] (+ neg_map, pos_map [P,B,K])."""

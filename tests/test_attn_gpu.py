@@ -1,0 +1,52 @@
+"""tcgen05 attention kernel parity on the B200 (through the C ABI, lecb_attn_fwd).
+
+Reference: fp32 torch softmax(QK^T/8)V on the same bf16-rounded q/k/v.  The kernel rounds the
+probabilities to bf16 before the PV product (fp32 accumulation) and the output to bf16: tolerance =
+2^-7 of the output scale."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(qkv, b, t, w, heads, causal):
+    q, k, v = qkv.float().view(b, t, 3, heads, 64).permute(2, 0, 3, 1, 4)          # [b,h,t,64]
+    s = (q @ k.transpose(-1, -2)) / 8.0
+    if causal:
+        s = s + torch.full((t, t), float("-inf"), device=s.device).triu(1)
+    return (s.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(b * t, w)
+
+
+@pytest.mark.parametrize("b,t,heads,causal", [
+    (2, 128, 2, False), (3, 785, 12, False), (2, 1025, 16, False), (1, 50, 1, False), (2, 197, 12, False),
+    (5, 77, 8, True), (2, 300, 4, True), (1, 128, 1, True), (2, 257, 2, False),
+])
+def test_attn_fwd(b, t, heads, causal):
+    from lecb200 import ops
+    w = heads * 64
+    g = torch.Generator(device="cpu").manual_seed(b * 1000 + t)
+    qkv = (torch.randn((b * t, 3 * w), generator=g) * 1.5).cuda().bfloat16()
+    out = ops.attn_fwd(qkv, b, t, w, heads, causal=causal)
+    torch.cuda.synchronize()
+    want = _ref(qkv, b, t, w, heads, causal)
+    err = (out.float() - want).abs().max().item()
+    scale = want.abs().max().item()
+    assert err <= scale * 2.0 ** -7 + 1e-3, f"attn b={b} t={t} h={heads} causal={causal}: err {err:.4g} scale {scale:.4g}"
+
+
+def test_attn_fwd_peaked_and_partial_rows():
+    """Large-magnitude scores (near one-hot softmax) and q_rows < T (class-token-only mode leaves other rows alone)."""
+    from lecb200 import ops
+    b, t, heads = 2, 785, 12
+    w = heads * 64
+    g = torch.Generator(device="cpu").manual_seed(7)
+    qkv = (torch.randn((b * t, 3 * w), generator=g) * 4.0).cuda().bfloat16()
+    want = _ref(qkv, b, t, w, heads, False)
+    out = ops.attn_fwd(qkv, b, t, w, heads)
+    assert (out.float() - want).abs().max().item() <= want.abs().max().item() * 2.0 ** -6
+    sentinel = torch.full((b * t, w), 7.0, device="cuda", dtype=torch.bfloat16)
+    out1 = ops.attn_fwd(qkv, b, t, w, heads, q_rows=1, out=sentinel.clone())
+    torch.cuda.synchronize()
+    o3 = out1.view(b, t, w)
+    assert (o3[:, 0].float() - want.view(b, t, w)[:, 0]).abs().max().item() <= want.abs().max().item() * 2.0 ** -6
+    assert (o3[:, 1:] == 7.0).all()
