@@ -102,6 +102,18 @@ int lecb_causal_attn_fwd(const void* qkv, void* out, int N, int L, int W, int he
  * q_rows == 1: the class token only, used by the dense last block); other rows of `out` are left untouched. */
 int lecb_attn_fwd(const void* qkv, void* out, int B, int T, int W, int heads, int q_rows, int causal, void* stream);
 
+/* ---- ViT visual tower row kernels (VisionTransformer.forward, M:259-276) ----
+ * lecb_patchify: x NCHW fp32 [B,3,H,W] -> bf16 [B*(H/p)*(W/p), Kpad], column k = c*p*p + py*p + px (the flattening
+ *   of conv1.weight [width,3,p,p]), zero beyond 3*p*p: the A operand of the patch-embedding GEMM (M:261).
+ * lecb_vit_embed_ln: out fp32 [B*T, D] = ln_pre( [class_embedding ; emb rows of image b] + positional_embedding )
+ *   (M:262-266); emb bf16 [B*(T-1), D].
+ * lecb_copy_cols: dst[r, 0:cols] = src[r, col0:col0+cols] (bf16): takes the value third of a packed qkv matrix. */
+int lecb_patchify(const float* x, void* out, int B, int H, int W, int patch, int Kpad, void* stream);
+int lecb_vit_embed_ln(const void* emb, const float* cls, const float* pos, const float* gamma, const float* beta,
+                      float* out, int B, int T, int D, float eps, void* stream);
+int lecb_copy_cols(const void* src, int64_t ld_src, int col0, void* dst, int64_t ld_dst, int64_t rows, int cols,
+                   void* stream);
+
 /* ---- dual-prompt head aggregation (T:456-470 test, T:496-514 train) ----
  * dots fp32 [B*P, ldn]: raw dot products of the UN-normalised local features with the unit prompt
  * features, columns [0,K) = positive, [K,2K) = negative, [2K,3K) = evidence (n_txt == 3);

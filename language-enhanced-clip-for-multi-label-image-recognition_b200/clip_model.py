@@ -78,17 +78,36 @@ class TransformerParams(_Holder):
         self.resblocks = nn.Sequential(*[_res_block(width, heads) for _ in range(layers)])
 
 
+class VisionTransformerParams(_Holder):
+    """Weights of CLIP's VisionTransformer (clip/model.py:240-276)."""
+
+    def __init__(self, input_resolution, patch_size, width, layers, heads, output_dim):
+        super().__init__()
+        self.input_resolution, self.output_dim, self.patch_size = input_resolution, output_dim, patch_size
+        self.conv1 = nn.Conv2d(3, width, patch_size, stride=patch_size, bias=False)
+        scale = width ** -0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn((input_resolution // patch_size) ** 2 + 1, width))
+        self.ln_pre = nn.LayerNorm(width)
+        self.transformer = TransformerParams(width, layers, heads)
+        self.ln_post = nn.LayerNorm(width)
+        self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+
+
 class CLIPParams(_Holder):
-    """Same constructor signature and state_dict keys as the reference `CLIP` (clip/model.py:279-333),
-    ModifiedResNet visual towers only (the only ones the reference's dense path supports, T:365-373)."""
+    """Same constructor signature and state_dict keys as the reference `CLIP` (clip/model.py:279-333).
+    ModifiedResNet towers are what the reference's dense path supports (T:365-373); VisionTransformer towers
+    (BASELINE configs 3, 5) use this repo's dense definition (oracle/restatement.py `vit_dense`)."""
 
     def __init__(self, embed_dim, image_resolution, vision_layers, vision_width, vision_patch_size,
                  context_length, vocab_size, transformer_width, transformer_heads, transformer_layers):
         super().__init__()
-        if not isinstance(vision_layers, (tuple, list)):
-            raise NotImplementedError("lecb200 mirrors the reference: DenseCLIP wraps ModifiedResNet towers only")
         self.context_length, self.vocab_size = context_length, vocab_size
-        self.visual = ModifiedResNetParams(vision_layers, embed_dim, vision_width * 32 // 64, image_resolution, vision_width)
+        if isinstance(vision_layers, (tuple, list)):
+            self.visual = ModifiedResNetParams(vision_layers, embed_dim, vision_width * 32 // 64, image_resolution, vision_width)
+        else:
+            self.visual = VisionTransformerParams(image_resolution, vision_patch_size, vision_width, vision_layers,
+                                                  vision_width // 64, embed_dim)
         self.transformer = TransformerParams(transformer_width, transformer_layers, transformer_heads)
         self.token_embedding = nn.Embedding(vocab_size, transformer_width)
         self.positional_embedding = nn.Parameter(torch.empty(context_length, transformer_width).normal_(std=0.01))
@@ -104,12 +123,18 @@ class CLIPParams(_Holder):
 def describe(clip_model) -> dict:
     """Architecture facts the engine needs, read off any CLIP-shaped module (ours or the reference's)."""
     sd = clip_model.state_dict()
-    if "visual.layer1.0.conv1.weight" not in sd:
-        raise NotImplementedError("visual tower is not a ModifiedResNet (reference T:365-373 has the same limit)")
-    layers = tuple(len({k.split(".")[2] for k in sd if k.startswith(f"visual.layer{b}.")}) for b in (1, 2, 3, 4))
-    width = sd["visual.layer1.0.conv1.weight"].shape[0]
     tw = sd["ln_final.weight"].shape[0]
-    return dict(layers=layers, width=width, embed_dim=sd["text_projection"].shape[1], vis_heads=width * 32 // 64,
-                text_width=tw, text_heads=tw // 64,
+    if "visual.proj" in sd:                         # VisionTransformer tower
+        width = sd["visual.conv1.weight"].shape[0]
+        vit = dict(kind="vit", width=width, patch=sd["visual.conv1.weight"].shape[-1], vis_heads=width // 64,
+                   layers=len({k.split(".")[3] for k in sd if k.startswith("visual.transformer.resblocks.")}),
+                   tokens=sd["visual.positional_embedding"].shape[0])
+    elif "visual.layer1.0.conv1.weight" in sd:
+        width = sd["visual.layer1.0.conv1.weight"].shape[0]
+        vit = dict(kind="rn", width=width, vis_heads=width * 32 // 64,
+                   layers=tuple(len({k.split(".")[2] for k in sd if k.startswith(f"visual.layer{b}.")}) for b in (1, 2, 3, 4)))
+    else:
+        raise NotImplementedError("visual tower is neither a ModifiedResNet nor a VisionTransformer")
+    return dict(**vit, embed_dim=sd["text_projection"].shape[1], text_width=tw, text_heads=tw // 64,
                 text_layers=len({k.split(".")[2] for k in sd if k.startswith("transformer.resblocks.")}),
                 context_length=sd["positional_embedding"].shape[0])

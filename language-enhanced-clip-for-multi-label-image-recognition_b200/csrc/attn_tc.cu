@@ -8,10 +8,19 @@
 //   P = exp2(S*c - m*c)   four softmax warps, thread == query row (tcgen05.ld 32x32b), online max / sum,
 //                         P written to shared memory as the bf16 K-major A operand of the next MMA
 //   O_blk = P V    tcgen05.mma  M=128 N=64 K=128, V tile used in place as an MN-major B operand
-// The running output lives in registers (o = o*alpha + O_blk, O_blk read back from TMEM), so no TMEM
-// rescale pass is needed; O_blk is double-buffered in TMEM.  TMEM: S [0,128) | O0 [128,192) | O1 [192,256).
+// O accumulates in TMEM across key blocks.  The softmax reference point m is only moved when a block's
+// probabilities would grow past 2^15 relative to it (lazy rescaling): block 0 takes an exact two-pass max,
+// later blocks are a single pass over S with the running m, and only a warp that sees a row sum above the
+// threshold re-does the block exactly and rescales its 32 rows of O in TMEM (tcgen05.ld / tcgen05.st) before
+// the block's PV MMA is released.  The result o / l is independent of where m sits.
+// TMEM: S [0,128) | O [128,192).
 //
 // Warps: 0-3 softmax (TMEM lane quarter == warp id), 4 TMA producer, 5 MMA issuer + TMEM owner.
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <type_traits>
+
 #include "lecb_common.cuh"
 #include "lecb_host.h"
 
@@ -69,8 +78,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   uint64_t* s_full = bars + 9;
   uint64_t* s_free = bars + 10;
   uint64_t* p_full = bars + 11;
-  uint64_t* p_free = bars + 12;
-  uint64_t* o_full = bars + 13;    // [2]
+  uint64_t* p_free = bars + 12;    // PV MMA of the block complete: P reusable, O includes the block
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5;
@@ -90,7 +98,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
-      mbar_init(&o_full[i], 1);
     }
     mbar_init(s_full, 1);
     mbar_init(s_free, 4);
@@ -134,18 +141,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         mbar_wait(&v_full[s], (i >> 1) & 1);
         mbar_wait(p_full, i & 1);
         tc_fence_after();
-        const uint32_t tO = tmem_base + 128u + static_cast<uint32_t>(s) * kAtDh;
+        const uint32_t tO = tmem_base + 128u;
 #pragma unroll
         for (int kk = 0; kk < kAtTile / 16; ++kk) {
           // A = P: two 64-key K-major blocks, 16 keys (32 bytes) per step inside a block
           const uint64_t adesc = make_kmajor_desc(smem_u32(sP + (kk >> 2) * kAtTileBytes), 128) + static_cast<uint64_t>(2 * (kk & 3));
           // B = V tile [keys][dh] used as an MN-major operand: 16 keys = 2048 bytes per step
           const uint64_t bdesc = make_kmajor_desc(smem_u32(sV + s * kAtTileBytes + kk * 2048), 128);
-          umma_f16(tO, adesc, bdesc, idesc_pv, kk != 0 ? 1u : 0u);
+          umma_f16(tO, adesc, bdesc, idesc_pv, (i | kk) != 0 ? 1u : 0u);
         }
         umma_commit(&v_empty[s]);
         umma_commit(p_free);
-        umma_commit(&o_full[s]);
       };
       mbar_wait(q_full, 0);
       for (int j = 0; j < n_kv; ++j) {
@@ -170,38 +176,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
     const int qi = q0 + row;
     const int limit = p.causal ? min(p.T - 1, qi) : p.T - 1;       // last key index this row may see
-    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-    float o[kAtDh];
-#pragma unroll
-    for (int d = 0; d < kAtDh; ++d) o[d] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    const uint32_t tS = tmem_base + lane_base;
+    const uint32_t tO = tmem_base + lane_base + 128u;
 
-    auto fold = [&](int i) {      // o = o * alpha_i + O_i
-      mbar_wait(&o_full[i & 1], (i >> 1) & 1);
-      tc_fence_after();
-      uint32_t r0[32], r1[32];
-      const uint32_t tO = tmem_base + lane_base + 128u + static_cast<uint32_t>(i & 1) * kAtDh;
-      tmem_ld_32x32(tO, r0);
-      tmem_ld_32x32(tO + 32u, r1);
-      tmem_ld_wait();
-#pragma unroll
-      for (int d = 0; d < 32; ++d) {
-        o[d] = fmaf(o[d], alpha_prev, __uint_as_float(r0[d]));
-        o[32 + d] = fmaf(o[32 + d], alpha_prev, __uint_as_float(r1[d]));
-      }
-    };
-
-    for (int j = 0; j < n_kv; ++j) {
-      const int kv0 = j * kAtTile;
-      const bool need_mask = (kv0 + kAtTile > p.T) || (p.causal && kv0 + kAtTile - 1 > q0);
-      const int lim = limit - kv0;             // columns c <= lim are visible
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      // pass 1: row maximum
+    // exact row maximum of the (masked) block
+    auto block_max = [&](bool need_mask, int lim) {
       float mx = -INFINITY;
 #pragma unroll 1
       for (int c4 = 0; c4 < 4; ++c4) {
         uint32_t r[32];
-        tmem_ld_32x32(tmem_base + lane_base + static_cast<uint32_t>(c4 * 32), r);
+        tmem_ld_32x32(tS + static_cast<uint32_t>(c4 * 32), r);
         tmem_ld_wait();
         if (need_mask) {
 #pragma unroll
@@ -211,25 +196,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
           for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
         }
       }
-      const float m_new = fmaxf(m, mx);
-      const float alpha = fast_exp2((m - m_new) * p.sc);
-      const float msc = m_new * p.sc;
-      if (j >= 1) mbar_wait(p_free, (j - 1) & 1);
-      // pass 2: probabilities -> bf16 K-major operand in shared memory
+      return mx;
+    };
+    // P = exp2(S*sc - msc) -> bf16 K-major operand in shared memory; returns the row sum.  The TMEM load of
+    // chunk c+1 is in flight while chunk c is exponentiated.  `wait_bar` (P buffer free) is taken just before
+    // the first store so the wait hides behind the first chunk's math.
+    auto write_p_impl = [&](auto mask_tag, float msc, int lim, uint64_t* wait_bar, uint32_t wait_parity) {
+      constexpr bool kMask = decltype(mask_tag)::value;
       float sum = 0.f;
-#pragma unroll 1
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32(tS, ra);
+      tmem_ld_wait();
+#pragma unroll
       for (int c4 = 0; c4 < 4; ++c4) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + lane_base + static_cast<uint32_t>(c4 * 32), r);
-        tmem_ld_wait();
+        uint32_t(&r)[32] = (c4 & 1) ? rb : ra;
+        uint32_t(&rn)[32] = (c4 & 1) ? ra : rb;
+        if (c4 < 3) tmem_ld_32x32(tS + static_cast<uint32_t>((c4 + 1) * 32), rn);
         float pv[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           float e = fast_exp2(fmaf(__uint_as_float(r[i]), p.sc, -msc));
-          if (need_mask && c4 * 32 + i > lim) e = 0.f;
+          if (kMask && c4 * 32 + i > lim) e = 0.f;
           pv[i] = e;
           sum += e;
         }
+        if (c4 == 0 && wait_bar != nullptr) mbar_wait(wait_bar, wait_parity);
         uint8_t* pblk = sP + (c4 >> 1) * kAtTileBytes;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -240,9 +231,50 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
           u.w = pack_bf16(pv[q * 8 + 6], pv[q * 8 + 7]);
           *reinterpret_cast<uint4*>(pblk + swizzled_chunk_offset(row, (c4 & 1) * 4 + q, 128)) = u;
         }
+        if (c4 < 3) tmem_ld_wait();
       }
-      l = fmaf(l, alpha, sum);
-      m = m_new;
+      return sum;
+    };
+    // the mask test costs two extra instructions per score: only the ragged last block / causal diagonal pays it
+    auto write_p = [&](float msc, bool need_mask, int lim, uint64_t* wait_bar, uint32_t wait_parity) {
+      return need_mask ? write_p_impl(std::true_type{}, msc, lim, wait_bar, wait_parity)
+                       : write_p_impl(std::false_type{}, msc, lim, wait_bar, wait_parity);
+    };
+
+    for (int j = 0; j < n_kv; ++j) {
+      const int kv0 = j * kAtTile;
+      const bool need_mask = (kv0 + kAtTile > p.T) || (p.causal && kv0 + kAtTile - 1 > q0);
+      const int lim = limit - kv0;             // columns c <= lim are visible
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      if (j == 0) {
+        m = block_max(need_mask, lim);
+        l = write_p(m * p.sc, need_mask, lim, nullptr, 0);
+      } else {
+        float sum = write_p(m * p.sc, need_mask, lim, p_free, (j - 1) & 1);
+        // lazy rescaling: keep m unless some probability of this block is enormous relative to it
+        if (__any_sync(0xffffffffu, !(sum <= 32768.f))) {
+          const float m_new = fmaxf(m, block_max(need_mask, lim));
+          const float alpha = fast_exp2((m - m_new) * p.sc);
+          // PV of block j-1 has completed (p_free waited in write_p) and PV of block j is not released yet:
+          // this warp's 32 rows of O can be rescaled in place
+          tc_fence_after();
+#pragma unroll 1
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            uint32_t r[32];
+            tmem_ld_32x32(tO + static_cast<uint32_t>(hlf * 32), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st_32x32(tO + static_cast<uint32_t>(hlf * 32), r);
+          }
+          tmem_st_wait();
+          sum = write_p(m_new * p.sc, need_mask, lim, nullptr, 0);
+          l *= alpha;
+          m = m_new;
+        }
+        l += sum;
+      }
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
@@ -250,21 +282,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         mbar_arrive(s_free);
         mbar_arrive(p_full);
       }
-      if (j >= 1) fold(j - 1);
-      alpha_prev = alpha;
     }
-    fold(n_kv - 1);
-    if (qi < p.q_rows) {
-      const float inv = 1.0f / l;
-      uint4* op = reinterpret_cast<uint4*>(p.out + (static_cast<int64_t>(b) * p.T + qi) * p.W + h * kAtDh);
+    // all PV MMAs done -> O complete
+    mbar_wait(p_free, (n_kv - 1) & 1);
+    tc_fence_after();
+    {      // the tcgen05.ld is warp-collective: every lane loads, only valid query rows store
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(tO, r0);
+      tmem_ld_32x32(tO + 32u, r1);
+      tmem_ld_wait();
+      if (qi < p.q_rows) {
+        const float inv = 1.0f / l;
+        uint4* op = reinterpret_cast<uint4*>(p.out + (static_cast<int64_t>(b) * p.T + qi) * p.W + h * kAtDh);
 #pragma unroll
-      for (int q = 0; q < kAtDh / 8; ++q) {
-        uint4 u;
-        u.x = pack_bf16(o[q * 8 + 0] * inv, o[q * 8 + 1] * inv);
-        u.y = pack_bf16(o[q * 8 + 2] * inv, o[q * 8 + 3] * inv);
-        u.z = pack_bf16(o[q * 8 + 4] * inv, o[q * 8 + 5] * inv);
-        u.w = pack_bf16(o[q * 8 + 6] * inv, o[q * 8 + 7] * inv);
-        op[q] = u;
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(r0[q * 8 + 0]) * inv, __uint_as_float(r0[q * 8 + 1]) * inv);
+          u.y = pack_bf16(__uint_as_float(r0[q * 8 + 2]) * inv, __uint_as_float(r0[q * 8 + 3]) * inv);
+          u.z = pack_bf16(__uint_as_float(r0[q * 8 + 4]) * inv, __uint_as_float(r0[q * 8 + 5]) * inv);
+          u.w = pack_bf16(__uint_as_float(r0[q * 8 + 6]) * inv, __uint_as_float(r0[q * 8 + 7]) * inv);
+          op[q] = u;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(r1[q * 8 + 0]) * inv, __uint_as_float(r1[q * 8 + 1]) * inv);
+          u.y = pack_bf16(__uint_as_float(r1[q * 8 + 2]) * inv, __uint_as_float(r1[q * 8 + 3]) * inv);
+          u.z = pack_bf16(__uint_as_float(r1[q * 8 + 4]) * inv, __uint_as_float(r1[q * 8 + 5]) * inv);
+          u.w = pack_bf16(__uint_as_float(r1[q * 8 + 6]) * inv, __uint_as_float(r1[q * 8 + 7]) * inv);
+          op[4 + q] = u;
+        }
       }
     }
   }
@@ -293,6 +340,13 @@ extern "C" int lecb_attn_fwd(const void* qkv, void* out, int B, int T, int W, in
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes);
     if (e != cudaSuccess) return fail(LECB_ERR_CUDA, "cudaFuncSetAttribute(attn smem=%d): %s", kAtSmemBytes, cudaGetErrorString(e));
+    // two CTAs per SM need the full 228 KB shared-memory carve-out
+    cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (getenv("LECB_DEBUG")) {
+      int occ = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, attn_fwd_kernel, kAtThreads, kAtSmemBytes);
+      fprintf(stderr, "[lecb] attn_fwd_kernel: %d CTAs/SM, %d B dynamic smem\n", occ, kAtSmemBytes);
+    }
     configured = true;
   }
   CUtensorMap tm;

@@ -68,14 +68,20 @@ static CUtensorMapSwizzle swizzle_for(uint32_t inner_bytes) {
 
 int encode_tiled_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
                     uint32_t box_cols) {
+  return encode_tiled_2d_ex(out, base, rows, cols, box_rows, box_cols, 2);
+}
+
+int encode_tiled_2d_ex(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                       uint32_t box_cols, uint32_t elem_bytes) {
   static EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(driver_entry("cuTensorMapEncodeTiled"));
   if (!fn) return fail(LECB_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   const cuuint64_t dims[2] = {cols, rows};
-  const cuuint64_t strides[1] = {cols * 2};
+  const cuuint64_t strides[1] = {cols * elem_bytes};
   const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(box_cols * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = fn(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_for(box_cols * elem_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(LECB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box=%ux%u", (int)r,

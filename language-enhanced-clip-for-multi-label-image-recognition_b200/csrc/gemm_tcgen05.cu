@@ -58,7 +58,9 @@ struct GemmParams {
   int num_m_tiles;
   int num_n_tiles;
   unsigned flags;
-  int staged;        // bf16 output through smem + TMA store
+  int staged;        // output through swizzled smem blocks + TMA store (bf16: 64 columns per block, fp32: 32)
+  int out_f32;       // staged fp32 output (+ optional fp32 residual)
+  int cblocks;       // staged blocks per tile = BN / columns per block
   int b_resident;    // all K blocks of the (single) W tile stay in smem for the CTA's lifetime; A ring gets the rest
   int res_stages;    // A-ring depth in b_resident mode
   // conv mode
@@ -106,7 +108,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&tfull[i], 1);
       // staged path: both epilogue groups read every accumulator (8 warps) unless a tile is a single block,
       // in which case the groups alternate tiles (4 warps); direct fp32 path: group 0 only
-      mbar_init(&tempty[i], (p.staged && kCBlocks > 1) ? 8 : 4);
+      mbar_init(&tempty[i], (p.staged && p.cblocks > 1) ? 8 : 4);
     }
     for (int i = 0; i < NB; ++i) {
       mbar_init(&cfree[i], 1);
@@ -205,15 +207,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ------------------------------- epilogue DMA (staged bf16 output) ----------
     if (lane == 0 && p.staged) {
       const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-      const uint32_t total = static_cast<uint32_t>(my_tiles) * kCBlocks;
+      const uint32_t cblocks = static_cast<uint32_t>(p.cblocks);
+      const int ccols = BN / p.cblocks;
+      const uint32_t total = static_cast<uint32_t>(my_tiles) * cblocks;
       const bool has_res = p.residual != nullptr;
       auto coords = [&](uint32_t g, int& m0, int& n0) {
-        const int i = static_cast<int>(g / kCBlocks), cb = static_cast<int>(g % kCBlocks);
+        const int i = static_cast<int>(g / cblocks), cb = static_cast<int>(g % cblocks);
         const int tile = blockIdx.x + i * gridDim.x;
         const int m_blk = tile / p.num_n_tiles;
         const int n_blk = tile - m_blk * p.num_n_tiles;
         m0 = m_blk * kTileM;
-        n0 = n_blk * BN + cb * kCCols;
+        n0 = n_blk * BN + cb * ccols;
       };
       auto make_free = [&](uint32_t g) {
         const int buf = g % NB;
@@ -261,7 +265,69 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int64_t row = static_cast<int64_t>(m_blk) * kTileM + erow;
       const bool row_ok = row < p.M;
       float ssq = 0.f;
-      if (p.staged) {
+      if (p.staged && p.out_f32) {
+        // fp32 output (+ fp32 residual): 32-column blocks (128-byte rows), same buffer ring and DMA protocol
+        const int cblocks = p.cblocks;
+        const uint32_t g0 = static_cast<uint32_t>(tile_seq) * cblocks;
+        int cb_first = (cblocks > 1) ? group : (((g0 & 1) == static_cast<uint32_t>(group)) ? 0 : cblocks);
+        if (cb_first >= cblocks) continue;
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cb = cb_first; cb < cblocks; cb += 2) {
+          const uint32_t gblk = g0 + cb;
+          const int buf = gblk % NB;
+          uint8_t* cbuf = sC + buf * Cfg::kCBytes;
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + lane_base + static_cast<uint32_t>(acc * BN + cb * 32), r);
+          tmem_ld_wait();
+          if (cb + 2 >= cblocks) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          mbar_wait(&cfree[buf], (gblk / NB) & 1);
+          const int n0 = n_blk * BN + cb * 32;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (n0 + j < p.N) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+            }
+          }
+          if (p.residual != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 f = *reinterpret_cast<const float4*>(cbuf + swizzled_chunk_offset(erow, q, 128));
+              v[q * 4 + 0] += f.x; v[q * 4 + 1] += f.y; v[q * 4 + 2] += f.z; v[q * 4 + 3] += f.w;
+            }
+          }
+          if (relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (gelu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            *reinterpret_cast<float4*>(cbuf + swizzled_chunk_offset(erow, q, 128)) =
+                make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            if (p.row_sumsq != nullptr && n0 + q * 4 < p.N)
+              ssq += v[q * 4] * v[q * 4] + v[q * 4 + 1] * v[q * 4 + 1] + v[q * 4 + 2] * v[q * 4 + 2] +
+                     v[q * 4 + 3] * v[q * 4 + 3];
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&cfull[buf]);
+        }
+      } else if (p.staged) {
         // block g = tile_seq * kCBlocks + cb belongs to group g % 2
         const uint32_t g0 = static_cast<uint32_t>(tile_seq) * kCBlocks;
         int cb_first = (kCBlocks > 1) ? group : (((g0 & 1) == static_cast<uint32_t>(group)) ? 0 : kCBlocks);
@@ -434,13 +500,19 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
     configured = true;
   }
   CUtensorMap tmC = tmA, tmR = tmA;      // placeholders when the staged path is off
-  p.staged = (p.flags & LECB_EPI_OUT_F32) ? 0 : 1;
+  const bool want_f32 = (p.flags & LECB_EPI_OUT_F32) != 0;
+  if (!want_f32 && (p.flags & LECB_EPI_RES_F32)) return fail(LECB_ERR_ARG, "fp32 residual requires LECB_EPI_OUT_F32");
+  // fp32 output is staged too (32-column blocks) when the tile is wide enough and the residual, if any, is fp32
+  p.out_f32 = (want_f32 && BN >= 64 && (p.residual == nullptr || (p.flags & LECB_EPI_RES_F32))) ? 1 : 0;
+  p.staged = (!want_f32 || p.out_f32) ? 1 : 0;
+  p.cblocks = p.out_f32 ? BN / 32 : Cfg::kCBlocks;
   if (p.staged) {
-    int st = encode_tiled_2d(&tmC, p.out, static_cast<uint64_t>(p.M), static_cast<uint64_t>(p.N), kTileM, Cfg::kCCols);
+    const uint32_t ccols = p.out_f32 ? 32 : Cfg::kCCols;
+    const uint32_t esz = p.out_f32 ? 4 : 2;
+    int st = encode_tiled_2d_ex(&tmC, p.out, static_cast<uint64_t>(p.M), static_cast<uint64_t>(p.N), kTileM, ccols, esz);
     if (st) return st;
     if (p.residual != nullptr) {
-      if (p.flags & LECB_EPI_RES_F32) return fail(LECB_ERR_ARG, "fp32 residual requires LECB_EPI_OUT_F32");
-      st = encode_tiled_2d(&tmR, p.residual, static_cast<uint64_t>(p.M), static_cast<uint64_t>(p.N), kTileM, Cfg::kCCols);
+      st = encode_tiled_2d_ex(&tmR, p.residual, static_cast<uint64_t>(p.M), static_cast<uint64_t>(p.N), kTileM, ccols, esz);
       if (st) return st;
     }
   }

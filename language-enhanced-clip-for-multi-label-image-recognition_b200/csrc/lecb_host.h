@@ -17,6 +17,9 @@ int check_launch(const char* what);                   // cudaGetLastError -> sta
 // 2-D row-major bf16 matrix [rows, cols]; box = box_rows x box_cols elements; swizzle = box_cols*2 bytes.
 int encode_tiled_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
                     uint32_t box_cols);
+// same for 2-byte (bf16 / fp16) or 4-byte (fp32) elements
+int encode_tiled_2d_ex(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                       uint32_t box_cols, uint32_t elem_bytes);
 // 3-D bf16 tensor [batches, rows, cols] (dense); box = 1 x box_rows x box_cols; rows past the end of a batch
 // are zero-filled, so a tile never reads the next batch's rows.
 int encode_tiled_3d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t batches,

@@ -23,7 +23,7 @@ from torch import nn
 
 from . import ops
 from .clip_model import describe
-from .engine import TextTower, VisualRN
+from .engine import TextTower, VisualRN, VisualViT
 
 
 def _cfg_get(node, path, default=None):
@@ -179,9 +179,10 @@ class DenseCLIPB200(nn.Module):
         self.text_encoder = TextEncoder(clip_model)
         self.model = clip_model
         self.return_interm_layers = return_interm_layers
-        ap = clip_model.visual.attnpool
-        self.v_linear_weight, self.v_linear_bias = ap.v_proj.weight, ap.v_proj.bias      # aliases, T:370-373
-        self.c_linear_weight, self.c_linear_bias = ap.c_proj.weight, ap.c_proj.bias
+        ap = getattr(clip_model.visual, "attnpool", None)
+        if ap is not None:                     # ModifiedResNet tower (the reference's only dense path)
+            self.v_linear_weight, self.v_linear_bias = ap.v_proj.weight, ap.v_proj.bias      # aliases, T:370-373
+            self.c_linear_weight, self.c_linear_bias = ap.c_proj.weight, ap.c_proj.bias
         self.logit_scale = clip_model.logit_scale
         self.dtype = clip_model.dtype
         self.cfg = cfg
@@ -194,13 +195,17 @@ class DenseCLIPB200(nn.Module):
         self._info = describe(clip_model)
 
     # ---------------------------------------------------------------- engines
-    def visual_engine(self) -> VisualRN:
+    def visual_engine(self):
         dev = self.model.visual.conv1.weight.device
         if self._visual is None or self._visual.device != dev:
             if dev.type != "cuda":
                 raise ops._lib.LecbError("lecb200 DenseCLIPB200 needs its weights on a CUDA device (no CPU path)")
             i = self._info
-            self._visual = VisualRN(self.model.state_dict(), i["layers"], i["width"], i["vis_heads"], i["embed_dim"], dev)
+            if i["kind"] == "vit":
+                self._visual = VisualViT(self.model.state_dict(), i["patch"], i["width"], i["layers"], i["vis_heads"],
+                                         i["embed_dim"], dev)
+            else:
+                self._visual = VisualRN(self.model.state_dict(), i["layers"], i["width"], i["vis_heads"], i["embed_dim"], dev)
         return self._visual
 
     def reset_prompt_cache(self):
@@ -209,6 +214,8 @@ class DenseCLIPB200(nn.Module):
 
     def encode_image(self, x):
         """T:385-399.  Returns NCHW fp32 like the reference (a view of the engine's NHWC bf16 output)."""
+        if self._info["kind"] == "vit":
+            raise NotImplementedError("encode_image returns the ModifiedResNet layer4 map (T:385-399); ViT towers have none")
         return self.visual_engine().trunk(x.float()).permute(0, 3, 1, 2).float()
 
     # ---------------------------------------------------------------- forward
@@ -242,10 +249,23 @@ class DenseCLIPB200(nn.Module):
     def _forward_test(self, image):
         use_evidence = bool(_cfg_get(self.cfg, "TRAINER.Caption.use_evidence", False))
         eng = self.visual_engine()
-        feat = eng.trunk(image.float())
-        b, h, w, _ = feat.shape
-        p = h * w
-        local, ssq, g = eng.pooled(feat)
+        row_mask = None
+        if self._info["kind"] == "vit":
+            # token rows [B, T]: row 0 of every image is the class token = the global feature; it is masked out of
+            # the spatial aggregation exactly like a padded caption token (lecb_head_aggregate row_mask)
+            local, ssq, p = eng.tokens(image.float())
+            b = image.shape[0]
+            g = local.view(b, p, -1)[:, 0].float().contiguous()
+            if getattr(self, "_cls_mask", None) is None or self._cls_mask.shape[0] != b * p or self._cls_mask.device != local.device:
+                m = torch.zeros((b, p), device=local.device, dtype=torch.uint8)
+                m[:, 0] = 1
+                self._cls_mask = m.view(-1)
+            row_mask = self._cls_mask
+        else:
+            feat = eng.trunk(image.float())
+            b, h, w, _ = feat.shape
+            p = h * w
+            local, ssq, g = eng.pooled(feat)
         _, _, _, temperature, spatial_T, _ = self.prompt_learner()
         tf = self._prompt_features(use_evidence)
         t_pos, t_neg = tf["text_features"], tf["text_features_neg"]
@@ -259,8 +279,10 @@ class DenseCLIPB200(nn.Module):
             self._packed_text = (tf, tuple(names), cat.to(torch.bfloat16).contiguous())
         logit_scale, spatial = self._scales(temperature, spatial_T, "image")
         dots = ops.gemm(local, self._packed_text[2], out_f32=True)                      # [B*P, n_txt*K] raw dot products
-        logits_local, neg_map, pos_map = ops.head_aggregate(dots, b, p, k, len(names), row_sumsq=ssq,
+        logits_local, neg_map, pos_map = ops.head_aggregate(dots, b, p, k, len(names), row_sumsq=ssq, row_mask=row_mask,
                                                             logit_scale=logit_scale, spatial_scale=spatial)
+        if row_mask is not None:
+            neg_map, pos_map = neg_map[1:], pos_map[1:]          # drop the class-token row: [P,B,K] patch maps
         g_unit = ops.l2norm_rows(g)
         g_add, topk_scores = None, None
         if self.caption_bank is not None:

@@ -129,6 +129,71 @@ class VisualRN:
         return local, ssq, g
 
 
+def _tower_blocks(g, prefix, layers):
+    out = []
+    for i in range(layers):
+        p = f"{prefix}.resblocks.{i}"
+        out.append({
+            "ln1": (g(p + ".ln_1.weight").float().contiguous(), g(p + ".ln_1.bias").float().contiguous()),
+            "ln2": (g(p + ".ln_2.weight").float().contiguous(), g(p + ".ln_2.bias").float().contiguous()),
+            "qkv": (g(p + ".attn.in_proj_weight").to(torch.bfloat16).contiguous(), g(p + ".attn.in_proj_bias").float().contiguous()),
+            "out": (g(p + ".attn.out_proj.weight").to(torch.bfloat16).contiguous(), g(p + ".attn.out_proj.bias").float().contiguous()),
+            "fc": (g(p + ".mlp.c_fc.weight").to(torch.bfloat16).contiguous(), g(p + ".mlp.c_fc.bias").float().contiguous()),
+            "proj": (g(p + ".mlp.c_proj.weight").to(torch.bfloat16).contiguous(), g(p + ".mlp.c_proj.bias").float().contiguous()),
+        })
+    return out
+
+
+class VisualViT:
+    """CLIP VisionTransformer tower (M:240-276) with this repo's dense last block (oracle `vit_dense`):
+    patch tokens of the last block take out_proj(v_proj(ln_1 x)) as their attention output (value path only,
+    the ViT analogue of T:405-411), the class token attends normally (tcgen05 attention kernel, one query row).
+    Residual stream fp32 [B*T, W]; GEMM operands bf16; token row b*T + 0 is the class token."""
+
+    def __init__(self, sd, patch, width, layers, heads, embed_dim, device):
+        g = lambda k: sd[k].detach().to(device)
+        self.patch, self.width, self.nlayers, self.heads, self.embed_dim, self.device = patch, width, layers, heads, embed_dim, device
+        k = 3 * patch * patch
+        self.kpad = (k + 63) // 64 * 64
+        w = torch.zeros((width, self.kpad), device=device, dtype=torch.float32)
+        w[:, :k] = g("visual.conv1.weight").float().reshape(width, k)
+        self.patch_w = w.to(torch.bfloat16).contiguous()
+        self.cls = g("visual.class_embedding").float().contiguous()
+        self.pos = g("visual.positional_embedding").float().contiguous()
+        self.ln_pre = (g("visual.ln_pre.weight").float().contiguous(), g("visual.ln_pre.bias").float().contiguous())
+        self.ln_post = (g("visual.ln_post.weight").float().contiguous(), g("visual.ln_post.bias").float().contiguous())
+        self.proj_t = g("visual.proj").t().to(torch.bfloat16).contiguous()           # [D, W] K-major
+        self.blocks = _tower_blocks(g, "visual.transformer", layers)
+
+    def _mlp(self, x, blk):
+        h, _, _, _ = ops.layernorm(x, *blk["ln2"])
+        u = ops.gemm(h, *blk["fc"], quick_gelu=True)
+        return ops.gemm_f32res(u, *blk["proj"], x)
+
+    def tokens(self, image):
+        """image fp32 NCHW [B,3,H,W] -> (feat bf16 [B*T, D] = ln_post(x) @ proj for every token, ssq fp32 [B*T], T)."""
+        b, _, hh, ww = image.shape
+        t = (hh // self.patch) * (ww // self.patch) + 1
+        assert t == self.pos.shape[0], f"image {hh}x{ww} does not match the positional embedding ({self.pos.shape[0]} tokens)"
+        w = self.width
+        emb = ops.gemm(ops.patchify(image.contiguous(), self.patch, self.kpad), self.patch_w)       # M:261
+        x = ops.vit_embed_ln(emb, self.cls, self.pos, *self.ln_pre, b, t)                           # M:262-266
+        for i, blk in enumerate(self.blocks):
+            h, _, _, _ = ops.layernorm(x, *blk["ln1"])
+            qkv = ops.gemm(h, *blk["qkv"])
+            if i + 1 < self.nlayers:
+                a = ops.attn_fwd(qkv, b, t, w, self.heads)
+            else:                                              # dense last block
+                a = ops.copy_cols(qkv, 2 * w, w)               # every token: its own value vector
+                ops.attn_fwd(qkv, b, t, w, self.heads, q_rows=1, out=a)      # class token: real attention
+            x = ops.gemm_f32res(a, *blk["out"], x)
+            x = self._mlp(x, blk)
+        h, _, _, _ = ops.layernorm(x, *self.ln_post)
+        ssq = torch.zeros((b * t,), device=image.device, dtype=torch.float32)
+        feat = ops.gemm(h, self.proj_t, row_sumsq=ssq)
+        return feat, ssq, t
+
+
 class TextTower:
     def __init__(self, sd, width, heads, layers, embed_dim, device):
         g = lambda k: sd[k].detach().to(device)

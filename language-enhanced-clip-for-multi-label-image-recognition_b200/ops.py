@@ -161,6 +161,36 @@ def attn_fwd(qkv, b, t, w, heads, q_rows=None, causal=False, out=None):
     return out
 
 
+def patchify(x, patch, kpad):
+    """x NCHW fp32 [B,3,H,W] -> bf16 [B*(H/p)*(W/p), kpad] patch rows (A operand of the patch-embedding GEMM)."""
+    _need(x, torch.float32, "x")
+    b, c, h, w = x.shape
+    assert c == 3
+    out = torch.empty((b * (h // patch) * (w // patch), kpad), device=x.device, dtype=torch.bfloat16)
+    check(lib.lecb_patchify(_ptr(x), _ptr(out), b, h, w, patch, kpad, _stream()), "lecb_patchify")
+    return out
+
+
+def vit_embed_ln(emb, cls, pos, gamma, beta, b, t, eps=1e-5):
+    """fp32 [B*T, D] = ln_pre([class_embedding ; emb] + positional_embedding)  (M:262-266)."""
+    _need(emb, torch.bfloat16, "emb")
+    d = emb.shape[-1]
+    out = torch.empty((b * t, d), device=emb.device, dtype=torch.float32)
+    check(lib.lecb_vit_embed_ln(_ptr(emb), _ptr(cls), _ptr(pos), _ptr(gamma), _ptr(beta), _ptr(out), b, t, d,
+                                float(eps), _stream()), "lecb_vit_embed_ln")
+    return out
+
+
+def copy_cols(src, col0, cols, out=None):
+    """bf16 [rows, cols] = src[:, col0:col0+cols] (hand-written strided copy)."""
+    _need(src, torch.bfloat16, "src")
+    rows, ld = src.shape
+    if out is None:
+        out = torch.empty((rows, cols), device=src.device, dtype=torch.bfloat16)
+    check(lib.lecb_copy_cols(_ptr(src), ld, col0, _ptr(out), out.shape[1], rows, cols, _stream()), "lecb_copy_cols")
+    return out
+
+
 def head_aggregate(dots, b, p, k, n_txt, row_sumsq=None, row_mask=None, logit_scale=4.0, spatial_scale=50.0,
                    want_maps=True):
     """dots fp32 [B*P, ldn] -> logits_local [B,K] (+ neg_map, pos_map [P,B,K])."""

@@ -17,6 +17,7 @@ Fixtures written:
   train_tiny.npz             same on the toy arch, B=6
   losses.npz                 ranking_loss / ASL_loss / dualcoop_loss values + grads on [16,80]
   map.npz                    reference numpy mAP on synthetic scores/labels
+  vit_{tiny,b16_224,l14_224}.npz   reference VisionTransformer.forward (class-token feature) on synthetic weights
 """
 from __future__ import annotations
 
@@ -136,6 +137,20 @@ def golden_train(tag, arch, batch, classnames, n_ctx, seed):
     np.savez_compressed(os.path.join(GOLD, f"train_{tag}.npz"), **out)
 
 
+def golden_vit(tag, arch, batch, seed):
+    """Reference `VisionTransformer.forward` (M:259-276) on the synthetic weights: pins the GLOBAL (class-token)
+    feature of the ViT path.  The dense patch features have no reference semantics."""
+    sd = synth.clip_state_dict(arch, seed=0)
+    img = synth.images(batch, arch.image_resolution, seed)
+    clip_model = RX.build_reference_clip(arch, sd)
+    with torch.no_grad():
+        g = clip_model.visual(img)
+    np.savez_compressed(os.path.join(GOLD, f"vit_{tag}.npz"), global_feat=g.float().numpy(),
+                        image_checksum=checksum(img), state_checksum=state_checksum(sd), batch=np.int64(batch),
+                        seed=np.int64(seed))
+    print(f"[vit_{tag}] global absmax={g.abs().max():.4f}", flush=True)
+
+
 def golden_losses():
     L = RX.loss_functions()
     g = torch.Generator().manual_seed(77)
@@ -188,6 +203,9 @@ def main(which=None):
         "head_rn50": lambda: golden_head("rn50_224", synth.RN50(224), 8, classnames, 16, 5000, 1235),
         "head_rn101": lambda: golden_head("rn101_448", synth.RN101(448), 2, classnames, 16, 2000, 1236, (True,)),
         "train_rn50": lambda: golden_train("rn50", synth.RN50(224), 4, classnames, 16, 1238),
+        "vit_tiny": lambda: golden_vit("tiny", synth.tiny_vit(), 3, 1250),
+        "vit_b16_224": lambda: golden_vit("b16_224", synth.VITB16(224), 2, 1251),
+        "vit_l14_224": lambda: golden_vit("l14_224", synth.VITL14(224), 1, 1252),
     }
     for name, fn in steps.items():
         if which and name not in which:

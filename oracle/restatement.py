@@ -86,6 +86,54 @@ def attnpool_global(sd, feat, heads):
 
 
 # --------------------------------------------------------------------------------------------
+# ViT visual tower (BASELINE configs 3, 5).  The reference `DenseCLIP` cannot wrap a VisionTransformer
+# (T:365-373 need layer4/attnpool; M:271-276 returns the class token only), so the DENSE output is this
+# repo's definition mirroring the ModifiedResNet rule "local = value->output path per patch,
+# global = the normally pooled token": in the LAST block every patch token's attention output is
+# out_proj(v_proj(ln_1(x))) (no q.k mixing) while the class token attends normally; then the block's
+# residual + MLP, ln_post and `proj` on every token.  The GLOBAL feature (token 0) is therefore exactly the
+# reference `VisionTransformer.forward` (M:259-276) and is pinned against it (tests/golden/vit_*.npz).
+# --------------------------------------------------------------------------------------------
+def vit_tokens(sd, image, patch, heads):
+    """M:259-276 up to (not including) the last residual block.  [B,3,H,W] -> x [B,1+P,W] after ln_pre and
+    blocks 0..L-2, plus the index of the last block."""
+    x = F.conv2d(image.float(), sd["visual.conv1.weight"], stride=patch)                  # M:261
+    b, w = x.shape[0], x.shape[1]
+    x = x.reshape(b, w, -1).permute(0, 2, 1)                                               # [B,P,W]
+    cls = sd["visual.class_embedding"].expand(b, 1, w)
+    x = torch.cat([cls, x], dim=1) + sd["visual.positional_embedding"]                     # M:264-265
+    x = F.layer_norm(x, (w,), sd["visual.ln_pre.weight"], sd["visual.ln_pre.bias"], 1e-5)
+    n = 0
+    while f"visual.transformer.resblocks.{n}.ln_1.weight" in sd:
+        n += 1
+    for i in range(n - 1):
+        x = _res_block(sd, f"visual.transformer.resblocks.{i}", x, heads, None)
+    return x, n - 1
+
+
+def vit_dense(sd, image, patch, heads):
+    """-> (g [B,D] = reference VisionTransformer output, local [P,B,D] = this repo's dense patch features)."""
+    x, last = vit_tokens(sd, image, patch, heads)
+    p = f"visual.transformer.resblocks.{last}"
+    b, t, w = x.shape
+    dh = w // heads
+    y = F.layer_norm(x, (w,), sd[p + ".ln_1.weight"], sd[p + ".ln_1.bias"], 1e-5)
+    qkv = F.linear(y, sd[p + ".attn.in_proj_weight"], sd[p + ".attn.in_proj_bias"])
+    q, k, v = qkv.split(w, dim=-1)
+    q0 = q[:, :1].reshape(b, 1, heads, dh).transpose(1, 2) * dh ** -0.5                     # class-token query only
+    kh = k.reshape(b, t, heads, dh).transpose(1, 2)
+    vh = v.reshape(b, t, heads, dh).transpose(1, 2)
+    o0 = (torch.softmax(q0 @ kh.transpose(-1, -2), dim=-1) @ vh).transpose(1, 2).reshape(b, 1, w)
+    a = torch.cat([o0, v[:, 1:]], dim=1)                                                    # patches: value path only
+    x = x + F.linear(a, sd[p + ".attn.out_proj.weight"], sd[p + ".attn.out_proj.bias"])
+    y = F.layer_norm(x, (w,), sd[p + ".ln_2.weight"], sd[p + ".ln_2.bias"], 1e-5)
+    x = x + F.linear(_quick_gelu(F.linear(y, sd[p + ".mlp.c_fc.weight"], sd[p + ".mlp.c_fc.bias"])),
+                     sd[p + ".mlp.c_proj.weight"], sd[p + ".mlp.c_proj.bias"])
+    x = F.layer_norm(x, (w,), sd["visual.ln_post.weight"], sd["visual.ln_post.bias"], 1e-5) @ sd["visual.proj"]
+    return x[:, 0], x[:, 1:].permute(1, 0, 2)
+
+
+# --------------------------------------------------------------------------------------------
 # text tower: T:72-101 TextEncoder over M:207-239 Transformer (causal mask M:364-370)
 # --------------------------------------------------------------------------------------------
 def _quick_gelu(x):
@@ -230,6 +278,15 @@ def dense_clip_test(sd, arch, image, pl_state, token_ids, use_evidence=False, ba
     feat = rn_trunk(sd, image, arch.vision_layers)
     local = local_features(sd, feat)
     g = attnpool_global(sd, feat, arch.vision_width * 32 // 64)
+    feats = [_unit(t) for t in prompt_features(sd, pl_state, token_ids, arch.transformer_heads, use_evidence)]
+    t_evi = feats[2] if use_evidence else None
+    return head_test(g, local, feats[0], feats[1], t_evi, bank, logit_scale, spatial_scale)
+
+
+def dense_clip_test_vit(sd, arch, image, pl_state, token_ids, use_evidence=False, bank=None,
+                        logit_scale=4.0, spatial_scale=50.0):
+    """The same head (T:441-472) on the ViT tower's dense tokens (repo-defined, see `vit_dense`)."""
+    g, local = vit_dense(sd, image, arch.vision_patch_size, arch.vision_width // 64)
     feats = [_unit(t) for t in prompt_features(sd, pl_state, token_ids, arch.transformer_heads, use_evidence)]
     t_evi = feats[2] if use_evidence else None
     return head_test(g, local, feats[0], feats[1], t_evi, bank, logit_scale, spatial_scale)

@@ -50,3 +50,24 @@ def test_attn_fwd_peaked_and_partial_rows():
     o3 = out1.view(b, t, w)
     assert (o3[:, 0].float() - want.view(b, t, w)[:, 0]).abs().max().item() <= want.abs().max().item() * 2.0 ** -6
     assert (o3[:, 1:] == 7.0).all()
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_attn_fwd_growing_scores_triggers_rescale(causal):
+    """Keys late in the sequence carry much larger scores than the first block: exercises the lazy-rescale path
+    (exact re-max of the block + in-place rescale of O in TMEM)."""
+    from lecb200 import ops
+    b, t, heads = 2, 640, 2
+    w = heads * 64
+    g = torch.Generator(device="cpu").manual_seed(11)
+    x = torch.randn((b, t, 3, heads, 64), generator=g)
+    ramp = torch.linspace(0.2, 9.0, t).view(1, t, 1, 1)
+    x[:, :, 1] *= ramp                                  # key magnitude grows along the sequence
+    x[:, :, 0] *= 3.0
+    qkv = x.reshape(b * t, 3 * w).cuda().bfloat16()
+    out = ops.attn_fwd(qkv, b, t, w, heads, causal=causal)
+    torch.cuda.synchronize()
+    want = _ref(qkv, b, t, w, heads, causal)
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - want).abs().max().item()
+    assert err <= want.abs().max().item() * 2.0 ** -6 + 1e-3, f"err {err}"

@@ -86,3 +86,27 @@ def test_gemm_rejects_bad_args():
     w = torch.zeros((8, 40), device="cuda", dtype=torch.bfloat16)
     with pytest.raises(LecbError):
         ops.gemm(a, w)          # K not a multiple of 32
+
+
+@pytest.mark.parametrize("m,n,k", [(300, 256, 512), (1111, 64, 64), (515, 768, 768), (50176, 240, 512), (100, 32, 64),
+                                   (4000, 1024, 3072)])
+def test_gemm_f32_out_staged(m, n, k):
+    """fp32 output (+ fp32 residual) through the staged TMA-store epilogue (32-column blocks), N tails, ragged M."""
+    from lecb200 import ops
+    a = _rand((m, k), 11).bfloat16()
+    w = _rand((n, k), 12, k ** -0.5).bfloat16()
+    bias = _rand((n,), 13)
+    res = _rand((m, n), 14)
+    base = a.float() @ w.float().t() + bias
+    tol = 2e-3 * (base.abs().max().item() + 1)
+    out = ops.gemm(a, w, bias, out_f32=True)
+    assert (out - base).abs().max().item() <= tol
+    out = ops.gemm_f32res(a, w, bias, res)
+    assert (out - (base + res)).abs().max().item() <= tol
+    ssq = torch.zeros((m,), device="cuda")
+    out = ops.gemm(a, w, bias, out_f32=True, row_sumsq=ssq)
+    torch.cuda.synchronize()
+    want = out.pow(2).sum(-1)
+    assert ((ssq - want).abs() / (want + 1e-6)).max().item() < 1e-4
+    g = ops.gemm(a, w, bias, quick_gelu=True, out_f32=True)
+    assert (g - base * torch.sigmoid(1.702 * base)).abs().max().item() <= tol

@@ -88,3 +88,20 @@ def test_map_matches_reference():
     g = C.load("map.npz")
     got = R.mean_average_precision(g["targets"], g["scores"])
     assert abs(got - float(g["mAP"])) < 1e-9
+
+
+@pytest.mark.parametrize("tag,arch_fn", [("tiny", lambda: C.synth.tiny_vit()), ("b16_224", lambda: C.synth.VITB16(224)),
+                                         ("l14_224", lambda: C.synth.VITL14(224))])
+def test_vit_global_matches_reference(tag, arch_fn):
+    """The ViT path's global (class-token) feature is the reference VisionTransformer.forward output (M:259-276)."""
+    g = C.load(f"vit_{tag}.npz")
+    arch = arch_fn()
+    sd = C.synth.clip_state_dict(arch, 0)
+    img = C.synth.images(int(g["batch"]), arch.image_resolution, int(g["seed"]))
+    np.testing.assert_allclose(C.checksum(img), g["image_checksum"], rtol=1e-12, err_msg="RNG drift: images")
+    with torch.no_grad():
+        glob, local = R.vit_dense(sd, img, arch.vision_patch_size, arch.vision_width // 64)
+    np.testing.assert_allclose(glob.numpy(), g["global_feat"], atol=ATOL, rtol=1e-4)
+    grid = arch.image_resolution // arch.vision_patch_size
+    assert tuple(local.shape) == (grid * grid, int(g["batch"]), arch.embed_dim)
+    assert torch.isfinite(local).all()
