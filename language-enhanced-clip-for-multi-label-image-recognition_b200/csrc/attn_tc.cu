@@ -2,18 +2,19 @@
 // full attention (M:207-228 inside M:240-276) and, with `causal`, the text transformer's masked
 // attention (M:364-370).
 //
-// One CTA = one (image, head, 128-query tile); two CTAs are co-resident per SM so one tile's softmax
-// overlaps the other's MMAs.  Per 128-key block:
-//   S = Q K^T      tcgen05.mma  M=128 N=128 K=64, Q/K tiles TMA-loaded (128B swizzle), fp32 S in TMEM
-//   P = exp2(S*c - m*c)   four softmax warps, thread == query row (tcgen05.ld 32x32b), online max / sum,
-//                         P written to shared memory as the bf16 K-major A operand of the next MMA
-//   O_blk = P V    tcgen05.mma  M=128 N=64 K=128, V tile used in place as an MN-major B operand
+// One CTA = one (image, head, 128-query tile); two CTAs are co-resident per SM.  K / V arrive as 128-key TMA
+// tiles (128B swizzle) and are consumed in 64-key sub-blocks with double-buffered S (TMEM) and P (smem), so
+// the tensor pipe computes Q K^T of sub-block j+1 while the softmax warps work on sub-block j:
+//   S = Q K^T      tcgen05.mma  M=128 N=64 K=64, fp32 S in TMEM
+//   P = exp2(S*c - m*c)   four softmax warps, thread == query row (tcgen05.ld 32x32b), row sums in registers,
+//                         P packed to bf16 pairs and written back to TMEM (tcgen05.st): it never touches smem
+//   O += P V       tcgen05.mma  M=128 N=64 K=64, A = P from TMEM, V tile used in place as an MN-major B operand
 // O accumulates in TMEM across key blocks.  The softmax reference point m is only moved when a block's
 // probabilities would grow past 2^15 relative to it (lazy rescaling): block 0 takes an exact two-pass max,
-// later blocks are a single pass over S with the running m, and only a warp that sees a row sum above the
+// later sub-blocks are a single pass over S with the running m, and only a warp that sees a row sum above the
 // threshold re-does the block exactly and rescales its 32 rows of O in TMEM (tcgen05.ld / tcgen05.st) before
 // the block's PV MMA is released.  The result o / l is independent of where m sits.
-// TMEM: S [0,128) | O [128,192).
+// TMEM: S0 [0,64) | S1 [64,128) | O [128,192) | P0 [192,224) | P1 [224,256).
 //
 // Warps: 0-3 softmax (TMEM lane quarter == warp id), 4 TMA producer, 5 MMA issuer + TMEM owner.
 #include <stdio.h>
@@ -26,16 +27,16 @@
 
 namespace lecb {
 
-constexpr int kAtTile = 128;        // queries per CTA and keys per block
+constexpr int kAtTile = 128;        // queries per CTA and keys per TMA tile
+constexpr int kAtSub = 64;          // keys per softmax / MMA sub-block
 constexpr int kAtDh = 64;
 constexpr int kAtThreads = 192;
 constexpr int kAtTileBytes = kAtTile * kAtDh * 2;    // 16 KB
 constexpr int kAtSmemQ = 0;
 constexpr int kAtSmemK = kAtTileBytes;               // 2 stages
 constexpr int kAtSmemV = 3 * kAtTileBytes;           // 2 stages
-constexpr int kAtSmemP = 5 * kAtTileBytes;           // 2 blocks of 64 keys (128 x 64 bf16 each)
-constexpr int kAtSmemBars = 7 * kAtTileBytes;
-constexpr int kAtSmemBytes = kAtSmemBars + 128;
+constexpr int kAtSmemBars = 5 * kAtTileBytes;
+constexpr int kAtSmemBytes = kAtSmemBars + 160;
 constexpr int kAtTmemCols = 256;
 
 struct AttnParams {
@@ -68,18 +69,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   uint8_t* sQ = smem + kAtSmemQ;
   uint8_t* sK = smem + kAtSmemK;
   uint8_t* sV = smem + kAtSmemV;
-  uint8_t* sP = smem + kAtSmemP;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAtSmemBars);
   uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;     // [2]
+  uint64_t* k_full = bars + 1;     // [2] 128-key K tiles
   uint64_t* k_empty = bars + 3;    // [2]
   uint64_t* v_full = bars + 5;     // [2]
   uint64_t* v_empty = bars + 7;    // [2]
-  uint64_t* s_full = bars + 9;
-  uint64_t* s_free = bars + 10;
-  uint64_t* p_full = bars + 11;
-  uint64_t* p_free = bars + 12;    // PV MMA of the block complete: P reusable, O includes the block
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* s_full = bars + 9;     // [2] S buffer holds Q K^T of a 64-key sub-block
+  uint64_t* s_free = bars + 11;    // [2] softmax has read it
+  uint64_t* p_full = bars + 13;    // [2] P block written
+  uint64_t* p_free = bars + 15;    // [2] PV MMA of the sub-block complete: P reusable, O includes the sub-block
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -87,7 +87,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int kv_end = p.causal ? min(p.T, q0 + kAtTile) : p.T;
-  const int n_kv = (kv_end + kAtTile - 1) / kAtTile;
+  const int n_sub = (kv_end + kAtSub - 1) / kAtSub;      // 64-key sub-blocks
+  const int n_kv = (n_sub + 1) / 2;                      // 128-key K / V tiles
 
   if (warp == 4 && lane == 0) {
     if ((smem_u32(smem) & 1023u) != 0) __trap();     // swizzled tiles need 1024-byte alignment
@@ -98,11 +99,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&p_free[i], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(s_free, 4);
-    mbar_init(p_full, 4);
-    mbar_init(p_free, 1);
     fence_barrier_init();
   }
   if (warp == 5) {
@@ -132,43 +133,45 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     }
   } else if (warp == 5) {
     // ------------------------------- MMA issuer ---------------------------------
+    // Sub-block jj uses S/P buffer jj & 1 and the (jj & 1) half of K/V tile jj >> 1.  QK^T of sub-block jj+1 is
+    // issued before PV of sub-block jj, so the tensor pipe always runs one S ahead of the softmax warps.
     if (lane == 0) {
-      constexpr uint32_t idesc_qk = attn_idesc(kAtTile, false);
+      constexpr uint32_t idesc_qk = attn_idesc(kAtSub, false);
       constexpr uint32_t idesc_pv = attn_idesc(kAtDh, true);
-      const uint32_t tS = tmem_base;
+      const uint32_t tO = tmem_base + 128u;
       auto issue_pv = [&](int i) {
-        const int s = i & 1;
-        mbar_wait(&v_full[s], (i >> 1) & 1);
-        mbar_wait(p_full, i & 1);
+        const int bf = i & 1, tile = i >> 1, s = tile & 1;
+        if (bf == 0) mbar_wait(&v_full[s], (tile >> 1) & 1);
+        mbar_wait(&p_full[bf], (i >> 1) & 1);
         tc_fence_after();
-        const uint32_t tO = tmem_base + 128u;
 #pragma unroll
-        for (int kk = 0; kk < kAtTile / 16; ++kk) {
-          // A = P: two 64-key K-major blocks, 16 keys (32 bytes) per step inside a block
-          const uint64_t adesc = make_kmajor_desc(smem_u32(sP + (kk >> 2) * kAtTileBytes), 128) + static_cast<uint64_t>(2 * (kk & 3));
-          // B = V tile [keys][dh] used as an MN-major operand: 16 keys = 2048 bytes per step
-          const uint64_t bdesc = make_kmajor_desc(smem_u32(sV + s * kAtTileBytes + kk * 2048), 128);
-          umma_f16(tO, adesc, bdesc, idesc_pv, (i | kk) != 0 ? 1u : 0u);
+        for (int kk = 0; kk < kAtSub / 16; ++kk) {
+          // A = P block in TMEM: bf16 pairs packed per column, 16 keys = 8 columns per step
+          const uint32_t tP = tmem_base + 192u + static_cast<uint32_t>(bf * (kAtSub / 2) + kk * 8);
+          // B = V tile [keys][dh] used in place as an MN-major operand: 16 keys = 2048 bytes per step
+          const uint64_t bdesc = make_kmajor_desc(smem_u32(sV + s * kAtTileBytes + bf * (kAtSub * 128) + kk * 2048), 128);
+          umma_f16_ts(tO, tP, bdesc, idesc_pv, (i | kk) != 0 ? 1u : 0u);
         }
-        umma_commit(&v_empty[s]);
-        umma_commit(p_free);
+        if (bf == 1 || i == n_sub - 1) umma_commit(&v_empty[s]);
+        umma_commit(&p_free[bf]);
       };
       mbar_wait(q_full, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int s = j & 1;
-        mbar_wait(&k_full[s], (j >> 1) & 1);
-        if (j >= 1) mbar_wait(s_free, (j - 1) & 1);
+      for (int jj = 0; jj < n_sub; ++jj) {
+        const int bf = jj & 1, tile = jj >> 1, s = tile & 1;
+        if (bf == 0) mbar_wait(&k_full[s], (tile >> 1) & 1);
+        if (jj >= 2) mbar_wait(&s_free[bf], ((jj >> 1) - 1) & 1);
         tc_fence_after();
         const uint64_t adesc = make_kmajor_desc(smem_u32(sQ), 128);
-        const uint64_t bdesc = make_kmajor_desc(smem_u32(sK + s * kAtTileBytes), 128);
+        const uint64_t bdesc = make_kmajor_desc(smem_u32(sK + s * kAtTileBytes + bf * (kAtSub * 128)), 128);
 #pragma unroll
         for (int k = 0; k < kAtDh / 16; ++k)
-          umma_f16(tS, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc_qk, k != 0 ? 1u : 0u);
-        umma_commit(&k_empty[s]);
-        umma_commit(s_full);
-        if (j >= 1) issue_pv(j - 1);
+          umma_f16(tmem_base + static_cast<uint32_t>(bf * kAtSub), adesc + static_cast<uint64_t>(2 * k),
+                   bdesc + static_cast<uint64_t>(2 * k), idesc_qk, k != 0 ? 1u : 0u);
+        if (bf == 1 || jj == n_sub - 1) umma_commit(&k_empty[s]);
+        umma_commit(&s_full[bf]);
+        if (jj >= 1) issue_pv(jj - 1);
       }
-      issue_pv(n_kv - 1);
+      issue_pv(n_sub - 1);
     }
   } else {
     // ------------------------------- softmax warps (thread == query row) --------
@@ -177,87 +180,87 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     const int qi = q0 + row;
     const int limit = p.causal ? min(p.T - 1, qi) : p.T - 1;       // last key index this row may see
     float m = -INFINITY, l = 0.f;
-    const uint32_t tS = tmem_base + lane_base;
     const uint32_t tO = tmem_base + lane_base + 128u;
 
-    // exact row maximum of the (masked) block
-    auto block_max = [&](bool need_mask, int lim) {
+    // exact row maximum of the (masked) 64-key sub-block in S buffer `tS`
+    auto block_max = [&](uint32_t tS, bool need_mask, int lim) {
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32(tS, ra);
+      tmem_ld_32x32(tS + 32u, rb);
+      tmem_ld_wait();
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c4 = 0; c4 < 4; ++c4) {
-        uint32_t r[32];
-        tmem_ld_32x32(tS + static_cast<uint32_t>(c4 * 32), r);
-        tmem_ld_wait();
-        if (need_mask) {
+      if (need_mask) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c4 * 32 + i <= lim) ? __uint_as_float(r[i]) : -INFINITY);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        for (int i = 0; i < 32; ++i) {
+          mx = fmaxf(mx, (i <= lim) ? __uint_as_float(ra[i]) : -INFINITY);
+          mx = fmaxf(mx, (32 + i <= lim) ? __uint_as_float(rb[i]) : -INFINITY);
         }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(ra[i]), __uint_as_float(rb[i])));
       }
       return mx;
     };
-    // P = exp2(S*sc - msc) -> bf16 K-major operand in shared memory; returns the row sum.  The TMEM load of
-    // chunk c+1 is in flight while chunk c is exponentiated.  `wait_bar` (P buffer free) is taken just before
-    // the first store so the wait hides behind the first chunk's math.
-    auto write_p_impl = [&](auto mask_tag, float msc, int lim, uint64_t* wait_bar, uint32_t wait_parity) {
+    // P = exp2(S*sc - msc) -> bf16 K-major operand block in shared memory; returns the row sum.  The second
+    // 32-column TMEM load is in flight while the first half is exponentiated; `wait_bar` (P block free) is
+    // taken just before the first store so that wait hides behind the first half's math.
+    auto write_p_impl = [&](auto mask_tag, uint32_t tS, uint32_t tP, float msc, int lim, uint64_t* wait_bar,
+                            uint32_t wait_parity) {
       constexpr bool kMask = decltype(mask_tag)::value;
       float sum = 0.f;
-      uint32_t ra[32], rb[32];
+      uint32_t ra[32], rb[32], pk[32];
       tmem_ld_32x32(tS, ra);
       tmem_ld_wait();
+      tmem_ld_32x32(tS + 32u, rb);
 #pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        uint32_t(&r)[32] = (c4 & 1) ? rb : ra;
-        uint32_t(&rn)[32] = (c4 & 1) ? ra : rb;
-        if (c4 < 3) tmem_ld_32x32(tS + static_cast<uint32_t>((c4 + 1) * 32), rn);
-        float pv[32];
+      for (int c2 = 0; c2 < 2; ++c2) {
+        uint32_t(&r)[32] = c2 ? rb : ra;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float e = fast_exp2(fmaf(__uint_as_float(r[i]), p.sc, -msc));
-          if (kMask && c4 * 32 + i > lim) e = 0.f;
-          pv[i] = e;
-          sum += e;
+        for (int i = 0; i < 32; i += 2) {
+          float e0 = fast_exp2(fmaf(__uint_as_float(r[i]), p.sc, -msc));
+          float e1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), p.sc, -msc));
+          if (kMask && c2 * 32 + i > lim) e0 = 0.f;
+          if (kMask && c2 * 32 + i + 1 > lim) e1 = 0.f;
+          sum += e0 + e1;
+          pk[c2 * 16 + i / 2] = pack_bf16(e0, e1);
         }
-        if (c4 == 0 && wait_bar != nullptr) mbar_wait(wait_bar, wait_parity);
-        uint8_t* pblk = sP + (c4 >> 1) * kAtTileBytes;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 u;
-          u.x = pack_bf16(pv[q * 8 + 0], pv[q * 8 + 1]);
-          u.y = pack_bf16(pv[q * 8 + 2], pv[q * 8 + 3]);
-          u.z = pack_bf16(pv[q * 8 + 4], pv[q * 8 + 5]);
-          u.w = pack_bf16(pv[q * 8 + 6], pv[q * 8 + 7]);
-          *reinterpret_cast<uint4*>(pblk + swizzled_chunk_offset(row, (c4 & 1) * 4 + q, 128)) = u;
-        }
-        if (c4 < 3) tmem_ld_wait();
+        if (c2 == 0) tmem_ld_wait();
       }
+      if (wait_bar != nullptr) mbar_wait(wait_bar, wait_parity);      // PV of sub-block jj-2 has consumed this P buffer
+      tmem_st_32x32(tP, pk);
+      tmem_st_wait();
       return sum;
     };
     // the mask test costs two extra instructions per score: only the ragged last block / causal diagonal pays it
-    auto write_p = [&](float msc, bool need_mask, int lim, uint64_t* wait_bar, uint32_t wait_parity) {
-      return need_mask ? write_p_impl(std::true_type{}, msc, lim, wait_bar, wait_parity)
-                       : write_p_impl(std::false_type{}, msc, lim, wait_bar, wait_parity);
+    auto write_p = [&](uint32_t tS, uint32_t tP, float msc, bool need_mask, int lim, uint64_t* wait_bar,
+                       uint32_t wait_parity) {
+      return need_mask ? write_p_impl(std::true_type{}, tS, tP, msc, lim, wait_bar, wait_parity)
+                       : write_p_impl(std::false_type{}, tS, tP, msc, lim, wait_bar, wait_parity);
     };
 
-    for (int j = 0; j < n_kv; ++j) {
-      const int kv0 = j * kAtTile;
-      const bool need_mask = (kv0 + kAtTile > p.T) || (p.causal && kv0 + kAtTile - 1 > q0);
+    for (int jj = 0; jj < n_sub; ++jj) {
+      const int bf = jj & 1;
+      const uint32_t par = (jj >> 1) & 1;
+      const int kv0 = jj * kAtSub;
+      const bool need_mask = (kv0 + kAtSub > p.T) || (p.causal && kv0 + kAtSub - 1 > q0);
       const int lim = limit - kv0;             // columns c <= lim are visible
-      mbar_wait(s_full, j & 1);
+      const uint32_t tS = tmem_base + lane_base + static_cast<uint32_t>(bf * kAtSub);
+      const uint32_t pblk = tmem_base + lane_base + 192u + static_cast<uint32_t>(bf * (kAtSub / 2));
+      uint64_t* pf = jj >= 2 ? &p_free[bf] : nullptr;          // PV of sub-block jj-2 read this P block
+      mbar_wait(&s_full[bf], par);
       tc_fence_after();
-      if (j == 0) {
-        m = block_max(need_mask, lim);
-        l = write_p(m * p.sc, need_mask, lim, nullptr, 0);
+      if (jj == 0) {
+        m = block_max(tS, need_mask, lim);
+        l = write_p(tS, pblk, m * p.sc, need_mask, lim, nullptr, 0);
       } else {
-        float sum = write_p(m * p.sc, need_mask, lim, p_free, (j - 1) & 1);
-        // lazy rescaling: keep m unless some probability of this block is enormous relative to it
+        float sum = write_p(tS, pblk, m * p.sc, need_mask, lim, pf, par ^ 1);
+        // lazy rescaling: keep m unless some probability of this sub-block is enormous relative to it
         if (__any_sync(0xffffffffu, !(sum <= 32768.f))) {
-          const float m_new = fmaxf(m, block_max(need_mask, lim));
+          const float m_new = fmaxf(m, block_max(tS, need_mask, lim));
           const float alpha = fast_exp2((m - m_new) * p.sc);
-          // PV of block j-1 has completed (p_free waited in write_p) and PV of block j is not released yet:
+          // every PV up to sub-block jj-1 must have landed in O; PV of sub-block jj is not released yet, so
           // this warp's 32 rows of O can be rescaled in place
+          mbar_wait(&p_free[bf ^ 1], ((jj - 1) >> 1) & 1);
           tc_fence_after();
 #pragma unroll 1
           for (int hlf = 0; hlf < 2; ++hlf) {
@@ -269,22 +272,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
             tmem_st_32x32(tO + static_cast<uint32_t>(hlf * 32), r);
           }
           tmem_st_wait();
-          sum = write_p(m_new * p.sc, need_mask, lim, nullptr, 0);
+          sum = write_p(tS, pblk, m_new * p.sc, need_mask, lim, nullptr, 0);
           l *= alpha;
           m = m_new;
         }
         l += sum;
       }
       tc_fence_before();
-      fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(s_free);
-        mbar_arrive(p_full);
+        mbar_arrive(&s_free[bf]);
+        mbar_arrive(&p_full[bf]);
       }
     }
-    // all PV MMAs done -> O complete
-    mbar_wait(p_free, (n_kv - 1) & 1);
+    // all PV MMAs done -> O complete (the last two sub-blocks' commits cover every earlier MMA)
+    if (n_sub >= 2) mbar_wait(&p_free[(n_sub - 2) & 1], ((n_sub - 2) >> 1) & 1);
+    mbar_wait(&p_free[(n_sub - 1) & 1], ((n_sub - 1) >> 1) & 1);
     tc_fence_after();
     {      // the tcgen05.ld is warp-collective: every lane loads, only valid query rows store
       uint32_t r0[32], r1[32];

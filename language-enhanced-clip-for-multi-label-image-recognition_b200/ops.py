@@ -144,6 +144,12 @@ def attnpool_query0(q, kmat, vmat, b, p, heads):
 
 
 def causal_attn(qkv, n, l, w, heads):
+    """Text-tower masked self-attention (M:221-223, mask M:364-370) on the tcgen05 attention kernel."""
+    return attn_fwd(qkv, n, l, w, heads, causal=True)
+
+
+def causal_attn_smem(qkv, n, l, w, heads):
+    """The CUDA-core shared-memory variant (kept as an independent cross-check of the tensor-core kernel)."""
     _need(qkv, torch.bfloat16, "qkv")
     out = torch.empty((n * l, w), device=qkv.device, dtype=torch.bfloat16)
     check(lib.lecb_causal_attn_fwd(_ptr(qkv), _ptr(out), n, l, w, heads, _stream()), "lecb_causal_attn_fwd")

@@ -71,3 +71,16 @@ def test_attn_fwd_growing_scores_triggers_rescale(causal):
     assert torch.isfinite(out.float()).all()
     err = (out.float() - want).abs().max().item()
     assert err <= want.abs().max().item() * 2.0 ** -6 + 1e-3, f"err {err}"
+
+
+def test_causal_tc_matches_smem_kernel():
+    """Two independent implementations of the text tower's causal attention agree (tcgen05 vs CUDA-core smem kernel)."""
+    from lecb200 import ops
+    n, l, heads = 37, 77, 8
+    w = heads * 64
+    g = torch.Generator(device="cpu").manual_seed(3)
+    qkv = torch.randn((n * l, 3 * w), generator=g).cuda().bfloat16()
+    a = ops.causal_attn(qkv, n, l, w, heads).float()
+    b = ops.causal_attn_smem(qkv, n, l, w, heads).float()
+    torch.cuda.synchronize()
+    assert (a - b).abs().max().item() <= 2.0 ** -6 * b.abs().max().item()
