@@ -330,9 +330,20 @@ def main():
         gemm_n = sum(table[n]["launches"] for n in ("lecb_gemm_bf16", "lecb_conv3x3_bf16") if n in table)
         total_ms = sum(d["ms"] for d in table.values())
         achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12
+        # DRAM bytes per launch of the same kernel family, from the committed ncu pass over one bench step
+        # (tools/gpu_profile_traffic.sh -> tools/summarize_ncu.py); never measured live (ncu is not a bench)
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "r01_step_traffic_summary.json")
+        if os.path.exists(tpath) and B == 256:
+            with open(tpath) as f:
+                fam = json.load(f)["by_kernel_family"].get("gemm_kernel")
+            if fam:
+                traffic, traffic_src = fam["dram_bytes_per_launch"], "profiles/r01_step_traffic_summary.json (ncu dram__bytes_read+write, mean over the step's launches)"
+        gemm_by = sum(table[n]["bytes"] for n in ("lecb_gemm_bf16", "lecb_conv3x3_bf16") if n in table)
         roofline = {"kernel": "lecb::gemm_kernel<BN,BK,conv> (tcgen05 GEMM + TMA-im2col conv)", "bound": "tensor",
                     "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
-                    "traffic": None, "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
+                    "traffic": traffic, "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": gemm_by / max(gemm_n, 1), "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
                     "launches_per_step": gemm_n, "avg_launch_us": 1e3 * gemm_ms / max(gemm_n, 1),
                     "share_of_step": gemm_ms / total_ms, "algorithmic_gflop_per_step": gemm_fl / 1e9}
         if args.profile_out:

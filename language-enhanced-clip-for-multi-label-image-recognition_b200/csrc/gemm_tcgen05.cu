@@ -569,6 +569,8 @@ static int dispatch(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& t
   if (p.num_kb <= 2) return dispatch_nb<kConv, 8>(BN, BK, tmA, tmB, p, s);
   if (p.num_kb <= 4) return dispatch_nb<kConv, 5>(BN, BK, tmA, tmB, p, s);
   if (p.num_kb <= 8) return dispatch_nb<kConv, 4>(BN, BK, tmA, tmB, p, s);
+  // fp32 output / residual moves twice the bytes per element: keep four blocks in flight up to K = 1024
+  if ((p.flags & LECB_EPI_OUT_F32) && p.num_kb <= 16) return dispatch_nb<kConv, 4>(BN, BK, tmA, tmB, p, s);
   return dispatch_nb<kConv, 2>(BN, BK, tmA, tmB, p, s);
 }
 

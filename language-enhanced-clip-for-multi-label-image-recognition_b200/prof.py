@@ -44,7 +44,8 @@ def _work(name, a):
     if name == "lecb_head_aggregate":
         ldn, b, p, k, n_txt = a[1], a[7], a[8], a[9], a[10]
         maps = 2 if a[5] else 0
-        return 20.0 * b * p * k, 4.0 * b * p * (n_txt * k + maps * k) + 4.0 * b * k
+        cols_read = n_txt if a[5] else n_txt - 1          # the positive columns are only read for the pos_map output
+        return 20.0 * b * p * k, 4.0 * b * p * (cols_read * k + maps * k) + 4.0 * b * k
     if name == "lecb_l2norm_rows":
         rows, d = a[2], a[3]
         return 3.0 * rows * d, rows * d * ((2 if a[4] else 4) + (2 if a[5] else 4))

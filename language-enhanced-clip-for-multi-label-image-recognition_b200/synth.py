@@ -59,7 +59,7 @@ def VITL14(res=448):
     return ClipArch(768, res, 24, 1024, 14, transformer_width=768, transformer_heads=12)
 
 
-def tiny_vit(res=64, patch=16, width=128, layers=3, embed_dim=64, text_width=64, text_layers=2):
+def tiny_vit(res=96, patch=16, width=128, layers=3, embed_dim=256, text_width=64, text_layers=2):
     """A small VisionTransformer-shaped arch (head dim 64 like every CLIP ViT) for fast tests."""
     return ClipArch(embed_dim, res, layers, width, patch, 77, 49408, text_width, max(1, text_width // 64), text_layers)
 

@@ -44,7 +44,8 @@ ssq = torch.rand((B * P,), device=dev) + 0.5
 ms = timeit(lambda: ops.head_aggregate(dots, B, P, K, 3, row_sumsq=ssq, want_maps=True))
 report("head_aggregate (evidence, maps)", B * P * (3 * K + 2 * K) * 4 + B * P * 4 + B * K * 4, ms, f"B={B} P={P} K={K}")
 ms = timeit(lambda: ops.head_aggregate(dots, B, P, K, 3, row_sumsq=ssq, want_maps=False))
-report("head_aggregate (evidence, no maps)", B * P * 3 * K * 4 + B * P * 4 + B * K * 4, ms, f"B={B} P={P} K={K}")
+# without the map outputs the positive-prompt columns are never read: 2K of the 3K floats per row
+report("head_aggregate (evidence, no maps)", B * P * 2 * K * 4 + B * P * 4 + B * K * 4, ms, f"B={B} P={P} K={K}")
 del dots
 # ASL fwd+bwd
 n = 1 << 21
