@@ -31,6 +31,7 @@ namespace lecb {
 constexpr int kTileM = 128;
 constexpr int kNumThreads = 352;
 constexpr int kWarpTma = 8, kWarpMma = 9, kWarpDma = 10;
+constexpr int kMaxStages = 8;
 
 template <int BN, int BK, int NB>
 struct GemmCfg {
@@ -61,8 +62,10 @@ struct GemmParams {
   int staged;        // output through swizzled smem blocks + TMA store (bf16: 64 columns per block, fp32: 32)
   int out_f32;       // staged fp32 output (+ optional fp32 residual)
   int cblocks;       // staged blocks per tile = BN / columns per block
-  int b_resident;    // all K blocks of the (single) W tile stay in smem for the CTA's lifetime; A ring gets the rest
+  int b_resident;    // all K blocks of this CTA's W tile stay in smem for the CTA's lifetime (the CTA owns ONE n tile
+                     // and strides over m tiles); the A ring gets the rest of the operand region
   int res_stages;    // A-ring depth in b_resident mode
+  int operand_bytes; // size of the operand region (ring, or resident W + A ring); staging buffers follow it
   // conv mode
   int H, W, kb_per_tap;
 };
@@ -79,11 +82,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * Cfg::kABytes;
-  uint8_t* sC = smem + kStages * Cfg::kStageBytes;
+  uint8_t* sC = smem + p.operand_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sC + NB * Cfg::kCBytes);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + kStages;
-  uint64_t* tfull = bars + 2 * kStages;
+  uint64_t* full = bars;                       // [kMaxStages] (the resident-W mode may run a deeper A ring)
+  uint64_t* empty = bars + kMaxStages;
+  uint64_t* tfull = bars + 2 * kMaxStages;
   uint64_t* tempty = tfull + 2;
   uint64_t* cfree = tempty + 2;
   uint64_t* cfull = cfree + NB;
@@ -96,11 +99,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  // Tile schedule.  Default: tile t = blockIdx.x + i * gridDim.x, n fastest.  b_resident: the CTA keeps n tile
+  // blockIdx.x % num_n_tiles and walks m tiles blockIdx.x / num_n_tiles + i * (gridDim.x / num_n_tiles).
+  const int res_n = p.b_resident ? static_cast<int>(blockIdx.x) % p.num_n_tiles : 0;
+  const int res_m0 = p.b_resident ? static_cast<int>(blockIdx.x) / p.num_n_tiles : 0;
+  const int res_ms = p.b_resident ? static_cast<int>(gridDim.x) / p.num_n_tiles : 1;
+  const int my_tiles = p.b_resident
+                           ? (res_m0 < p.num_m_tiles ? (p.num_m_tiles - res_m0 + res_ms - 1) / res_ms : 0)
+                           : (static_cast<int>(blockIdx.x) < num_tiles ? (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0);
+  auto tile_coords = [&](int i, int& m_blk, int& n_blk) {
+    if (p.b_resident) {
+      m_blk = res_m0 + i * res_ms;
+      n_blk = res_n;
+    } else {
+      const int tile = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
+      m_blk = tile / p.num_n_tiles;
+      n_blk = tile - m_blk * p.num_n_tiles;
+    }
+  };
 
   if (warp == kWarpTma && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
@@ -131,13 +152,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      if (p.b_resident && blockIdx.x < num_tiles) {      // the whole W tile once per CTA
+      if (p.b_resident && my_tiles > 0) {      // this CTA's whole W tile, once
         mbar_arrive_expect_tx(bres, static_cast<uint32_t>(p.num_kb) * Cfg::kBBytes);
-        for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(&tmB, bres, smem + kb * Cfg::kBBytes, kb * BK, 0);
+        for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(&tmB, bres, smem + kb * Cfg::kBBytes, kb * BK, res_n * BN);
       }
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.num_n_tiles;
-        const int n_blk = tile - m_blk * p.num_n_tiles;
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        int m_blk, n_blk;
+        tile_coords(ti, m_blk, n_blk);
         int pw = 0, ph = 0, pn = 0;
         if (kConv) {
           const int64_t m0 = static_cast<int64_t>(m_blk) * kTileM;
@@ -175,8 +196,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      if (p.b_resident && blockIdx.x < num_tiles) mbar_wait(bres, 0);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      if (p.b_resident && my_tiles > 0) mbar_wait(bres, 0);
+      for (int ti = 0; ti < my_tiles; ++ti) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
@@ -206,16 +227,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp == kWarpDma) {
     // ------------------------------- epilogue DMA (staged bf16 output) ----------
     if (lane == 0 && p.staged) {
-      const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
       const uint32_t cblocks = static_cast<uint32_t>(p.cblocks);
       const int ccols = BN / p.cblocks;
       const uint32_t total = static_cast<uint32_t>(my_tiles) * cblocks;
       const bool has_res = p.residual != nullptr;
       auto coords = [&](uint32_t g, int& m0, int& n0) {
         const int i = static_cast<int>(g / cblocks), cb = static_cast<int>(g % cblocks);
-        const int tile = blockIdx.x + i * gridDim.x;
-        const int m_blk = tile / p.num_n_tiles;
-        const int n_blk = tile - m_blk * p.num_n_tiles;
+        int m_blk, n_blk;
+        tile_coords(i, m_blk, n_blk);
         m0 = m_blk * kTileM;
         n0 = n_blk * BN + cb * ccols;
       };
@@ -256,10 +275,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const bool res_f32 = p.flags & LECB_EPI_RES_F32;
     const uint32_t erow = static_cast<uint32_t>(quarter * 32 + lane);   // row inside the tile == TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    int tile_seq = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_seq) {
-      const int m_blk = tile / p.num_n_tiles;
-      const int n_blk = tile - m_blk * p.num_n_tiles;
+    for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq) {
+      int m_blk, n_blk;
+      tile_coords(tile_seq, m_blk, n_blk);
       const int acc = tile_seq & 1;
       const uint32_t acc_phase = (tile_seq >> 1) & 1;
       const int64_t row = static_cast<int64_t>(m_blk) * kTileM + erow;
@@ -495,8 +513,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
   static bool configured = false;
   auto kern = gemm_kernel<BN, BK, NB, kConv>;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) return fail(LECB_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return fail(LECB_ERR_CUDA, "cudaFuncSetAttribute(smem=227K): %s", cudaGetErrorString(e));
     configured = true;
   }
   CUtensorMap tmC = tmA, tmR = tmA;      // placeholders when the staged path is off
@@ -516,24 +534,21 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
       if (st) return st;
     }
   }
-  // Small weight matrices (e.g. the 64-channel 3x3 convs: 9 x 8 KB) stay resident in shared memory: the mainloop
-  // then streams only A tiles, removing a third of the L2 -> SM fill traffic those layers are bound by.
-  p.b_resident = 0;
-  if (p.num_n_tiles == 1 && p.num_kb >= 2) {
-    const int region = Cfg::kStages * Cfg::kStageBytes;
-    const int wbytes = p.num_kb * Cfg::kBBytes;
-    int ring = (region - wbytes) / Cfg::kABytes;
-    if (ring > Cfg::kStages) ring = Cfg::kStages;
-    if (wbytes <= 96 * 1024 && ring >= 4) {
-      p.b_resident = 1;
-      p.res_stages = ring;
-    }
-  }
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  // Weight tiles that fit stay resident in shared memory for the CTA's lifetime (64-channel 3x3 convs: 9 x 8 KB;
+  // the K <= 256 expand convs: 128 KB): the mainloop then streams only A tiles, which removes the W re-fetch from
+  // the L2 -> SM traffic those layers are bound by.  The CTA owns one n tile and strides over m tiles.
   const int sms = sm_count();
   if (sms <= 0) return fail(LECB_ERR_CUDA, "no CUDA device");
-  const int grid = tiles < sms ? tiles : sms;
-  kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmR, p);
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  p.operand_bytes = Cfg::kStages * Cfg::kStageBytes;
+  int smem_bytes = Cfg::kSmemBytes;
+  int grid = tiles < sms ? tiles : sms;
+  if (p.b_resident) {                     // planned by dispatch(): W tile + A ring + NB staging buffers fit
+    p.operand_bytes = p.num_kb * Cfg::kBBytes + p.res_stages * Cfg::kABytes;
+    smem_bytes = p.operand_bytes + NB * Cfg::kCBytes + 1024 + 512;
+    grid = (sms / p.num_n_tiles) * p.num_n_tiles;
+  }
+  kern<<<grid, kNumThreads, smem_bytes, stream>>>(tmA, tmB, tmC, tmR, p);
   count_launch();
   return check_launch("gemm_kernel");
 }
@@ -563,15 +578,45 @@ static int dispatch_nb(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap
 // The staging-buffer count trades operand stages for epilogue depth: with a short K loop the tile is bound by
 // the residual read + output write, and the number of 16 KB residual blocks that can be in flight per SM
 // (each buffer cycles free -> TMA load -> add -> TMA store -> drain) sets the achievable HBM bandwidth.
+// A ring depth the resident-W mode would get with `nb` staging buffers (0 = does not fit).
+static int resident_ring(int BN, int BK, int num_kb, int nb) {
+  const int ccols = BN >= 64 ? 64 : BN;
+  const int budget = 227 * 1024 - nb * (kTileM * ccols * 2) - 1024 - 512;
+  const int wbytes = num_kb * BN * BK * 2;
+  if (wbytes > 128 * 1024) return 0;
+  int ring = (budget - wbytes) / (kTileM * BK * 2);
+  return ring > kMaxStages ? kMaxStages : (ring < 0 ? 0 : ring);
+}
+
 template <bool kConv>
 static int dispatch(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t s) {
-  if (kConv) return dispatch_nb<kConv, 2>(BN, BK, tmA, tmB, p, s);
-  if (p.num_kb <= 2) return dispatch_nb<kConv, 8>(BN, BK, tmA, tmB, p, s);
-  if (p.num_kb <= 4) return dispatch_nb<kConv, 5>(BN, BK, tmA, tmB, p, s);
-  if (p.num_kb <= 8) return dispatch_nb<kConv, 4>(BN, BK, tmA, tmB, p, s);
-  // fp32 output / residual moves twice the bytes per element: keep four blocks in flight up to K = 1024
-  if ((p.flags & LECB_EPI_OUT_F32) && p.num_kb <= 16) return dispatch_nb<kConv, 4>(BN, BK, tmA, tmB, p, s);
-  return dispatch_nb<kConv, 2>(BN, BK, tmA, tmB, p, s);
+  int nb = 2;
+  if (!kConv) {
+    if (p.num_kb <= 2) nb = 8;
+    else if (p.num_kb <= 4) nb = 5;
+    else if (p.num_kb <= 8) nb = 4;
+    // fp32 output / residual moves twice the bytes per element: keep four blocks in flight up to K = 1024
+    else if ((p.flags & LECB_EPI_OUT_F32) && p.num_kb <= 16) nb = 4;
+  }
+  // Resident-W mode (see launch_gemm): worth it when every CTA walks many m tiles of one n tile AND the staging
+  // depth does not have to shrink for it — measured on layer3's expand conv (K 256 -> N 1024, 128 KB W tile):
+  // giving up two of the five residual/staging buffers costs more HBM overlap than the W re-fetch saves.
+  p.b_resident = 0;
+  const int sms = sm_count();
+  if (p.num_kb >= 2 && p.num_n_tiles <= 8 && sms > 0 && p.num_m_tiles >= 4 * sms && !getenv("LECB_NO_RESIDENT")) {
+    const int ring = resident_ring(BN, BK, p.num_kb, nb);
+    if (ring >= 3) {
+      p.b_resident = 1;
+      p.res_stages = ring;
+    }
+  }
+  switch (nb) {
+    case 8: return dispatch_nb<kConv, 8>(BN, BK, tmA, tmB, p, s);
+    case 5: return dispatch_nb<kConv, 5>(BN, BK, tmA, tmB, p, s);
+    case 4: return dispatch_nb<kConv, 4>(BN, BK, tmA, tmB, p, s);
+    case 3: return dispatch_nb<kConv, 3>(BN, BK, tmA, tmB, p, s);
+    default: return dispatch_nb<kConv, 2>(BN, BK, tmA, tmB, p, s);
+  }
 }
 
 }  // namespace lecb

@@ -66,6 +66,12 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar,
       ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 prefetch of a 2-D tile (no shared memory, no completion tracking): warms L2 for a later tma_load_2d
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
 // 4-D im2col load over an NHWC tensor (dims {C,W,H,N}): `pixelsPerColumn` pixels starting at base
 // pixel (w,h,n) inside the bounding box, each displaced by the filter offset (off_w, off_h).
 __device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap* m, uint64_t* bar, void* smem, int c, int w,

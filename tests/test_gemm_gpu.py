@@ -110,3 +110,32 @@ def test_gemm_f32_out_staged(m, n, k):
     assert ((ssq - want).abs() / (want + 1e-6)).max().item() < 1e-4
     g = ops.gemm(a, w, bias, quick_gelu=True, out_f32=True)
     assert (g - base * torch.sigmoid(1.702 * base)).abs().max().item() <= tol
+
+
+@pytest.mark.parametrize("m,n,k", [(100003, 1024, 256), (90000, 512, 128), (80000, 256, 64), (77000, 768, 128),
+                                   (76000, 64, 256), (100352, 240, 512)])
+def test_gemm_resident_weights_mode(m, n, k):
+    """Tall problems (>= 4 m tiles per SM) with small weights run with the CTA's W tile resident in shared memory and a
+    CTA-owns-one-n-tile schedule (1, 2, 3 and 4 n tiles, ragged M, N tail, bf16 + fp32 epilogues)."""
+    from lecb200 import ops
+    a = _rand((m, k), 21).bfloat16()
+    w = _rand((n, k), 22, k ** -0.5).bfloat16()
+    bias = _rand((n,), 23)
+    res = _rand((m, n), 24).bfloat16()
+    base = a.float() @ w.float().t() + bias
+    _check(ops.gemm(a, w, bias, residual=res, relu=True), (base + res.float()).relu(), "resident bias+res+relu")
+    _check(ops.gemm(a, w, bias), base, "resident bias")
+    f32 = ops.gemm(a, w, bias, out_f32=True)
+    assert (f32 - base).abs().max().item() <= 2e-3 * (base.abs().max().item() + 1)
+
+
+def test_conv3x3_resident_weights_mode():
+    from lecb200 import ops
+    b, h, w, cin, cout = 8, 112, 112, 64, 64
+    x = _rand((b, h, w, cin), 31).bfloat16()
+    wt = _rand((cout, 3, 3, cin), 32, (9 * cin) ** -0.5).bfloat16()
+    bias = _rand((cout,), 33, 0.1)
+    out = ops.conv3x3(x, wt, bias, relu=True)
+    torch.cuda.synchronize()
+    want = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), bias, padding=1)
+    _check(out, want.relu().permute(0, 2, 3, 1), "resident conv")
