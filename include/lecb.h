@@ -154,6 +154,9 @@ int lecb_layernorm_bwd(const float* dy, const float* x, const float* gamma, cons
                        const float* dx_in, float* dx_f32, void* dx_bf16, int64_t rows, int D, void* stream);
 /* causal attention backward: qkv, dqkv bf16 [N*L,3W]; dout bf16 [N*L,W]; L <= 96 (M:221-223) */
 int lecb_causal_attn_bwd(const void* qkv, const void* dout, void* dqkv, int N, int L, int W, int heads, void* stream);
+/* the same on tcgen05 tensor cores (five M=128 MMAs per (sequence, head), transposed operands read in place through
+ * MN-major descriptors); L <= 128.  Probabilities and dS are rounded to bf16 for the MMAs, like lecb_attn_fwd. */
+int lecb_attn_causal_bwd(const void* qkv, const void* dout, void* dqkv, int N, int L, int W, int heads, void* stream);
 /* backward of y = x/||x|| on fp32 rows (T:487-488,503) */
 int lecb_l2norm_bwd(const float* x, const float* dy, float* dx, int64_t rows, int D, void* stream);
 /* gradient of logits_local w.r.t. the raw dot products (same operands as lecb_head_aggregate; T:496-514) */

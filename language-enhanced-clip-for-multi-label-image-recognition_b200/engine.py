@@ -230,8 +230,7 @@ class TextTower:
         for blk in self.blocks:
             h, _, m1, r1 = ops.layernorm(x, *blk["ln1"], save_stats=True)
             qkv = ops.gemm(h, *blk["qkv"])
-            # the differentiated branch keeps fp32 probabilities: lecb_causal_attn_bwd recomputes exactly these
-            a = ops.causal_attn_smem(qkv, n, l, w, self.heads)
+            a = ops.causal_attn(qkv, n, l, w, self.heads)      # bwd (lecb_attn_causal_bwd) rounds P to bf16 the same way
             x1 = ops.gemm_f32res(a, *blk["out"], x)
             h, _, m2, r2 = ops.layernorm(x1, *blk["ln2"], save_stats=True)
             v = ops.gemm(h, *blk["fc"])                         # pre-activation kept for the QuickGELU backward

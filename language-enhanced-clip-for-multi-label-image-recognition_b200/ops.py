@@ -279,6 +279,16 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx_in=None, want_bf16=True):
 
 
 def causal_attn_bwd(qkv, dout, n, l, w, heads):
+    """Backward of the text tower's masked attention on tcgen05 (dqkv bf16 [N*L,3W])."""
+    _need(qkv, torch.bfloat16, "qkv")
+    _need(dout, torch.bfloat16, "dout")
+    dqkv = torch.empty_like(qkv)
+    check(lib.lecb_attn_causal_bwd(_ptr(qkv), _ptr(dout), _ptr(dqkv), n, l, w, heads, _stream()), "lecb_attn_causal_bwd")
+    return dqkv
+
+
+def causal_attn_bwd_smem(qkv, dout, n, l, w, heads):
+    """CUDA-core shared-memory variant (fp32 probabilities), kept as an independent cross-check."""
     _need(qkv, torch.bfloat16, "qkv")
     _need(dout, torch.bfloat16, "dout")
     dqkv = torch.empty_like(qkv)

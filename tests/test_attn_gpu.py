@@ -84,3 +84,29 @@ def test_causal_tc_matches_smem_kernel():
     b = ops.causal_attn_smem(qkv, n, l, w, heads).float()
     torch.cuda.synchronize()
     assert (a - b).abs().max().item() <= 2.0 ** -6 * b.abs().max().item()
+
+
+@pytest.mark.parametrize("n,l,heads", [(3, 77, 8), (2, 128, 2), (5, 33, 1), (2, 16, 12), (4, 96, 4)])
+def test_attn_causal_bwd(n, l, heads):
+    """tcgen05 causal-attention backward vs torch autograd (fp32) on the same bf16-rounded q/k/v/dO, and vs the
+    CUDA-core kernel.  P and dS are rounded to bf16 for the MMAs: tolerance 2^-6 of each gradient's scale."""
+    from lecb200 import ops
+    w = heads * 64
+    g = torch.Generator(device="cpu").manual_seed(n * 100 + l)
+    qkv = torch.randn((n * l, 3 * w), generator=g).cuda().bfloat16()
+    dout = torch.randn((n * l, w), generator=g).cuda().bfloat16()
+    x = qkv.float().clone().requires_grad_(True)
+    q, k, v = x.view(n, l, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) / 8.0 + torch.full((l, l), float("-inf"), device="cuda").triu(1)
+    o = (s.softmax(-1) @ v).permute(0, 2, 1, 3).reshape(n * l, w)
+    o.backward(dout.float())
+    want = x.grad
+    got = ops.causal_attn_bwd(qkv, dout, n, l, w, heads).float()
+    ref2 = ops.causal_attn_bwd_smem(qkv, dout, n, l, w, heads).float() if l <= 96 else None
+    torch.cuda.synchronize()
+    for name, sl in (("dq", slice(0, w)), ("dk", slice(w, 2 * w)), ("dv", slice(2 * w, 3 * w))):
+        scale = want[:, sl].abs().max().item()
+        err = (got[:, sl] - want[:, sl]).abs().max().item()
+        assert err <= scale * 2.0 ** -6, f"{name}: err {err:.4g} scale {scale:.4g}"
+        if ref2 is not None:
+            assert (got[:, sl] - ref2[:, sl]).abs().max().item() <= scale * 2.0 ** -6
