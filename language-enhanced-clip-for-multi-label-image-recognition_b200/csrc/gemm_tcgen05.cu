@@ -44,7 +44,7 @@ struct GemmCfg {
   static constexpr int kStagesRaw = (227 * 1024 - NB * kCBytes - 2560) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);
-  static constexpr int kSmemBytes = kStages * kStageBytes + NB * kCBytes + 1024 /*align slack*/ + 512 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + NB * kCBytes + 512 /*barriers*/ + 2048 /*bias, 2 tiles*/;
   static_assert(kStages >= 2, "need at least a double-buffered operand ring");
 };
 
@@ -78,8 +78,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr int kStages = Cfg::kStages;
   constexpr int kCCols = Cfg::kCCols;
   constexpr int kCBlocks = Cfg::kCBlocks;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];     // swizzled tiles need 1024-byte alignment (checked below)
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * Cfg::kABytes;
   uint8_t* sC = smem + p.operand_bytes;
@@ -92,6 +91,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* cfull = cfree + NB;
   uint64_t* bres = cfull + NB;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres + 1);
+  float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);      // [2][256]: bias slice of a tile
   // b_resident: [ W k-blocks (num_kb * kBBytes) | A ring (res_stages * kABytes) ] inside the operand region
   const int nstages = p.b_resident ? p.res_stages : kStages;
   uint8_t* sA_ring = p.b_resident ? smem + p.num_kb * Cfg::kBBytes : sA;
@@ -119,6 +119,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   };
 
   if (warp == kWarpTma && lane == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < kMaxStages; ++i) {
@@ -283,6 +284,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int64_t row = static_cast<int64_t>(m_blk) * kTileM + erow;
       const bool row_ok = row < p.M;
       float ssq = 0.f;
+      // The tile's bias slice goes through shared memory: with the whole carve-out given to operand tiles there is
+      // no L1 left, so per-block __ldg of the bias cost an exposed L2 round trip per 64 columns (measured: -20 % on
+      // K = 768 GEMMs).  One element per epilogue thread, requested before the accumulator wait; double-buffered by
+      // tile parity (the named barrier of tile i+1 orders every reader of tile i-1's slice before its overwrite).
+      const float* sb = sbias + acc * 256;
+      if (p.bias != nullptr) {
+        const int tid = static_cast<int>(threadIdx.x);      // 0..255: the eight epilogue warps
+        const int col = n_blk * BN + tid;
+        if (tid < BN) sbias[acc * 256 + tid] = col < p.N ? __ldg(p.bias + col) : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       if (p.staged && p.out_f32) {
         // fp32 output (+ fp32 residual): 32-column blocks (128-byte rows), same buffer ring and DMA protocol
         const int cblocks = p.cblocks;
@@ -310,12 +322,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           if (p.bias != nullptr) {
+            const float4* bp = reinterpret_cast<const float4*>(sb + (n0 - n_blk * BN));
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              if (n0 + j < p.N) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-              }
+              const float4 b = bp[j / 4];
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
             }
           }
           if (p.residual != nullptr) {
@@ -376,12 +387,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[half][j]);
             if (p.bias != nullptr) {
+              const float4* bp = reinterpret_cast<const float4*>(sb + (n0 - n_blk * BN));
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                if (n0 + j < p.N) {
-                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-                  v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                }
+                const float4 b = bp[j / 4];
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
               }
             }
             if (p.residual != nullptr) {
@@ -439,12 +449,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           if (p.bias != nullptr) {
+            const float4* bp = reinterpret_cast<const float4*>(sb + (n0 - n_blk * BN));
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              if (n0 + j < p.N) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-              }
+              const float4 b = bp[j / 4];
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
             }
           }
           if (p.residual != nullptr && row_ok && res_f32) {
@@ -545,7 +554,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
   int grid = tiles < sms ? tiles : sms;
   if (p.b_resident) {                     // planned by dispatch(): W tile + A ring + NB staging buffers fit
     p.operand_bytes = p.num_kb * Cfg::kBBytes + p.res_stages * Cfg::kABytes;
-    smem_bytes = p.operand_bytes + NB * Cfg::kCBytes + 1024 + 512;
+    smem_bytes = p.operand_bytes + NB * Cfg::kCBytes + 512 + 2048;
     grid = (sms / p.num_n_tiles) * p.num_n_tiles;
   }
   kern<<<grid, kNumThreads, smem_bytes, stream>>>(tmA, tmB, tmC, tmR, p);
@@ -581,7 +590,7 @@ static int dispatch_nb(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap
 // A ring depth the resident-W mode would get with `nb` staging buffers (0 = does not fit).
 static int resident_ring(int BN, int BK, int num_kb, int nb) {
   const int ccols = BN >= 64 ? 64 : BN;
-  const int budget = 227 * 1024 - nb * (kTileM * ccols * 2) - 1024 - 512;
+  const int budget = 227 * 1024 - nb * (kTileM * ccols * 2) - 512 - 2048;
   const int wbytes = num_kb * BN * BK * 2;
   if (wbytes > 128 * 1024) return 0;
   int ring = (budget - wbytes) / (kTileM * BK * 2);
@@ -635,7 +644,18 @@ extern "C" int lecb_gemm_bf16(const void* A, const void* W, const float* bias, c
   const int BK = (K % 64 == 0) ? 64 : 32;
   int BN = pick_bn(N);
   if (BK == 32 && BN > 64) BN = 64;
-  if (getenv("LECB_EXP_BN128") && N == 256 && K >= 512 && residual == nullptr) BN = 128;   // experiment knob
+  if (BN == 256) {
+    // wave quantisation: with few m tiles (text tower, small batches) 128-wide tiles can fill the last wave much
+    // better than 256-wide ones; switch when that buys more than 15 %
+    const int sms = sm_count();
+    if (sms > 0) {
+      const int64_t mt = (M + kTileM - 1) / kTileM;
+      const int64_t t256 = mt * ((N + 255) / 256), t128 = mt * ((N + 127) / 128);
+      const double e256 = static_cast<double>(t256) / (((t256 + sms - 1) / sms) * sms);
+      const double e128 = static_cast<double>(t128) / (((t128 + sms - 1) / sms) * sms);
+      if (e128 > 1.15 * e256) BN = 128;
+    }
+  }
   GemmParams p{};
   p.bias = bias;
   p.residual = residual;
