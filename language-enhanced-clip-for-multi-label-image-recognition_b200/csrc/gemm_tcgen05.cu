@@ -288,12 +288,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // no L1 left, so per-block __ldg of the bias cost an exposed L2 round trip per 64 columns (measured: -20 % on
       // K = 768 GEMMs).  One element per epilogue thread, requested before the accumulator wait; double-buffered by
       // tile parity (the named barrier of tile i+1 orders every reader of tile i-1's slice before its overwrite).
-      const float* sb = sbias + acc * 256;
+      // Narrow tiles (BN <= 64, where the two epilogue groups alternate tiles) use a private 64-float slice per warp
+      // and need no cross-warp barrier.
+      const float* sb = BN <= 64 ? sbias + warp * 64 : sbias + acc * 256;
       if (p.bias != nullptr) {
-        const int tid = static_cast<int>(threadIdx.x);      // 0..255: the eight epilogue warps
-        const int col = n_blk * BN + tid;
-        if (tid < BN) sbias[acc * 256 + tid] = col < p.N ? __ldg(p.bias + col) : 0.f;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (BN <= 64) {
+          __syncwarp();                                       // the warp's previous tile is done with its slice
+#pragma unroll
+          for (int c = lane; c < BN; c += 32) {
+            const int col = n_blk * BN + c;
+            sbias[warp * 64 + c] = col < p.N ? __ldg(p.bias + col) : 0.f;
+          }
+          __syncwarp();
+        } else {
+          const int tid = static_cast<int>(threadIdx.x);      // 0..255: the eight epilogue warps
+          const int col = n_blk * BN + tid;
+          if (tid < BN) sbias[acc * 256 + tid] = col < p.N ? __ldg(p.bias + col) : 0.f;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
       }
       if (p.staged && p.out_f32) {
         // fp32 output (+ fp32 residual): 32-column blocks (128-byte rows), same buffer ring and DMA protocol
