@@ -69,7 +69,10 @@ class TextEncoder(nn.Module):
         x = (prompts.float() + tw.pos).contiguous()
         if if_sequence:
             return tw.forward(x, sequence=True)
-        return tw.forward(x, eot_index=tokenized_prompts.to(x.device).argmax(dim=-1))
+        eot = tokenized_prompts.argmax(dim=-1)
+        # causal mask + EOT-row readout: positions after the last EOT cannot influence the result (exact trim)
+        l_eff = int(eot.max()) + 1
+        return tw.forward(x[:, :l_eff].contiguous(), eot_index=eot.to(x.device))
 
 
 class PromptLearner(nn.Module):

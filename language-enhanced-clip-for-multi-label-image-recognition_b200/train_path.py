@@ -21,10 +21,14 @@ def _cfg(model, path, default=None):
 class _DualPromptHead(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pack, logit_scale_t, *prompts):
-        tower, tok_prompts, local, ssq, mask, g_unit, b, l, logit_scale, spatial = pack
+        tower, (tok_prompts, l_eff), local, ssq, mask, g_unit, b, l, logit_scale, spatial = pack
         n_txt = len(prompts)
         k = prompts[0].shape[0]
-        x = (torch.cat([p.detach().float() for p in prompts], 0) + tower.pos).contiguous()        # [n*K, 77, W]
+        # The mask is causal (M:364-370) and only the EOT row of a prompt is used (T:100), so positions after the
+        # last EOT can never reach the output or receive gradient: run the tower on the first l_eff positions only
+        # (exact, ~3x less work for "X*16 <class>." prompts whose EOT sits near position 20 of 77).
+        ctx.full_len = prompts[0].shape[1]
+        x = (torch.cat([p.detach().float() for p in prompts], 0) + tower.pos)[:, :l_eff].contiguous()   # [n*K, l_eff, W]
         eot = tok_prompts.repeat(n_txt)          # EOT index per prompt sequence, already on the device
         t_raw, saved = tower.forward_train(x, eot)                                                # [n*K, D] fp32
         t_hat = ops.l2norm_rows(t_raw)
@@ -54,7 +58,9 @@ class _DualPromptHead(torch.autograd.Function):
         if d_tpos is not None:
             d_that[:k] += d_tpos.float()
         d_traw = ops.l2norm_bwd(t_raw, d_that)
-        dx = tower.backward(saved, d_traw)                                                          # [n*K, 77, W]
+        dx = tower.backward(saved, d_traw)                                                          # [n*K, l_eff, W]
+        if dx.shape[1] < ctx.full_len:           # positions past the last EOT carry exactly zero gradient
+            dx = torch.nn.functional.pad(dx, (0, 0, 0, ctx.full_len - dx.shape[1]))
         grads = tuple(dx[i * k:(i + 1) * k] for i in range(n_txt))
         d_scale = None
         if ctx.learn_scale:          # logits = exp(temperature) * (...)  =>  dL/dtemperature = sum(dlogits * logits)
@@ -119,8 +125,10 @@ def forward_train(model, captions):
     learn = bool(_cfg(model, "TRAIN.IF_LEARN_SCALE", False))
     logit_scale = float(temperature.exp()) if learn else 4.0
     spatial = float(_cfg(model, "TRAIN.spatial_SCALE_text"))
-    if getattr(model, "_eot_dev", None) is None or model._eot_dev.device != local.device:
-        model._eot_dev = model.tokenized_prompts.argmax(dim=-1).to(local.device)      # cached: keeps the step graph-capturable
+    if getattr(model, "_eot_dev", None) is None or model._eot_dev[0].device != local.device:
+        eot = model.tokenized_prompts.argmax(dim=-1)
+        # cached (EOT indices on the device, live prompt length): keeps the step free of host syncs / graph-capturable
+        model._eot_dev = (eot.to(local.device), int(eot.max()) + 1)
     pack = (model.text_encoder.tower(), model._eot_dev, local, ssq, mask, g_unit, b, l, logit_scale, spatial)
     plist = (prompts, prompts_double, prompts_evidence) if use_evidence else (prompts, prompts_double)
     logits, logits_local, text_features = _DualPromptHead.apply(pack, temperature if learn else None, *plist)
