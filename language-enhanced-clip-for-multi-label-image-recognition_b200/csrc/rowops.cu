@@ -1,9 +1,14 @@
 // HBM-bound row / pixel kernels: stem conv1 (3x3 stride 2, 3->C), 2x2 average pool, token mean,
 // row L2 normalisation, LayerNorm.  128-bit vectorised, coalesced, warp-shuffle reductions.
+#include <stdlib.h>
+
 #include "lecb_common.cuh"
 #include "lecb_host.h"
 
 namespace lecb {
+
+int launch_stem_conv1_tc(const float* x, const float* w, const float* bias, void* out, int B, int H, int W,
+                         cudaStream_t s);      // stem_tc.cu
 
 // ------------------------------------------------------------------------------------------------
 // Stem conv1: NCHW fp32 [B,3,H,W] -> NHWC bf16 [B,H/2,W/2,CO], 3x3 stride 2 pad 1, folded BN + ReLU.
@@ -276,6 +281,8 @@ extern "C" int lecb_stem_conv1(const float* x, const float* w, const float* bias
   const int64_t total = static_cast<int64_t>(B) * (H / 2) * ((W / 2 + 1) / 2);     // two output pixels per thread
   const unsigned grid = static_cast<unsigned>((total + 127) / 128);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (Cout == 32 && !getenv("LECB_STEM_CUDA_CORES"))      // the real CLIP ResNets (width 64): tensor-core implicit GEMM
+    return launch_stem_conv1_tc(x, w, bias, out, B, H, W, s);
   if (Cout == 32)
     stem_conv1_kernel<32><<<grid, 128, 0, s>>>(x, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W);
   else if (Cout == 48)

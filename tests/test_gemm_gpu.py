@@ -139,3 +139,27 @@ def test_conv3x3_resident_weights_mode():
     torch.cuda.synchronize()
     want = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), bias, padding=1)
     _check(out, want.relu().permute(0, 2, 3, 1), "resident conv")
+
+
+@pytest.mark.parametrize("b,h,w", [(2, 64, 64), (3, 224, 224), (1, 450, 446), (5, 32, 96)])
+def test_stem_conv1_tensor_core(b, h, w):
+    """Stem conv1 (3x3 / stride 2 / pad 1, 3 -> 32, folded BN + ReLU) as a tcgen05 implicit GEMM vs torch conv2d on the
+    same bf16-rounded operands, and vs the CUDA-core kernel (ragged last tile, odd image counts, non-square images)."""
+    import os
+    from lecb200 import ops
+    x = _rand((b, 3, h, w), 41)
+    wt = _rand((32, 3, 3, 3), 42, 27 ** -0.5)
+    bias = _rand((32,), 43, 0.1)
+    w27 = wt.permute(1, 2, 3, 0).reshape(27, 32).contiguous()
+    out = ops.stem_conv1(x, w27, bias)
+    torch.cuda.synchronize()
+    want = torch.nn.functional.conv2d(x.bfloat16().float(), wt.bfloat16().float(), bias, stride=2, padding=1).relu().permute(0, 2, 3, 1)
+    _check(out, want, f"stem conv1 tc {b}x{h}x{w}")
+    os.environ["LECB_STEM_CUDA_CORES"] = "1"
+    try:
+        ref = ops.stem_conv1(x, w27, bias)
+    finally:
+        del os.environ["LECB_STEM_CUDA_CORES"]
+    torch.cuda.synchronize()
+    # the CUDA-core kernel keeps fp32 inputs/weights: differences are the bf16 rounding of the operands
+    assert (out.float() - ref.float()).abs().max().item() <= 3e-2 * (ref.float().abs().max().item() + 1e-6)
