@@ -167,6 +167,16 @@ int lecb_head_aggregate_bwd(const float* dots, int ldn, const float* row_sumsq, 
 int lecb_tn_gemm_small(const float* a, int lda, const void* b, int b_is_bf16, float* out, int R, int J, int D,
                        float alpha, int accumulate, void* stream);
 
+/* ---- test-time score fusion around the scoring path ----
+ * lecb_block_fuse: data fp32 [B,NB,K] per-window scores -> out[b,k] = weight * s_ag + base[b,k] (base may be NULL),
+ *   s_ag = max_n d if max_n d > threshold else min_n d.  mode 0: d = data (Caption_distill_double.py:655-662);
+ *   mode 1 / 2: windows re-weighted by 1 + mean(sims[b,n,:]) and 1 + unbiased var_k as in gen_final_ans.py `fuse`
+ *   (18-36) / `fuse6` (38-71); sims fp32 [B,NB,sims_ld].
+ * lecb_cooc_adjust: out = pred + weight * pred @ P, P fp32 [K,K] row-normalised co-occurrence (T:611-618). */
+int lecb_block_fuse(const float* data, const float* sims, int sims_ld, const float* base, float* out, int B, int NB,
+                    int K, int mode, float threshold, float weight, void* stream);
+int lecb_cooc_adjust(const float* pred, const float* P, float* out, int B, int K, float weight, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

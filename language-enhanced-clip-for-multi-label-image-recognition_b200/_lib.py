@@ -53,6 +53,9 @@ SIGNATURES = {
     "lecb_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
     "lecb_head_aggregate_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                         c_int, c_float, c_float, c_void_p]),
+    "lecb_block_fuse": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float,
+                                c_void_p]),
+    "lecb_cooc_adjust": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     "lecb_tn_gemm_small": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_int,
                                    c_void_p]),
 }

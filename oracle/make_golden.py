@@ -17,6 +17,7 @@ Fixtures written:
   train_tiny.npz             same on the toy arch, B=6
   losses.npz                 ranking_loss / ASL_loss / dualcoop_loss values + grads on [16,80]
   map.npz                    reference numpy mAP on synthetic scores/labels
+  fusion.npz                 reference fuse / fuse6 (gen_final_ans.py) and adjust_predictions (T:611-615) on synthetic scores
   vit_{tiny,b16_224,l14_224}.npz   reference VisionTransformer.forward (class-token feature) on synthetic weights
 """
 from __future__ import annotations
@@ -151,6 +152,24 @@ def golden_vit(tag, arch, batch, seed):
     print(f"[vit_{tag}] global absmax={g.abs().max():.4f}", flush=True)
 
 
+def golden_fusion():
+    """gen_final_ans.py `fuse` / `fuse6` and the trainer's `adjust_predictions` run on synthetic window scores."""
+    g = torch.Generator().manual_seed(91)
+    data = torch.rand((24, 116, 80), generator=g) * 0.6 - 0.1          # window scores around the 0.2 / 0.3 thresholds
+    sims = torch.rand((24, 116, 5), generator=g) * 0.4
+    output = torch.rand((24, 80), generator=g)
+    adj = torch.rand((80, 80), generator=g) * 100
+    nums = torch.rand((80,), generator=g) * 1000 + 50
+    ns = RX.fusion_functions(sims)
+    p = adj / nums[:, None]
+    p = p / p.sum(-1)[:, None]
+    np.savez_compressed(os.path.join(GOLD, "fusion.npz"), data=data.numpy(), sims=sims.numpy(), output=output.numpy(),
+                        adj=adj.numpy(), nums=nums.numpy(), fuse=ns["fuse"](data).numpy(), fuse6=ns["fuse6"](data).numpy(),
+                        fuse_t05=ns["fuse"](data, threshold=0.5).numpy(),
+                        adjusted=ns["adjust_predictions"](output, p, 0.5).numpy())
+    print("[fusion] fuse/fuse6/adjust_predictions written", flush=True)
+
+
 def golden_losses():
     L = RX.loss_functions()
     g = torch.Generator().manual_seed(77)
@@ -203,6 +222,7 @@ def main(which=None):
         "head_rn50": lambda: golden_head("rn50_224", synth.RN50(224), 8, classnames, 16, 5000, 1235),
         "head_rn101": lambda: golden_head("rn101_448", synth.RN101(448), 2, classnames, 16, 2000, 1236, (True,)),
         "train_rn50": lambda: golden_train("rn50", synth.RN50(224), 4, classnames, 16, 1238),
+        "fusion": golden_fusion,
         "vit_tiny": lambda: golden_vit("tiny", synth.tiny_vit(), 3, 1250),
         "vit_b16_224": lambda: golden_vit("b16_224", synth.VITB16(224), 2, 1251),
         "vit_l14_224": lambda: golden_vit("l14_224", synth.VITL14(224), 1, 1252),

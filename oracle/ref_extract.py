@@ -133,6 +133,24 @@ def loss_functions():
     return ns
 
 
+def fusion_functions(sims_scores):
+    """-> namespace with the reference `fuse` / `fuse6` of gen_final_ans.py:18-71 (they read the module global
+    `sims_scores`, provided here) and `adjust_predictions`, the helper nested in Caption_distill_double.test (T:611-615)."""
+    import torch
+    code = _extract(os.path.join(MC, "gen_final_ans.py"), ["fuse", "fuse6"])
+    ns = {"torch": torch, "sims_scores": sims_scores, "__name__": "_lecb_ref_fusion"}
+    exec(code, ns)
+    with open(os.path.join(MC, "trainers", "Caption_distill_double.py"), "r") as f:
+        tree = ast.parse(f.read())
+    nested = [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "adjust_predictions"]
+    if not nested:
+        raise RuntimeError("adjust_predictions not found in the reference trainer")
+    mod = ast.Module(body=[nested[0]], type_ignores=[])
+    ast.fix_missing_locations(mod)
+    exec(compile(mod, "Caption_distill_double.py", "exec"), ns)
+    return ns
+
+
 def mAP_function():
     """The numpy `mAP` of dassl/evaluation/evaluator.py:137-175 (AST-extracted: pure numpy)."""
     import numpy as np

@@ -357,6 +357,35 @@ def mean_average_precision(targets: np.ndarray, scores: np.ndarray) -> float:
     return float(100.0 * np.mean(aps))
 
 
+def aggregate_blocks(output, output_blocks, threshold=0.3, weight=1.4):
+    """T:655-662: per class, the max over the sliding windows if it exceeds the threshold, else the min."""
+    alpha = output_blocks.max(dim=1)[0]
+    beta = output_blocks.min(dim=1)[0]
+    gamma = (alpha > threshold).int()
+    return weight * (gamma * alpha + (1 - gamma) * beta) + output
+
+
+def _max_min_threshold(data, threshold):
+    alpha, beta = data.max(dim=1)[0], data.min(dim=1)[0]
+    gamma = (alpha > threshold).int()
+    return gamma * alpha + (1 - gamma) * beta
+
+
+def fuse(data, sims_scores, threshold=0.2):
+    """gen_final_ans.py:18-36: windows re-weighted by 1 + mean similarity, then by 1 + var_k (unbiased)."""
+    data = (1 + sims_scores.mean(-1, keepdim=True)) * data
+    data = (1 + torch.var(data, dim=2).unsqueeze(-1)) * data
+    return _max_min_threshold(data, threshold)
+
+
+def fuse6(data, sims_scores, threshold=0.2):
+    """gen_final_ans.py:38-71."""
+    v0 = 1 + torch.var(data, dim=2).unsqueeze(-1)
+    d_sim = (1 + sims_scores.mean(-1, keepdim=True)) * data
+    v1 = 1 + torch.var(d_sim, dim=2).unsqueeze(-1)
+    return _max_min_threshold(v0 * v1 * d_sim, threshold)
+
+
 def cooccurrence_adjust(pred, adj, nums, weight=0.5):
     """T:614-618,632-636: pred + w * pred @ rownorm(adj / nums)."""
     p = torch.as_tensor(adj / nums[:, None], dtype=torch.float32)

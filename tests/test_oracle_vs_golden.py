@@ -105,3 +105,18 @@ def test_vit_global_matches_reference(tag, arch_fn):
     grid = arch.image_resolution // arch.vision_patch_size
     assert tuple(local.shape) == (grid * grid, int(g["batch"]), arch.embed_dim)
     assert torch.isfinite(local).all()
+
+
+def test_fusion_matches_reference():
+    """Test-time fusion: the restatement vs the reference's own fuse / fuse6 / adjust_predictions."""
+    g = C.load("fusion.npz")
+    data, sims, out = (torch.from_numpy(g[k]) for k in ("data", "sims", "output"))
+    np.testing.assert_allclose(R.fuse(data, sims).numpy(), g["fuse"], atol=1e-6)
+    np.testing.assert_allclose(R.fuse(data, sims, 0.5).numpy(), g["fuse_t05"], atol=1e-6)
+    np.testing.assert_allclose(R.fuse6(data, sims).numpy(), g["fuse6"], atol=1e-6)
+    np.testing.assert_allclose(R.cooccurrence_adjust(out, g["adj"], g["nums"], 0.5).numpy(), g["adjusted"], atol=1e-6)
+    # aggregation without re-weighting (T:655-662) == fuse with zero similarity and the variance factor divided out
+    agg = R.aggregate_blocks(out, data, 0.3, 1.4)
+    alpha, beta = data.max(1)[0], data.min(1)[0]
+    want = 1.4 * torch.where(alpha > 0.3, alpha, beta) + out
+    np.testing.assert_allclose(agg.numpy(), want.numpy(), atol=1e-6)
