@@ -6,6 +6,8 @@ import numpy as np
 import pytest
 import torch
 
+from oracle import restatement as R
+
 from . import _cases as C
 from ._gpu_common import LOGIT_TOL, build_model
 
@@ -88,3 +90,26 @@ def test_train_step_matches_reference(ev, loss_name):
         cos = float((got.cpu().flatten() @ torch.from_numpy(gref).flatten()) / (got.cpu().norm() * np.linalg.norm(gref)))
         print(f"[train{sfx}] grad {pname}: max err / max ref = {err:.4f}, cosine = {cos:.5f}")
         assert err < 5e-2 and cos > 0.999, (pname, err, cos)
+
+
+def test_caption_bank_builder_matches_oracle(tmp_path):
+    """bank rows == unit EOT features of the oracle text tower; pickle round trip; retrieval consumes it."""
+    from lecb200 import bank as B
+    c = C.train_case("rn50")
+    head = dict(arch=c["arch"], sd=c["sd"], pl_state=c["pl_state"])
+    model = build_model(head, use_evidence=False)
+    caps = C.synth.captions(24, 5, vocab=c["arch"].vocab_size)
+    bank = B.build_caption_bank(model.text_encoder, caps, batch_size=16)
+    assert bank.dtype == torch.float16 and tuple(bank.shape) == (24, c["arch"].embed_dim)
+    with torch.no_grad():
+        ref = R.text_encode(c["sd"], R.embed_tokens(c["sd"], caps), caps.argmax(-1), c["arch"].transformer_heads)
+        ref = ref / ref.norm(dim=-1, keepdim=True)
+    err = (bank.float().cpu() - ref).abs().max().item()
+    assert err < 5e-3, err                          # unit vectors of dim 1024 through a bf16 tower
+    path = str(tmp_path / "bank.pkl")
+    B.save_caption_bank(path, bank)
+    import pickle
+    with open(path, "rb") as f:
+        raw = pickle.load(f)                        # what Caption_distill_double.py:35-36 does
+    assert isinstance(raw, torch.Tensor) and raw.device.type == "cpu" and torch.equal(raw, bank.cpu())
+    assert torch.equal(B.load_caption_bank(path), bank)
