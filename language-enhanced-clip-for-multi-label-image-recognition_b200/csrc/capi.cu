@@ -106,6 +106,23 @@ int encode_tiled_3d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t 
   return LECB_OK;
 }
 
+int encode_tiled_4d_nhwc(CUtensorMap* out, const void* base, int B, int H, int W, int C, uint32_t box_c, uint32_t box_w,
+                         uint32_t box_h) {
+  static EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(driver_entry("cuTensorMapEncodeTiled"));
+  if (!fn) return fail(LECB_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const cuuint32_t box[4] = {box_c, box_w, box_h, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(box_c * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(LECB_ERR_CUDA, "cuTensorMapEncodeTiled(4d) failed (%d) B=%d H=%d W=%d C=%d box=%ux%ux%u", (int)r, B, H, W, C,
+                box_c, box_w, box_h);
+  return LECB_OK;
+}
+
 int encode_im2col_3x3(CUtensorMap* out, const void* base, int B, int H, int W, int C, uint32_t channels,
                       uint32_t pixels) {
   static EncodeIm2colFn fn = reinterpret_cast<EncodeIm2colFn>(driver_entry("cuTensorMapEncodeIm2col"));

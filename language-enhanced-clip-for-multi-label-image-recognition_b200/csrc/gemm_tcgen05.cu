@@ -68,6 +68,10 @@ struct GemmParams {
   int operand_bytes; // size of the operand region (ring, or resident W + A ring); staging buffers follow it
   // conv mode
   int H, W, kb_per_tap;
+  // halo-tile conv mode (Cin == 64, W resident): an m tile is a th x tw patch of one image; the stage holds three
+  // (th+2) x tw halo copies (one per horizontal tap, so every tap's A operand is a dense, 1024-byte aligned
+  // [128][64] K-major tile at copy[kx] + ky * tw rows): each input pixel crosses L2 -> SM ~3.4x instead of 9x
+  int halo, tw, th, tiles_x, tiles_y, copy_bytes, batch;
 };
 
 template <int BN, int BK, int NB, bool kConv>
@@ -161,6 +165,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         int m_blk, n_blk;
         tile_coords(ti, m_blk, n_blk);
         int pw = 0, ph = 0, pn = 0;
+        if (kConv && p.halo) {
+          const int tx = m_blk % p.tiles_x;
+          const int ty = (m_blk / p.tiles_x) % p.tiles_y;
+          const int img = m_blk / (p.tiles_x * p.tiles_y);
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], 3u * static_cast<uint32_t>(p.copy_bytes));
+          uint8_t* dst = sA_ring + stage * 3 * p.copy_bytes;
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+            tma_load_4d(&tmA, &full[stage], dst + kx * p.copy_bytes, 0, tx * p.tw - 1 + kx, ty * p.th - 1, img);
+          if (++stage == nstages) {
+            stage = 0;
+            phase ^= 1;
+          }
+          continue;
+        }
         if (kConv) {
           const int64_t m0 = static_cast<int64_t>(m_blk) * kTileM;
           const int hw = p.H * p.W;
@@ -202,6 +222,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        if (kConv && p.halo) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint8_t* src = sA_ring + stage * 3 * p.copy_bytes;
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            const int ky = tap / 3, kx = tap - ky * 3;
+            const uint64_t adesc = make_kmajor_desc(smem_u32(src + kx * p.copy_bytes + ky * p.tw * 128), 128);
+            const uint64_t bdesc = make_kmajor_desc(smem_u32(smem + tap * Cfg::kBBytes), 128);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                       (tap | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == nstages) {
+            stage = 0;
+            phase ^= 1;
+          }
+          umma_commit(&tfull[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+          continue;
+        }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -256,7 +300,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         mbar_wait(&cfull[buf], (g / NB) & 1);
         int m0, n0;
         coords(g, m0, n0);
-        tma_store_2d(&tmC, sC + buf * Cfg::kCBytes, n0, m0);
+        if (kConv && p.halo) {
+          const int m_blk = m0 / kTileM;
+          const int tx = m_blk % p.tiles_x;
+          const int ty = (m_blk / p.tiles_x) % p.tiles_y;
+          const int img = m_blk / (p.tiles_x * p.tiles_y);
+          tma_store_4d(&tmC, sC + buf * Cfg::kCBytes, n0, tx * p.tw, ty * p.th, img);     // clips ragged tiles
+        } else {
+          tma_store_2d(&tmC, sC + buf * Cfg::kCBytes, n0, m0);
+        }
         tma_store_commit();
         // recycle the buffer of the PREVIOUS block (its store had a whole block time to drain) so the lane
         // never stalls on the store it has just issued
@@ -548,7 +600,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
   if (p.staged) {
     const uint32_t ccols = p.out_f32 ? 32 : Cfg::kCCols;
     const uint32_t esz = p.out_f32 ? 4 : 2;
-    int st = encode_tiled_2d_ex(&tmC, p.out, static_cast<uint64_t>(p.M), static_cast<uint64_t>(p.N), kTileM, ccols, esz);
+    int st = p.halo ? encode_tiled_4d_nhwc(&tmC, p.out, p.batch, p.H, p.W, p.N, ccols, p.tw, p.th)
+                    : encode_tiled_2d_ex(&tmC, p.out, static_cast<uint64_t>(p.M), static_cast<uint64_t>(p.N), kTileM, ccols, esz);
     if (st) return st;
     if (p.residual != nullptr) {
       st = encode_tiled_2d_ex(&tmR, p.residual, static_cast<uint64_t>(p.M), static_cast<uint64_t>(p.N), kTileM, ccols, esz);
@@ -565,7 +618,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
   int smem_bytes = Cfg::kSmemBytes;
   int grid = tiles < sms ? tiles : sms;
   if (p.b_resident) {                     // planned by dispatch(): W tile + A ring + NB staging buffers fit
-    p.operand_bytes = p.num_kb * Cfg::kBBytes + p.res_stages * Cfg::kABytes;
+    p.operand_bytes = p.num_kb * Cfg::kBBytes + p.res_stages * (p.halo ? 3 * p.copy_bytes : Cfg::kABytes);
     smem_bytes = p.operand_bytes + NB * Cfg::kCBytes + 512 + 2048;
     grid = (sms / p.num_n_tiles) * p.num_n_tiles;
   }
@@ -624,7 +677,17 @@ static int dispatch(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& t
   // giving up two of the five residual/staging buffers costs more HBM overlap than the W re-fetch saves.
   p.b_resident = 0;
   const int sms = sm_count();
-  if (p.num_kb >= 2 && p.num_n_tiles <= 8 && sms > 0 && p.num_m_tiles >= 4 * sms && !getenv("LECB_NO_RESIDENT")) {
+  if (kConv && p.halo) {                  // halo-tile conv: W resident (9 x BN x 64), stages of three halo copies
+    const int budget = 227 * 1024 - nb * (kTileM * 64 * 2) - 512 - 2048 - 9 * BN * 64 * 2;
+    int stages = budget / (3 * p.copy_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages >= 2) {
+      p.b_resident = 1;
+      p.res_stages = stages;
+    } else {
+      return fail(LECB_ERR_UNSUPPORTED, "halo conv does not fit shared memory (BN=%d copy=%d)", BN, p.copy_bytes);
+    }
+  } else if (p.num_kb >= 2 && p.num_n_tiles <= 8 && sms > 0 && p.num_m_tiles >= 4 * sms && !getenv("LECB_NO_RESIDENT")) {
     const int ring = resident_ring(BN, BK, p.num_kb, nb);
     if (ring >= 3) {
       p.b_resident = 1;
@@ -704,19 +767,48 @@ extern "C" int lecb_conv3x3_bf16(const void* x, const void* w, const float* bias
   p.residual = nullptr;
   p.out = out;
   p.row_sumsq = nullptr;
-  p.M = M;
   p.N = Cout;
   p.kb_per_tap = Cin / BK;
   p.num_kb = 9 * p.kb_per_tap;
-  p.num_m_tiles = static_cast<int>((M + kTileM - 1) / kTileM);
   p.num_n_tiles = (Cout + BN - 1) / BN;
   p.flags = flags;
   p.H = H;
   p.W = Wd;
+  p.batch = B;
   CUtensorMap tmA, tmB;
-  int st = encode_im2col_3x3(&tmA, x, B, H, Wd, Cin, BK, kTileM);
+  int st = encode_tiled_2d(&tmB, w, static_cast<uint64_t>(Cout), static_cast<uint64_t>(9) * Cin, BN, BK);
   if (st) return st;
-  st = encode_tiled_2d(&tmB, w, static_cast<uint64_t>(Cout), static_cast<uint64_t>(9) * Cin, BN, BK);
+  // Halo-tile mode for the 64-channel layers (the im2col path re-fetches every input pixel once per tap and those
+  // layers are bound by that L2 -> SM fill): pick the patch shape that tiles the image with the least waste.
+  const int sms = sm_count();
+  if (Cin == 64 && BN == 64 && p.num_n_tiles == 1 && sms > 0 && !getenv("LECB_NO_HALO")) {
+    int th = 16, tw = 8;
+    auto waste = [&](int a, int b) {       // padded / real pixels for an a x b patch
+      return static_cast<double>(((H + a - 1) / a) * a) * (((Wd + b - 1) / b) * b) / (static_cast<double>(H) * Wd);
+    };
+    if (waste(8, 16) < waste(16, 8)) {
+      th = 8;
+      tw = 16;
+    }
+    const int tiles_x = (Wd + tw - 1) / tw, tiles_y = (H + th - 1) / th;
+    const int64_t tiles = static_cast<int64_t>(B) * tiles_x * tiles_y;
+    if (tiles >= 2 * sms && tiles < 0x7fffffff && waste(th, tw) <= 1.15) {
+      p.halo = 1;
+      p.th = th;
+      p.tw = tw;
+      p.tiles_x = tiles_x;
+      p.tiles_y = tiles_y;
+      p.copy_bytes = (th + 2) * tw * 128;
+      p.num_m_tiles = static_cast<int>(tiles);
+      p.M = tiles * kTileM;
+      st = encode_tiled_4d_nhwc(&tmA, x, B, H, Wd, Cin, 64, tw, th + 2);
+      if (st) return st;
+      return dispatch<true>(BN, BK, tmA, tmB, p, static_cast<cudaStream_t>(stream));
+    }
+  }
+  p.M = M;
+  p.num_m_tiles = static_cast<int>((M + kTileM - 1) / kTileM);
+  st = encode_im2col_3x3(&tmA, x, B, H, Wd, Cin, BK, kTileM);
   if (st) return st;
   return dispatch<true>(BN, BK, tmA, tmB, p, static_cast<cudaStream_t>(stream));
 }

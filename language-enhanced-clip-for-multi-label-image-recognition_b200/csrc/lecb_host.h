@@ -24,6 +24,9 @@ int encode_tiled_2d_ex(CUtensorMap* out, const void* base, uint64_t rows, uint64
 // are zero-filled, so a tile never reads the next batch's rows.
 int encode_tiled_3d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t batches,
                     uint32_t box_cols, uint32_t box_rows);
+// NHWC bf16 tensor as a plain 4-D tiled map (dims {C,W,H,N}); box = 1 x box_h x box_w x box_c
+int encode_tiled_4d_nhwc(CUtensorMap* out, const void* base, int B, int H, int W, int C, uint32_t box_c, uint32_t box_w,
+                         uint32_t box_h);
 // NHWC bf16 tensor, 3x3 / pad 1 / stride 1 im2col window; box = `pixels` x `channels`.
 int encode_im2col_3x3(CUtensorMap* out, const void* base, int B, int H, int W, int C, uint32_t channels,
                       uint32_t pixels);

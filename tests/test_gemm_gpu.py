@@ -163,3 +163,17 @@ def test_stem_conv1_tensor_core(b, h, w):
     torch.cuda.synchronize()
     # the CUDA-core kernel keeps fp32 inputs/weights: differences are the bf16 rounding of the operands
     assert (out.float() - ref.float()).abs().max().item() <= 3e-2 * (ref.float().abs().max().item() + 1e-6)
+
+
+@pytest.mark.parametrize("b,h,w,cout", [(8, 112, 112, 64), (4, 224, 112, 64), (24, 56, 56, 64), (20, 50, 64, 64), (6, 112, 112, 40)])
+def test_conv3x3_halo_tile_mode(b, h, w, cout):
+    """64-channel 3x3 convs run in halo-tile mode (patch tiles, three shifted halo copies per stage, TMA zero-fill as the
+    conv padding, 4-D TMA store that clips ragged patches): exact tilings, ragged H, 8x16 and 16x8 patches, Cout < 64."""
+    from lecb200 import ops
+    x = _rand((b, h, w, 64), 51).bfloat16()
+    wt = _rand((cout, 3, 3, 64), 52, (9 * 64) ** -0.5).bfloat16()
+    bias = _rand((cout,), 53, 0.1)
+    out = ops.conv3x3(x, wt, bias, relu=True)
+    torch.cuda.synchronize()
+    want = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), bias, padding=1)
+    _check(out, want.relu().permute(0, 2, 3, 1), f"halo conv {b}x{h}x{w}->{cout}")
