@@ -72,6 +72,10 @@ struct GemmParams {
   // (th+2) x tw halo copies (one per horizontal tap, so every tap's A operand is a dense, 1024-byte aligned
   // [128][64] K-major tile at copy[kx] + ky * tw rows): each input pixel crosses L2 -> SM ~3.4x instead of 9x
   int halo, tw, th, tiles_x, tiles_y, copy_bytes, batch;
+  int halo_single;    // tw == 8: ONE (th+2) x (tw+2) halo copy per stage.  The swizzle of a K-major operand is a function of
+                      // the absolute shared-memory address bits (measured: a descriptor may start on any 128-byte row
+                      // with base_offset 0), so tap (ky,kx) is just start = copy + (ky*(tw+2) + kx) * 128 with an
+                      // 8-row-group stride of (tw+2) * 128 bytes: every input pixel crosses L2 -> SM 1.4x instead of 9x
 };
 
 template <int BN, int BK, int NB, bool kConv>
@@ -170,6 +174,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int ty = (m_blk / p.tiles_x) % p.tiles_y;
           const int img = m_blk / (p.tiles_x * p.tiles_y);
           mbar_wait(&empty[stage], phase ^ 1);
+          if (p.halo_single) {
+            mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>((p.th + 2) * (p.tw + 2) * 128));
+            tma_load_4d(&tmA, &full[stage], sA_ring + stage * p.copy_bytes, 0, tx * p.tw - 1, ty * p.th - 1, img);
+            if (++stage == nstages) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           mbar_arrive_expect_tx(&full[stage], 3u * static_cast<uint32_t>(p.copy_bytes));
           uint8_t* dst = sA_ring + stage * 3 * p.copy_bytes;
 #pragma unroll
@@ -225,11 +238,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (kConv && p.halo) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint8_t* src = sA_ring + stage * 3 * p.copy_bytes;
+          const uint8_t* src = sA_ring + stage * (p.halo_single ? 1 : 3) * p.copy_bytes;
+          const uint32_t pitch = static_cast<uint32_t>(p.tw + 2) * 128u;
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap) {
             const int ky = tap / 3, kx = tap - ky * 3;
-            const uint64_t adesc = make_kmajor_desc(smem_u32(src + kx * p.copy_bytes + ky * p.tw * 128), 128);
+            uint64_t adesc;
+            if (p.halo_single) {
+              adesc = make_kmajor_desc(smem_u32(src + ky * pitch + kx * 128), 128);
+              adesc = (adesc & ~(static_cast<uint64_t>(0x3FFF) << 32)) | (static_cast<uint64_t>(pitch >> 4) << 32);
+            } else {
+              adesc = make_kmajor_desc(smem_u32(src + kx * p.copy_bytes + ky * p.tw * 128), 128);
+            }
             const uint64_t bdesc = make_kmajor_desc(smem_u32(smem + tap * Cfg::kBBytes), 128);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -618,7 +638,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
   int smem_bytes = Cfg::kSmemBytes;
   int grid = tiles < sms ? tiles : sms;
   if (p.b_resident) {                     // planned by dispatch(): W tile + A ring + NB staging buffers fit
-    p.operand_bytes = p.num_kb * Cfg::kBBytes + p.res_stages * (p.halo ? 3 * p.copy_bytes : Cfg::kABytes);
+    p.operand_bytes = p.num_kb * Cfg::kBBytes + p.res_stages * (p.halo ? (p.halo_single ? 1 : 3) * p.copy_bytes : Cfg::kABytes);
     smem_bytes = p.operand_bytes + NB * Cfg::kCBytes + 512 + 2048;
     grid = (sms / p.num_n_tiles) * p.num_n_tiles;
   }
@@ -679,7 +699,7 @@ static int dispatch(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& t
   const int sms = sm_count();
   if (kConv && p.halo) {                  // halo-tile conv: W resident (9 x BN x 64), stages of three halo copies
     const int budget = 227 * 1024 - nb * (kTileM * 64 * 2) - 512 - 2048 - 9 * BN * 64 * 2;
-    int stages = budget / (3 * p.copy_bytes);
+    int stages = budget / ((p.halo_single ? 1 : 3) * p.copy_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages >= 2) {
       p.b_resident = 1;
@@ -801,7 +821,16 @@ extern "C" int lecb_conv3x3_bf16(const void* x, const void* w, const float* bias
       p.copy_bytes = (th + 2) * tw * 128;
       p.num_m_tiles = static_cast<int>(tiles);
       p.M = tiles * kTileM;
-      st = encode_tiled_4d_nhwc(&tmA, x, B, H, Wd, Cin, 64, tw, th + 2);
+      // Measured (RN101, layer1 conv2): the single-copy layout moves 2.4x fewer bytes and fits five stages, yet runs
+      // 18 % SLOWER than three aligned copies — operand groups that straddle 1024-byte swizzle atoms cost the tensor
+      // pipe more than the L2 traffic saved.  Kept behind a switch as the record of that experiment.
+      if (tw == 8 && getenv("LECB_HALO_SINGLE")) {
+        p.halo_single = 1;
+        p.copy_bytes = ((th + 2) * (tw + 2) * 128 + 1023) / 1024 * 1024;
+        st = encode_tiled_4d_nhwc(&tmA, x, B, H, Wd, Cin, 64, tw + 2, th + 2);
+      } else {
+        st = encode_tiled_4d_nhwc(&tmA, x, B, H, Wd, Cin, 64, tw, th + 2);
+      }
       if (st) return st;
       return dispatch<true>(BN, BK, tmA, tmB, p, static_cast<cudaStream_t>(stream));
     }
