@@ -687,7 +687,7 @@ static int dispatch(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& t
   int nb = 2;
   if (!kConv) {
     if (p.num_kb <= 2) nb = 8;
-    else if (p.num_kb <= 4) nb = 5;
+    else if (p.num_kb <= 4) nb = getenv("LECB_NB_K4") ? atoi(getenv("LECB_NB_K4")) : 5;
     else if (p.num_kb <= 8) nb = 4;
     // fp32 output / residual moves twice the bytes per element: keep four blocks in flight up to K = 1024
     else if ((p.flags & LECB_EPI_OUT_F32) && p.num_kb <= 16) nb = 4;
