@@ -2,7 +2,7 @@
 // full attention (M:207-228 inside M:240-276) and, with `causal`, the text transformer's masked
 // attention (M:364-370).
 //
-// One CTA = one (image, head, 128-query tile); two CTAs are co-resident per SM.  K / V arrive as 128-key TMA
+// Work item = one (image, head, 128-query tile); persistent CTAs, two co-resident per SM, loop over items.  K / V arrive as 128-key TMA
 // tiles (128B swizzle) and are consumed in 64-key sub-blocks with double-buffered S (TMEM) and P (smem), so
 // the tensor pipe computes Q K^T of sub-block j+1 while the softmax warps work on sub-block j:
 //   S = Q K^T      tcgen05.mma  M=128 N=64 K=64, fp32 S in TMEM
@@ -32,16 +32,17 @@ constexpr int kAtSub = 64;          // keys per softmax / MMA sub-block
 constexpr int kAtDh = 64;
 constexpr int kAtThreads = 192;
 constexpr int kAtTileBytes = kAtTile * kAtDh * 2;    // 16 KB
-constexpr int kAtSmemQ = 0;
-constexpr int kAtSmemK = kAtTileBytes;               // 2 stages
-constexpr int kAtSmemV = 3 * kAtTileBytes;           // 2 stages
-constexpr int kAtSmemBars = 5 * kAtTileBytes;
-constexpr int kAtSmemBytes = kAtSmemBars + 160;
+constexpr int kAtSmemQ = 0;                          // 2 buffers (next item's Q prefetched)
+constexpr int kAtSmemK = 2 * kAtTileBytes;           // 2 stages
+constexpr int kAtSmemV = 4 * kAtTileBytes;           // 2 stages
+constexpr int kAtSmemBars = 6 * kAtTileBytes;
+constexpr int kAtSmemBytes = kAtSmemBars + 192;
 constexpr int kAtTmemCols = 256;
 
 struct AttnParams {
   __nv_bfloat16* out;
   int T, W, q_rows, causal;
+  int q_tiles, heads, total_items;
   float sc;            // log2(e) / sqrt(dh)
 };
 
@@ -66,35 +67,46 @@ __host__ __device__ constexpr uint32_t attn_idesc(uint32_t n, bool b_mn_major) {
 __global__ void __launch_bounds__(kAtThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem + kAtSmemQ;
+  uint8_t* sQ = smem + kAtSmemQ;     // 2 buffers: the next work item's Q tile is prefetched
   uint8_t* sK = smem + kAtSmemK;
   uint8_t* sV = smem + kAtSmemV;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAtSmemBars);
-  uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;     // [2] 128-key K tiles
-  uint64_t* k_empty = bars + 3;    // [2]
-  uint64_t* v_full = bars + 5;     // [2]
-  uint64_t* v_empty = bars + 7;    // [2]
-  uint64_t* s_full = bars + 9;     // [2] S buffer holds Q K^T of a 64-key sub-block
-  uint64_t* s_free = bars + 11;    // [2] softmax has read it
-  uint64_t* p_full = bars + 13;    // [2] P block written
-  uint64_t* p_free = bars + 15;    // [2] PV MMA of the sub-block complete: P reusable, O includes the sub-block
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* q_full = bars;         // [2]
+  uint64_t* q_empty = bars + 2;    // [2] last Q K^T of the item issued and complete
+  uint64_t* k_full = bars + 4;     // [2] 128-key K tiles
+  uint64_t* k_empty = bars + 6;    // [2]
+  uint64_t* v_full = bars + 8;     // [2]
+  uint64_t* v_empty = bars + 10;   // [2]
+  uint64_t* s_full = bars + 12;    // [2] S buffer holds Q K^T of a 64-key sub-block
+  uint64_t* s_free = bars + 14;    // [2] softmax has read it
+  uint64_t* p_full = bars + 16;    // [2] P block written
+  uint64_t* p_free = bars + 18;    // [2] PV MMA of the sub-block complete: P reusable, O includes the sub-block
+  uint64_t* o_free = bars + 20;    // softmax warps have read the finished item's O
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kAtTile;
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
-  const int kv_end = p.causal ? min(p.T, q0 + kAtTile) : p.T;
-  const int n_sub = (kv_end + kAtSub - 1) / kAtSub;      // 64-key sub-blocks
-  const int n_kv = (n_sub + 1) / 2;                      // 128-key K / V tiles
+
+  // Persistent CTA: work item w = (image b, head h, query tile qt), w = blockIdx.x + i * gridDim.x.  Every
+  // barrier parity below is derived from RUNNING counters (items, K/V tiles, sub-blocks) that all three roles
+  // advance identically, so the pipelines never drain between items: the producer prefetches the next item's
+  // Q / K / V and the tensor pipe starts its Q K^T while the softmax warps are still storing the previous O.
+  auto decode = [&](int w, int& q0, int& h, int& b, int& n_sub, int& n_kv) {
+    const int qt = w % p.q_tiles;
+    h = (w / p.q_tiles) % p.heads;
+    b = w / (p.q_tiles * p.heads);
+    q0 = qt * kAtTile;
+    const int kv_end = p.causal ? min(p.T, q0 + kAtTile) : p.T;
+    n_sub = (kv_end + kAtSub - 1) / kAtSub;      // 64-key sub-blocks
+    n_kv = (n_sub + 1) / 2;                      // 128-key K / V tiles
+  };
 
   if (warp == 4 && lane == 0) {
     if ((smem_u32(smem) & 1023u) != 0) __trap();     // swizzled tiles need 1024-byte alignment
     tma_prefetch_desc(&tmQKV);
-    mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
       mbar_init(&k_full[i], 1);
       mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);
@@ -104,6 +116,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       mbar_init(&p_full[i], 4);
       mbar_init(&p_free[i], 1);
     }
+    mbar_init(o_free, 4);
     fence_barrier_init();
   }
   if (warp == 5) {
@@ -118,68 +131,83 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   if (warp == 4) {
     // ------------------------------- TMA producer -------------------------------
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, kAtTileBytes);
-      tma_load_3d(&tmQKV, q_full, sQ, h * kAtDh, q0, b);
-      for (int j = 0; j < n_kv; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&k_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[s], kAtTileBytes);
-        tma_load_3d(&tmQKV, &k_full[s], sK + s * kAtTileBytes, p.W + h * kAtDh, j * kAtTile, b);
-        mbar_wait(&v_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[s], kAtTileBytes);
-        tma_load_3d(&tmQKV, &v_full[s], sV + s * kAtTileBytes, 2 * p.W + h * kAtDh, j * kAtTile, b);
+      int it = 0, kvc = 0;
+      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++it) {
+        int q0, h, b, n_sub, n_kv;
+        decode(w, q0, h, b, n_sub, n_kv);
+        const int qb = it & 1;
+        mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&q_full[qb], kAtTileBytes);
+        tma_load_3d(&tmQKV, &q_full[qb], sQ + qb * kAtTileBytes, h * kAtDh, q0, b);
+        for (int j = 0; j < n_kv; ++j, ++kvc) {
+          const int s = kvc & 1;
+          const uint32_t ph = (kvc >> 1) & 1;
+          mbar_wait(&k_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&k_full[s], kAtTileBytes);
+          tma_load_3d(&tmQKV, &k_full[s], sK + s * kAtTileBytes, p.W + h * kAtDh, j * kAtTile, b);
+          mbar_wait(&v_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&v_full[s], kAtTileBytes);
+          tma_load_3d(&tmQKV, &v_full[s], sV + s * kAtTileBytes, 2 * p.W + h * kAtDh, j * kAtTile, b);
+        }
       }
     }
   } else if (warp == 5) {
     // ------------------------------- MMA issuer ---------------------------------
-    // Sub-block jj uses S/P buffer jj & 1 and the (jj & 1) half of K/V tile jj >> 1.  QK^T of sub-block jj+1 is
-    // issued before PV of sub-block jj, so the tensor pipe always runs one S ahead of the softmax warps.
+    // Sub-block g (running index) uses S/P buffer g & 1; sub-block jj of an item uses the (jj & 1) half of K/V tile
+    // kvc + (jj >> 1).  Q K^T of sub-block jj+1 is issued before P V of sub-block jj, so the tensor pipe always runs
+    // one S ahead of the softmax warps.
     if (lane == 0) {
       constexpr uint32_t idesc_qk = attn_idesc(kAtSub, false);
       constexpr uint32_t idesc_pv = attn_idesc(kAtDh, true);
       const uint32_t tO = tmem_base + 128u;
-      auto issue_pv = [&](int i) {
-        const int bf = i & 1, tile = i >> 1, s = tile & 1;
-        if (bf == 0) mbar_wait(&v_full[s], (tile >> 1) & 1);
-        mbar_wait(&p_full[bf], (i >> 1) & 1);
-        tc_fence_after();
+      int it = 0, kvc = 0, sc = 0;
+      for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++it) {
+        int q0, h, b, n_sub, n_kv;
+        decode(w, q0, h, b, n_sub, n_kv);
+        const int qb = it & 1;
+        auto issue_pv = [&](int i) {
+          const int g = sc + i, bf = g & 1, half = i & 1, tile = kvc + (i >> 1), s = tile & 1;
+          if (half == 0) mbar_wait(&v_full[s], (tile >> 1) & 1);
+          mbar_wait(&p_full[bf], (g >> 1) & 1);
+          if (i == 0 && it >= 1) mbar_wait(o_free, (it - 1) & 1);      // the previous item's O has been read out
+          tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < kAtSub / 16; ++kk) {
-          // A = P block in TMEM: bf16 pairs packed per column, 16 keys = 8 columns per step
-          const uint32_t tP = tmem_base + 192u + static_cast<uint32_t>(bf * (kAtSub / 2) + kk * 8);
-          // B = V tile [keys][dh] used in place as an MN-major operand: 16 keys = 2048 bytes per step
-          const uint64_t bdesc = make_kmajor_desc(smem_u32(sV + s * kAtTileBytes + bf * (kAtSub * 128) + kk * 2048), 128);
-          umma_f16_ts(tO, tP, bdesc, idesc_pv, (i | kk) != 0 ? 1u : 0u);
+          for (int kk = 0; kk < kAtSub / 16; ++kk) {
+            // A = P block in TMEM: bf16 pairs packed per column, 16 keys = 8 columns per step
+            const uint32_t tP = tmem_base + 192u + static_cast<uint32_t>(bf * (kAtSub / 2) + kk * 8);
+            // B = V tile [keys][dh] used in place as an MN-major operand: 16 keys = 2048 bytes per step
+            const uint64_t bdesc = make_kmajor_desc(smem_u32(sV + s * kAtTileBytes + half * (kAtSub * 128) + kk * 2048), 128);
+            umma_f16_ts(tO, tP, bdesc, idesc_pv, (i | kk) != 0 ? 1u : 0u);
+          }
+          if (half == 1 || i == n_sub - 1) umma_commit(&v_empty[s]);
+          umma_commit(&p_free[bf]);
+        };
+        mbar_wait(&q_full[qb], (it >> 1) & 1);
+        for (int jj = 0; jj < n_sub; ++jj) {
+          const int g = sc + jj, bf = g & 1, half = jj & 1, tile = kvc + (jj >> 1), s = tile & 1;
+          if (half == 0) mbar_wait(&k_full[s], (tile >> 1) & 1);
+          if (g >= 2) mbar_wait(&s_free[bf], ((g >> 1) - 1) & 1);
+          tc_fence_after();
+          const uint64_t adesc = make_kmajor_desc(smem_u32(sQ + qb * kAtTileBytes), 128);
+          const uint64_t bdesc = make_kmajor_desc(smem_u32(sK + s * kAtTileBytes + half * (kAtSub * 128)), 128);
+#pragma unroll
+          for (int k = 0; k < kAtDh / 16; ++k)
+            umma_f16(tmem_base + static_cast<uint32_t>(bf * kAtSub), adesc + static_cast<uint64_t>(2 * k),
+                     bdesc + static_cast<uint64_t>(2 * k), idesc_qk, k != 0 ? 1u : 0u);
+          if (half == 1 || jj == n_sub - 1) umma_commit(&k_empty[s]);
+          if (jj == n_sub - 1) umma_commit(&q_empty[qb]);
+          umma_commit(&s_full[bf]);
+          if (jj >= 1) issue_pv(jj - 1);
         }
-        if (bf == 1 || i == n_sub - 1) umma_commit(&v_empty[s]);
-        umma_commit(&p_free[bf]);
-      };
-      mbar_wait(q_full, 0);
-      for (int jj = 0; jj < n_sub; ++jj) {
-        const int bf = jj & 1, tile = jj >> 1, s = tile & 1;
-        if (bf == 0) mbar_wait(&k_full[s], (tile >> 1) & 1);
-        if (jj >= 2) mbar_wait(&s_free[bf], ((jj >> 1) - 1) & 1);
-        tc_fence_after();
-        const uint64_t adesc = make_kmajor_desc(smem_u32(sQ), 128);
-        const uint64_t bdesc = make_kmajor_desc(smem_u32(sK + s * kAtTileBytes + bf * (kAtSub * 128)), 128);
-#pragma unroll
-        for (int k = 0; k < kAtDh / 16; ++k)
-          umma_f16(tmem_base + static_cast<uint32_t>(bf * kAtSub), adesc + static_cast<uint64_t>(2 * k),
-                   bdesc + static_cast<uint64_t>(2 * k), idesc_qk, k != 0 ? 1u : 0u);
-        if (bf == 1 || jj == n_sub - 1) umma_commit(&k_empty[s]);
-        umma_commit(&s_full[bf]);
-        if (jj >= 1) issue_pv(jj - 1);
+        issue_pv(n_sub - 1);
+        sc += n_sub;
+        kvc += n_kv;
       }
-      issue_pv(n_sub - 1);
     }
   } else {
     // ------------------------------- softmax warps (thread == query row) --------
     const int row = warp * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    const int qi = q0 + row;
-    const int limit = p.causal ? min(p.T - 1, qi) : p.T - 1;       // last key index this row may see
-    float m = -INFINITY, l = 0.f;
     const uint32_t tO = tmem_base + lane_base + 128u;
 
     // exact row maximum of the (masked) 64-key sub-block in S buffer `tS`
@@ -238,84 +266,97 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
                        : write_p_impl(std::false_type{}, tS, tP, msc, lim, wait_bar, wait_parity);
     };
 
-    for (int jj = 0; jj < n_sub; ++jj) {
-      const int bf = jj & 1;
-      const uint32_t par = (jj >> 1) & 1;
-      const int kv0 = jj * kAtSub;
-      const bool need_mask = (kv0 + kAtSub > p.T) || (p.causal && kv0 + kAtSub - 1 > q0);
-      const int lim = limit - kv0;             // columns c <= lim are visible
-      const uint32_t tS = tmem_base + lane_base + static_cast<uint32_t>(bf * kAtSub);
-      const uint32_t pblk = tmem_base + lane_base + 192u + static_cast<uint32_t>(bf * (kAtSub / 2));
-      uint64_t* pf = jj >= 2 ? &p_free[bf] : nullptr;          // PV of sub-block jj-2 read this P block
-      mbar_wait(&s_full[bf], par);
-      tc_fence_after();
-      if (jj == 0) {
-        m = block_max(tS, need_mask, lim);
-        l = write_p(tS, pblk, m * p.sc, need_mask, lim, nullptr, 0);
-      } else {
-        float sum = write_p(tS, pblk, m * p.sc, need_mask, lim, pf, par ^ 1);
-        // lazy rescaling: keep m unless some probability of this sub-block is enormous relative to it
-        if (__any_sync(0xffffffffu, !(sum <= 32768.f))) {
-          const float m_new = fmaxf(m, block_max(tS, need_mask, lim));
-          const float alpha = fast_exp2((m - m_new) * p.sc);
-          // every PV up to sub-block jj-1 must have landed in O; PV of sub-block jj is not released yet, so
-          // this warp's 32 rows of O can be rescaled in place
-          mbar_wait(&p_free[bf ^ 1], ((jj - 1) >> 1) & 1);
-          tc_fence_after();
+    int sc = 0;
+    for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
+      int q0, h, b, n_sub, n_kv;
+      decode(w, q0, h, b, n_sub, n_kv);
+      const int qi = q0 + row;
+      const int limit = p.causal ? min(p.T - 1, qi) : p.T - 1;       // last key index this row may see
+      float m = -INFINITY, l = 0.f;
+      for (int jj = 0; jj < n_sub; ++jj) {
+        const int g = sc + jj, bf = g & 1;
+        const uint32_t par = (g >> 1) & 1;
+        const int kv0 = jj * kAtSub;
+        const bool need_mask = (kv0 + kAtSub > p.T) || (p.causal && kv0 + kAtSub - 1 > q0);
+        const int lim = limit - kv0;             // columns c <= lim are visible
+        const uint32_t tS = tmem_base + lane_base + static_cast<uint32_t>(bf * kAtSub);
+        const uint32_t pblk = tmem_base + lane_base + 192u + static_cast<uint32_t>(bf * (kAtSub / 2));
+        uint64_t* pf = g >= 2 ? &p_free[bf] : nullptr;          // PV of sub-block g-2 read this P buffer
+        mbar_wait(&s_full[bf], par);
+        tc_fence_after();
+        if (jj == 0) {
+          m = block_max(tS, need_mask, lim);
+          l = write_p(tS, pblk, m * p.sc, need_mask, lim, pf, par ^ 1);
+        } else {
+          float sum = write_p(tS, pblk, m * p.sc, need_mask, lim, pf, par ^ 1);
+          // lazy rescaling: keep m unless some probability of this sub-block is enormous relative to it
+          if (__any_sync(0xffffffffu, !(sum <= 32768.f))) {
+            const float m_new = fmaxf(m, block_max(tS, need_mask, lim));
+            const float alpha = fast_exp2((m - m_new) * p.sc);
+            // every PV up to sub-block g-1 must have landed in O; PV of sub-block g is not released yet, so
+            // this warp's 32 rows of O can be rescaled in place
+            mbar_wait(&p_free[bf ^ 1], ((g - 1) >> 1) & 1);
+            tc_fence_after();
 #pragma unroll 1
-          for (int hlf = 0; hlf < 2; ++hlf) {
-            uint32_t r[32];
-            tmem_ld_32x32(tO + static_cast<uint32_t>(hlf * 32), r);
-            tmem_ld_wait();
+            for (int hlf = 0; hlf < 2; ++hlf) {
+              uint32_t r[32];
+              tmem_ld_32x32(tO + static_cast<uint32_t>(hlf * 32), r);
+              tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st_32x32(tO + static_cast<uint32_t>(hlf * 32), r);
+              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+              tmem_st_32x32(tO + static_cast<uint32_t>(hlf * 32), r);
+            }
+            tmem_st_wait();
+            sum = write_p(tS, pblk, m_new * p.sc, need_mask, lim, nullptr, 0);
+            l *= alpha;
+            m = m_new;
           }
-          tmem_st_wait();
-          sum = write_p(tS, pblk, m_new * p.sc, need_mask, lim, nullptr, 0);
-          l *= alpha;
-          m = m_new;
+          l += sum;
         }
-        l += sum;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&s_free[bf]);
+          mbar_arrive(&p_full[bf]);
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&s_free[bf]);
-        mbar_arrive(&p_full[bf]);
-      }
-    }
-    // all PV MMAs done -> O complete (the last two sub-blocks' commits cover every earlier MMA)
-    if (n_sub >= 2) mbar_wait(&p_free[(n_sub - 2) & 1], ((n_sub - 2) >> 1) & 1);
-    mbar_wait(&p_free[(n_sub - 1) & 1], ((n_sub - 1) >> 1) & 1);
-    tc_fence_after();
-    {      // the tcgen05.ld is warp-collective: every lane loads, only valid query rows store
-      uint32_t r0[32], r1[32];
-      tmem_ld_32x32(tO, r0);
-      tmem_ld_32x32(tO + 32u, r1);
-      tmem_ld_wait();
-      if (qi < p.q_rows) {
-        const float inv = 1.0f / l;
-        uint4* op = reinterpret_cast<uint4*>(p.out + (static_cast<int64_t>(b) * p.T + qi) * p.W + h * kAtDh);
+      // all PV MMAs of the item done -> O complete (the last two sub-blocks' commits cover every earlier MMA)
+      const int gl = sc + n_sub - 1;
+      if (gl >= 1) mbar_wait(&p_free[(gl - 1) & 1], ((gl - 1) >> 1) & 1);
+      mbar_wait(&p_free[gl & 1], (gl >> 1) & 1);
+      tc_fence_after();
+      {      // the tcgen05.ld is warp-collective: every lane loads, only valid query rows store
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(tO, r0);
+        tmem_ld_32x32(tO + 32u, r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_free);          // O is in registers: the next item's first PV may overwrite it
+        if (qi < p.q_rows) {
+          const float inv = 1.0f / l;
+          uint4* op = reinterpret_cast<uint4*>(p.out + (static_cast<int64_t>(b) * p.T + qi) * p.W + h * kAtDh);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 u;
-          u.x = pack_bf16(__uint_as_float(r0[q * 8 + 0]) * inv, __uint_as_float(r0[q * 8 + 1]) * inv);
-          u.y = pack_bf16(__uint_as_float(r0[q * 8 + 2]) * inv, __uint_as_float(r0[q * 8 + 3]) * inv);
-          u.z = pack_bf16(__uint_as_float(r0[q * 8 + 4]) * inv, __uint_as_float(r0[q * 8 + 5]) * inv);
-          u.w = pack_bf16(__uint_as_float(r0[q * 8 + 6]) * inv, __uint_as_float(r0[q * 8 + 7]) * inv);
-          op[q] = u;
-        }
+          for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            u.x = pack_bf16(__uint_as_float(r0[q * 8 + 0]) * inv, __uint_as_float(r0[q * 8 + 1]) * inv);
+            u.y = pack_bf16(__uint_as_float(r0[q * 8 + 2]) * inv, __uint_as_float(r0[q * 8 + 3]) * inv);
+            u.z = pack_bf16(__uint_as_float(r0[q * 8 + 4]) * inv, __uint_as_float(r0[q * 8 + 5]) * inv);
+            u.w = pack_bf16(__uint_as_float(r0[q * 8 + 6]) * inv, __uint_as_float(r0[q * 8 + 7]) * inv);
+            op[q] = u;
+          }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 u;
-          u.x = pack_bf16(__uint_as_float(r1[q * 8 + 0]) * inv, __uint_as_float(r1[q * 8 + 1]) * inv);
-          u.y = pack_bf16(__uint_as_float(r1[q * 8 + 2]) * inv, __uint_as_float(r1[q * 8 + 3]) * inv);
-          u.z = pack_bf16(__uint_as_float(r1[q * 8 + 4]) * inv, __uint_as_float(r1[q * 8 + 5]) * inv);
-          u.w = pack_bf16(__uint_as_float(r1[q * 8 + 6]) * inv, __uint_as_float(r1[q * 8 + 7]) * inv);
-          op[4 + q] = u;
+          for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            u.x = pack_bf16(__uint_as_float(r1[q * 8 + 0]) * inv, __uint_as_float(r1[q * 8 + 1]) * inv);
+            u.y = pack_bf16(__uint_as_float(r1[q * 8 + 2]) * inv, __uint_as_float(r1[q * 8 + 3]) * inv);
+            u.z = pack_bf16(__uint_as_float(r1[q * 8 + 4]) * inv, __uint_as_float(r1[q * 8 + 5]) * inv);
+            u.w = pack_bf16(__uint_as_float(r1[q * 8 + 6]) * inv, __uint_as_float(r1[q * 8 + 7]) * inv);
+            op[4 + q] = u;
+          }
         }
       }
+      sc += n_sub;
     }
   }
 
@@ -363,7 +404,14 @@ extern "C" int lecb_attn_fwd(const void* qkv, void* out, int B, int T, int W, in
   p.q_rows = q_rows;
   p.causal = causal;
   p.sc = 1.4426950408889634f / 8.0f;
-  dim3 grid((q_rows + kAtTile - 1) / kAtTile, heads, B);
+  p.q_tiles = (q_rows + kAtTile - 1) / kAtTile;
+  p.heads = heads;
+  const int64_t total = static_cast<int64_t>(p.q_tiles) * heads * B;
+  LECB_CHECK_ARG(total < 0x7fffffff, "lecb_attn_fwd: too many work items");
+  p.total_items = static_cast<int>(total);
+  const int sms = sm_count();
+  if (sms <= 0) return fail(LECB_ERR_CUDA, "no CUDA device");
+  const int grid = p.total_items < 2 * sms ? p.total_items : 2 * sms;        // persistent: two CTAs per SM
   attn_fwd_kernel<<<grid, kAtThreads, kAtSmemBytes, static_cast<cudaStream_t>(stream)>>>(tm, p);
   count_launch();
   return check_launch("attn_fwd_kernel");
