@@ -691,6 +691,9 @@ static int dispatch(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& t
     else if (p.num_kb <= 8) nb = 4;
     // fp32 output / residual moves twice the bytes per element: keep four blocks in flight up to K = 1024
     else if ((p.flags & LECB_EPI_OUT_F32) && p.num_kb <= 16) nb = 4;
+    // QuickGELU costs two MUFU ops per element: the epilogue of a 128x256 tile is then almost as long as a K = 768
+    // mainloop, and with two staging buffers it stalls on store drain (measured 971 -> 1164 TF/s with four)
+    else if ((p.flags & LECB_EPI_QUICKGELU) && p.num_kb <= 16) nb = 4;
   }
   // Resident-W mode (see launch_gemm): worth it when every CTA walks many m tiles of one n tile AND the staging
   // depth does not have to shrink for it — measured on layer3's expand conv (K 256 -> N 1024, 128 KB W tile):
