@@ -156,7 +156,7 @@ def cpu_reference_rate(arch, steps, warmup, budget_s, threads=None):
     step(probe)
     t_img = time.perf_counter() - t0
     total_steps = steps + warmup
-    per_step = max(1, min(8, int(budget_s / max(t_img, 1e-3) / max(total_steps, 1))))
+    per_step = max(1, min(32, int(budget_s / max(t_img, 1e-3) / max(total_steps, 1))))
     imgs = synth.images(per_step, arch.image_resolution, 100)
     for _ in range(warmup):
         step(imgs)
@@ -371,7 +371,7 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_rate(arch, steps=2, warmup=1, budget_s=20.0)
+        r = cpu_reference_rate(arch, steps=3, warmup=1, budget_s=25.0)
         cpu_baseline = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
