@@ -95,9 +95,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* empty = bars + kMaxStages;
   uint64_t* tfull = bars + 2 * kMaxStages;
   uint64_t* tempty = tfull + 2;
+  // staging barriers: one (free, full) pair per buffer — but never fewer than two pairs: with a single buffer the two
+  // epilogue groups would share one barrier and a group could be two phases ahead of it (parity aliasing), so the
+  // barrier index (block % kNBar) is decoupled from the buffer index (block % NB)
+  constexpr int kNBar = NB < 2 ? 2 : NB;
   uint64_t* cfree = tempty + 2;
-  uint64_t* cfull = cfree + NB;
-  uint64_t* bres = cfull + NB;
+  uint64_t* cfull = cfree + kNBar;
+  uint64_t* bres = cfull + kNBar;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres + 1);
   float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);      // [2][256]: bias slice of a tile
   // b_resident: [ W k-blocks (num_kb * kBBytes) | A ring (res_stages * kABytes) ] inside the operand region
@@ -140,7 +144,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // in which case the groups alternate tiles (4 warps); direct fp32 path: group 0 only
       mbar_init(&tempty[i], (p.staged && p.cblocks > 1) ? 8 : 4);
     }
-    for (int i = 0; i < NB; ++i) {
+    for (int i = 0; i < kNBar; ++i) {
       mbar_init(&cfree[i], 1);
       mbar_init(&cfull[i], 4);
     }
@@ -304,20 +308,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         n0 = n_blk * BN + cb * ccols;
       };
       auto make_free = [&](uint32_t g) {
-        const int buf = g % NB;
+        const int buf = g % NB, bi = g % kNBar;
         if (has_res) {
           int m0, n0;
           coords(g, m0, n0);
-          mbar_arrive_expect_tx(&cfree[buf], Cfg::kCBytes);
-          tma_load_2d(&tmR, &cfree[buf], sC + buf * Cfg::kCBytes, n0, m0);
+          mbar_arrive_expect_tx(&cfree[bi], Cfg::kCBytes);
+          tma_load_2d(&tmR, &cfree[bi], sC + buf * Cfg::kCBytes, n0, m0);
         } else {
-          mbar_arrive(&cfree[buf]);
+          mbar_arrive(&cfree[bi]);
         }
       };
       for (uint32_t g = 0; g < NB && g < total; ++g) make_free(g);
       for (uint32_t g = 0; g < total; ++g) {
         const int buf = g % NB;
-        mbar_wait(&cfull[buf], (g / NB) & 1);
+        mbar_wait(&cfull[g % kNBar], (g / kNBar) & 1);
         int m0, n0;
         coords(g, m0, n0);
         if (kConv && p.halo) {
@@ -332,7 +336,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tma_store_commit();
         // recycle the buffer of the PREVIOUS block (its store had a whole block time to drain) so the lane
         // never stalls on the store it has just issued
-        if (g >= 1 && g - 1 + NB < total) {
+        if (NB == 1) {                    // single staging buffer: it is free again once this store has read it
+          if (g + 1 < total) {
+            tma_store_wait_read0();
+            make_free(g + 1);
+          }
+        } else if (g >= 1 && g - 1 + NB < total) {
           tma_store_wait_read1();
           make_free(g - 1 + NB);
         }
@@ -400,7 +409,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
           }
-          mbar_wait(&cfree[buf], (gblk / NB) & 1);
+          mbar_wait(&cfree[gblk % kNBar], (gblk / kNBar) & 1);
           const int n0 = n_blk * BN + cb * 32;
           float v[32];
 #pragma unroll
@@ -438,7 +447,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&cfull[buf]);
+          if (lane == 0) mbar_arrive(&cfull[gblk % kNBar]);
         }
       } else if (p.staged) {
         // block g = tile_seq * kCBlocks + cb belongs to group g % 2
@@ -463,7 +472,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[acc]);
           }
-          mbar_wait(&cfree[buf], (gblk / NB) & 1);
+          mbar_wait(&cfree[gblk % kNBar], (gblk / kNBar) & 1);
 #pragma unroll
           for (int half = 0; half < kCCols / 32; ++half) {
             const int n0 = n_blk * BN + cb * kCCols + half * 32;
@@ -516,7 +525,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&cfull[buf]);
+          if (lane == 0) mbar_arrive(&cfull[gblk % kNBar]);
         }
       } else {
         if (group != 0) continue;                 // direct fp32 stores: one group is plenty (small GEMMs)
@@ -701,15 +710,19 @@ static int dispatch(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& t
   p.b_resident = 0;
   const int sms = sm_count();
   if (kConv && p.halo) {                  // halo-tile conv: W resident (9 x BN x 64), stages of three halo copies
-    const int budget = 227 * 1024 - nb * (kTileM * 64 * 2) - 512 - 2048 - 9 * BN * 64 * 2;
-    int stages = budget / ((p.halo_single ? 1 : 3) * p.copy_bytes);
-    if (stages > kMaxStages) stages = kMaxStages;
-    if (stages >= 2) {
-      p.b_resident = 1;
-      p.res_stages = stages;
-    } else {
-      return fail(LECB_ERR_UNSUPPORTED, "halo conv does not fit shared memory (BN=%d copy=%d)", BN, p.copy_bytes);
+    auto stages_with = [&](int nbuf) {
+      const int budget = 227 * 1024 - nbuf * (kTileM * 64 * 2) - 512 - 2048 - 9 * BN * 64 * 2;
+      const int st = budget / ((p.halo_single ? 1 : 3) * p.copy_bytes);
+      return st > kMaxStages ? kMaxStages : st;
+    };
+    int stages = stages_with(nb);
+    if (stages < 2 && stages_with(1) >= 1) {       // Cout = 128: 144 KB of weights leave room for ONE halo stage and
+      nb = 1;                                      // one staging buffer; still ~3x faster than re-fetching per tap
+      stages = stages_with(1);
     }
+    if (stages < 1) return fail(LECB_ERR_UNSUPPORTED, "halo conv does not fit shared memory (BN=%d copy=%d)", BN, p.copy_bytes);
+    p.b_resident = 1;
+    p.res_stages = stages;
   } else if (p.num_kb >= 2 && p.num_n_tiles <= 8 && sms > 0 && p.num_m_tiles >= 4 * sms && !getenv("LECB_NO_RESIDENT")) {
     const int ring = resident_ring(BN, BK, p.num_kb, nb);
     if (ring >= 3) {
@@ -717,6 +730,7 @@ static int dispatch(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& t
       p.res_stages = ring;
     }
   }
+  if (kConv && nb == 1) return dispatch_nb<kConv, 1>(BN, BK, tmA, tmB, p, s);
   switch (nb) {
     case 8: return dispatch_nb<kConv, 8>(BN, BK, tmA, tmB, p, s);
     case 5: return dispatch_nb<kConv, 5>(BN, BK, tmA, tmB, p, s);
@@ -804,7 +818,7 @@ extern "C" int lecb_conv3x3_bf16(const void* x, const void* w, const float* bias
   // Halo-tile mode for the 64-channel layers (the im2col path re-fetches every input pixel once per tap and those
   // layers are bound by that L2 -> SM fill): pick the patch shape that tiles the image with the least waste.
   const int sms = sm_count();
-  if (Cin == 64 && BN == 64 && p.num_n_tiles == 1 && sms > 0 && !getenv("LECB_NO_HALO")) {
+  if (Cin == 64 && (BN == 64 || BN == 128) && p.num_n_tiles == 1 && sms > 0 && !getenv("LECB_NO_HALO")) {
     int th = 16, tw = 8;
     auto waste = [&](int a, int b) {       // padded / real pixels for an a x b patch
       return static_cast<double>(((H + a - 1) / a) * a) * (((Wd + b - 1) / b) * b) / (static_cast<double>(H) * Wd);

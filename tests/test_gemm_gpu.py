@@ -165,7 +165,8 @@ def test_stem_conv1_tensor_core(b, h, w):
     assert (out.float() - ref.float()).abs().max().item() <= 3e-2 * (ref.float().abs().max().item() + 1e-6)
 
 
-@pytest.mark.parametrize("b,h,w,cout", [(8, 112, 112, 64), (4, 224, 112, 64), (24, 56, 56, 64), (20, 50, 64, 64), (6, 112, 112, 40)])
+@pytest.mark.parametrize("b,h,w,cout", [(8, 112, 112, 64), (4, 224, 112, 64), (24, 56, 56, 64), (20, 50, 64, 64), (6, 112, 112, 40),
+                                        (4, 224, 112, 128), (8, 112, 112, 96)])
 def test_conv3x3_halo_tile_mode(b, h, w, cout):
     """64-channel 3x3 convs run in halo-tile mode (patch tiles, three shifted halo copies per stage, TMA zero-fill as the
     conv padding, 4-D TMA store that clips ragged patches): exact tilings, ragged H, 8x16 and 16x8 patches, Cout < 64."""
