@@ -235,30 +235,44 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int acc = 0;
       uint32_t acc_phase = 0;
       if (p.b_resident && my_tiles > 0) mbar_wait(bres, 0);
+      // halo-tile conv: descriptor pieces that do not change from tile to tile
+      uint32_t halo_off[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      uint64_t halo_a_hi = 0, halo_a0 = 0, halo_b0 = 0;
+      if (kConv && p.halo) {
+        const uint32_t pitch = static_cast<uint32_t>(p.tw + 2) * 128u;       // single-copy variant: halo row pitch
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t ky = tap / 3, kx = tap % 3;
+          halo_off[tap] = (p.halo_single ? ky * pitch + kx * 128u
+                                         : kx * static_cast<uint32_t>(p.copy_bytes) + ky * static_cast<uint32_t>(p.tw) * (BK * 2)) >> 4;
+        }
+        uint64_t d0 = make_kmajor_desc(0, BK * 2);
+        if (p.halo_single) d0 = (d0 & ~(static_cast<uint64_t>(0x3FFF) << 32)) | (static_cast<uint64_t>(pitch >> 4) << 32);
+        halo_a_hi = d0 & 0xFFFFFFFF00000000ull;
+        halo_a0 = d0 & 0xFFFFFFFFull;                 // low word without the address field (LBO bits)
+        halo_b0 = make_kmajor_desc(smem_u32(smem), BK * 2);
+      }
       for (int ti = 0; ti < my_tiles; ++ti) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
         if (kConv && p.halo) {
+          // The nine taps are issued from a fully unrolled sequence: every operand descriptor is the stage's base
+          // descriptor plus a per-tap offset (16-byte units) computed once per CTA.  With N <= 128 an MMA lasts only
+          // 45-64 cycles (smem-read bound, tools/micro/mma_chain.cu), so per-tap address arithmetic on the issuing
+          // thread (ncu: ~250 cycles per tap in a rolled loop) was what bound these layers, not the tensor pipe.
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint8_t* src = sA_ring + stage * (p.halo_single ? 1 : 3) * p.copy_bytes;
-          const uint32_t pitch = static_cast<uint32_t>(p.tw + 2) * 128u;
-#pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
-            const int ky = tap / 3, kx = tap - ky * 3;
-            uint64_t adesc;
-            if (p.halo_single) {
-              adesc = make_kmajor_desc(smem_u32(src + ky * pitch + kx * 128), 128);
-              adesc = (adesc & ~(static_cast<uint64_t>(0x3FFF) << 32)) | (static_cast<uint64_t>(pitch >> 4) << 32);
-            } else {
-              adesc = make_kmajor_desc(smem_u32(src + kx * p.copy_bytes + ky * p.tw * 128), 128);
-            }
-            const uint64_t bdesc = make_kmajor_desc(smem_u32(smem + tap * Cfg::kBBytes), 128);
+          const uint32_t a_lo = static_cast<uint32_t>(halo_a0) + (smem_u32(src) >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                       (tap | k) != 0 ? 1u : 0u);
+          for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t adesc = halo_a_hi | static_cast<uint64_t>(a_lo + halo_off[tap] + 2u * k);
+              const uint64_t bdesc = halo_b0 + static_cast<uint64_t>(tap * (Cfg::kBBytes >> 4) + 2 * k);
+              umma_f16(d_tmem, adesc, bdesc, idesc, (tap | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty[stage]);
           if (++stage == nstages) {
@@ -695,7 +709,7 @@ template <bool kConv>
 static int dispatch(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t s) {
   int nb = 2;
   if (!kConv) {
-    if (p.num_kb <= 2) nb = 8;
+    if (p.num_kb <= 2) nb = getenv("LECB_NB_K2") ? atoi(getenv("LECB_NB_K2")) : 8;
     else if (p.num_kb <= 4) nb = getenv("LECB_NB_K4") ? atoi(getenv("LECB_NB_K4")) : 5;
     else if (p.num_kb <= 8) nb = 4;
     // fp32 output / residual moves twice the bytes per element: keep four blocks in flight up to K = 1024
@@ -711,10 +725,13 @@ static int dispatch(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& t
   const int sms = sm_count();
   if (kConv && p.halo) {                  // halo-tile conv: W resident (9 x BN x 64), stages of three halo copies
     auto stages_with = [&](int nbuf) {
-      const int budget = 227 * 1024 - nbuf * (kTileM * 64 * 2) - 512 - 2048 - 9 * BN * 64 * 2;
+      const int budget = 227 * 1024 - nbuf * (kTileM * (BN >= 64 ? 64 : BN) * 2) - 512 - 2048 - 9 * BN * BK * 2;
       const int st = budget / ((p.halo_single ? 1 : 3) * p.copy_bytes);
       return st > kMaxStages ? kMaxStages : st;
     };
+    // Cin = 32 (stem convs, 64-byte rows): a tile is 24 KB of HBM traffic against ~0.5 us of MMAs, so the output
+    // blocks need the deeper store pipeline more than the halo ring needs a fifth stage
+    if (BK == 32) nb = getenv("LECB_NB_HALO32") ? atoi(getenv("LECB_NB_HALO32")) : 4;
     int stages = stages_with(nb);
     if (stages < 2 && stages_with(1) >= 1) {       // Cout = 128: 144 KB of weights leave room for ONE halo stage and
       nb = 1;                                      // one staging buffer; still ~3x faster than re-fetching per tap
@@ -723,9 +740,9 @@ static int dispatch(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& t
     if (stages < 1) return fail(LECB_ERR_UNSUPPORTED, "halo conv does not fit shared memory (BN=%d copy=%d)", BN, p.copy_bytes);
     p.b_resident = 1;
     p.res_stages = stages;
-  } else if (p.num_kb >= 2 && p.num_n_tiles <= 8 && sms > 0 && p.num_m_tiles >= 4 * sms && !getenv("LECB_NO_RESIDENT")) {
+  } else if (p.num_kb >= (getenv("LECB_RES_K1") ? 1 : 2) && p.num_n_tiles <= 8 && sms > 0 && p.num_m_tiles >= 4 * sms && !getenv("LECB_NO_RESIDENT")) {
     const int ring = resident_ring(BN, BK, p.num_kb, nb);
-    if (ring >= 3) {
+    if (ring >= (getenv("LECB_RING_MIN") ? atoi(getenv("LECB_RING_MIN")) : 3)) {
       p.b_resident = 1;
       p.res_stages = ring;
     }
@@ -733,6 +750,7 @@ static int dispatch(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& t
   if (kConv && nb == 1) return dispatch_nb<kConv, 1>(BN, BK, tmA, tmB, p, s);
   switch (nb) {
     case 8: return dispatch_nb<kConv, 8>(BN, BK, tmA, tmB, p, s);
+    case 6: return dispatch_nb<kConv, 6>(BN, BK, tmA, tmB, p, s);
     case 5: return dispatch_nb<kConv, 5>(BN, BK, tmA, tmB, p, s);
     case 4: return dispatch_nb<kConv, 4>(BN, BK, tmA, tmB, p, s);
     case 3: return dispatch_nb<kConv, 3>(BN, BK, tmA, tmB, p, s);
@@ -768,6 +786,9 @@ extern "C" int lecb_gemm_bf16(const void* A, const void* W, const float* bias, c
       if (e128 > 1.15 * e256) BN = 128;
     }
   }
+  // experiment knob: narrower tiles for the short-K expand convs so the W tile (BN x K) can stay resident next to a
+  // full staging ring
+  if (BN == 256 && K <= 256 && N >= 512 && getenv("LECB_EXPAND_BN128")) BN = 128;
   GemmParams p{};
   p.bias = bias;
   p.residual = residual;
@@ -818,7 +839,7 @@ extern "C" int lecb_conv3x3_bf16(const void* x, const void* w, const float* bias
   // Halo-tile mode for the 64-channel layers (the im2col path re-fetches every input pixel once per tap and those
   // layers are bound by that L2 -> SM fill): pick the patch shape that tiles the image with the least waste.
   const int sms = sm_count();
-  if (Cin == 64 && (BN == 64 || BN == 128) && p.num_n_tiles == 1 && sms > 0 && !getenv("LECB_NO_HALO")) {
+  if ((Cin == 64 || Cin == 32) && BN <= 128 && p.num_n_tiles == 1 && sms > 0 && !getenv("LECB_NO_HALO")) {
     int th = 16, tw = 8;
     auto waste = [&](int a, int b) {       // padded / real pixels for an a x b patch
       return static_cast<double>(((H + a - 1) / a) * a) * (((Wd + b - 1) / b) * b) / (static_cast<double>(H) * Wd);
@@ -835,18 +856,18 @@ extern "C" int lecb_conv3x3_bf16(const void* x, const void* w, const float* bias
       p.tw = tw;
       p.tiles_x = tiles_x;
       p.tiles_y = tiles_y;
-      p.copy_bytes = (th + 2) * tw * 128;
+      p.copy_bytes = (th + 2) * tw * Cin * 2;        // rows of Cin * 2 = 128 (64) bytes, a whole number of swizzle atoms
       p.num_m_tiles = static_cast<int>(tiles);
       p.M = tiles * kTileM;
       // Measured (RN101, layer1 conv2): the single-copy layout moves 2.4x fewer bytes and fits five stages, yet runs
       // 18 % SLOWER than three aligned copies — operand groups that straddle 1024-byte swizzle atoms cost the tensor
       // pipe more than the L2 traffic saved.  Kept behind a switch as the record of that experiment.
-      if (tw == 8 && getenv("LECB_HALO_SINGLE")) {
+      if (tw == 8 && Cin == 64 && getenv("LECB_HALO_SINGLE")) {
         p.halo_single = 1;
         p.copy_bytes = ((th + 2) * (tw + 2) * 128 + 1023) / 1024 * 1024;
         st = encode_tiled_4d_nhwc(&tmA, x, B, H, Wd, Cin, 64, tw + 2, th + 2);
       } else {
-        st = encode_tiled_4d_nhwc(&tmA, x, B, H, Wd, Cin, 64, tw, th + 2);
+        st = encode_tiled_4d_nhwc(&tmA, x, B, H, Wd, Cin, Cin, tw, th + 2);
       }
       if (st) return st;
       return dispatch<true>(BN, BK, tmA, tmB, p, static_cast<cudaStream_t>(stream));

@@ -10,6 +10,8 @@ bias, ReLU / residual-add fused in the epilogue.  Weights are packed once at con
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
@@ -54,7 +56,9 @@ class VisualRN:
         self.layers, self.width, self.heads, self.embed_dim, self.device = tuple(layers), width, heads, embed_dim, device
         w, b = _fold_bn(sd, "visual.conv1.weight", "visual.bn1")
         self.stem1 = (w.permute(1, 2, 3, 0).reshape(27, -1).contiguous(), b)          # fp32 [27,Cout]
-        self.stem_pairs = (width // 2) % 64 != 0          # Ci = 32 stem convs run on the pixel-pair view
+        # Ci = 32 stem convs run directly (halo-tile conv with 64-byte rows, gemm_tcgen05.cu); narrower test towers
+        # (Ci = 16) use the pixel-pair view to reach the kernel's Cin % 32 == 0 granularity
+        self.stem_pairs = ((width // 2) % 32 != 0) or bool(os.environ.get("LECB_STEM_PAIRS"))
         for name, conv, bn in (("stem2", "visual.conv2.weight", "visual.bn2"), ("stem3", "visual.conv3.weight", "visual.bn3")):
             w, b = _fold_bn(sd, conv, bn)
             w = w.permute(0, 2, 3, 1).contiguous()                                    # [Co,3,3,Ci] fp32

@@ -178,3 +178,18 @@ def test_conv3x3_halo_tile_mode(b, h, w, cout):
     torch.cuda.synchronize()
     want = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), bias, padding=1)
     _check(out, want.relu().permute(0, 2, 3, 1), f"halo conv {b}x{h}x{w}->{cout}")
+
+
+@pytest.mark.parametrize("b,h,w,cout", [(4, 224, 224, 32), (4, 224, 224, 64), (9, 112, 96, 64), (16, 50, 64, 32), (6, 112, 112, 40),
+                                        (3, 224, 224, 24)])
+def test_conv3x3_halo_tile_mode_cin32(b, h, w, cout):
+    """The Ci = 32 stem convs (T:385-399 via M:144-151) in halo-tile mode with 64-byte rows (64B swizzle, K step 32,
+    two MMAs per tap): exact tilings, ragged H, both patch shapes, Cout tails."""
+    from lecb200 import ops
+    x = _rand((b, h, w, 32), 61).bfloat16()
+    wt = _rand((cout, 3, 3, 32), 62, (9 * 32) ** -0.5).bfloat16()
+    bias = _rand((cout,), 63, 0.1)
+    out = ops.conv3x3(x, wt, bias, relu=True)
+    torch.cuda.synchronize()
+    want = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), bias, padding=1)
+    _check(out, want.relu().permute(0, 2, 3, 1), f"halo conv cin32 {b}x{h}x{w}->{cout}")
