@@ -84,7 +84,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   uint64_t* o_free = bars + 20;    // softmax warps have read the finished item's O
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
 
   // Persistent CTA: work item w = (image b, head h, query tile qt), w = blockIdx.x + i * gridDim.x.  Every
@@ -130,7 +130,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 
   if (warp == 4) {
     // ------------------------------- TMA producer -------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       int it = 0, kvc = 0;
       for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++it) {
         int q0, h, b, n_sub, n_kv;
@@ -156,7 +156,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     // Sub-block g (running index) uses S/P buffer g & 1; sub-block jj of an item uses the (jj & 1) half of K/V tile
     // kvc + (jj >> 1).  Q K^T of sub-block jj+1 is issued before P V of sub-block jj, so the tensor pipe always runs
     // one S ahead of the softmax warps.
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_qk = attn_idesc(kAtSub, false);
       constexpr uint32_t idesc_pv = attn_idesc(kAtDh, true);
       const uint32_t tO = tmem_base + 128u;

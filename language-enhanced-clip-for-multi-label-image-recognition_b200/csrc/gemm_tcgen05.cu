@@ -108,7 +108,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int nstages = p.b_resident ? p.res_stages : kStages;
   uint8_t* sA_ring = p.b_resident ? smem + p.num_kb * Cfg::kBBytes : sA;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   // Tile schedule.  Default: tile t = blockIdx.x + i * gridDim.x, n fastest.  b_resident: the CTA keeps n tile
@@ -162,7 +162,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == kWarpTma) {
     // ------------------------------- TMA producer -------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       if (p.b_resident && my_tiles > 0) {      // this CTA's whole W tile, once
@@ -228,7 +228,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == kWarpMma) {
     // ------------------------------- MMA issuer ---------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_f16(BN, (p.flags & LECB_GEMM_F16_OPERANDS) == 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -309,7 +309,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == kWarpDma) {
     // ------------------------------- epilogue DMA (staged bf16 output) ----------
-    if (lane == 0 && p.staged) {
+    if (p.staged && elect_one()) {
       const uint32_t cblocks = static_cast<uint32_t>(p.cblocks);
       const int ccols = BN / p.cblocks;
       const uint32_t total = static_cast<uint32_t>(my_tiles) * cblocks;
@@ -350,10 +350,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tma_store_commit();
         // recycle the buffer of the PREVIOUS block (its store had a whole block time to drain) so the lane
         // never stalls on the store it has just issued
-        if (NB == 1) {                    // single staging buffer: it is free again once this store has read it
-          if (g + 1 < total) {
+        if (NB <= 2) {
+          // one or two staging buffers: release THIS block's buffer as soon as its store has read it.  Recycling the
+          // previous block's buffer (below) would hand block g+1 its buffer only after block g is finished, i.e.
+          // serialise the two epilogue groups (ncu on the 64-channel halo convs: 30 % of all samples on this wait)
+          if (g + NB < total) {
             tma_store_wait_read0();
-            make_free(g + 1);
+            make_free(g + NB);
           }
         } else if (g >= 1 && g - 1 + NB < total) {
           tma_store_wait_read1();
