@@ -40,6 +40,8 @@ enum lecb_status {
 #define LECB_EPI_OUT_F32 4u     /* store fp32 instead of bf16                                 */
 #define LECB_EPI_RES_F32 8u     /* `residual` is fp32 [M,N] instead of bf16                   */
 #define LECB_GEMM_F16_OPERANDS 16u /* A and W hold IEEE fp16 instead of bf16 (retrieval, T:445)  */
+#define LECB_EPI_AVGPOOL2 32u   /* lecb_conv3x3_bf16 only: 2x2 average pool after the activation (M:147,177 stem avgpool; */
+                                /* M:27,46 Bottleneck avgpool) fused into the epilogue; out is [B,H/2,W/2,Cout]            */
 
 int lecb_abi_version(void);
 const char* lecb_last_error(void);
@@ -63,6 +65,9 @@ int lecb_gemm_bf16(const void* A, const void* W, const float* bias, const void* 
  * conv2/conv3).  Requirements: Cin % 32 == 0, Cout % 8 == 0. */
 int lecb_conv3x3_bf16(const void* x, const void* w, const float* bias, void* out, int B, int H, int Wd,
                       int Cin, int Cout, unsigned flags, void* stream);
+/* 1 if lecb_conv3x3_bf16 accepts LECB_EPI_AVGPOOL2 for this problem (halo-tile mode: Cin 32 / 64, Cout <= 128,
+ * even H and W, at least two 128-pixel patches per SM), else 0 — the caller then runs lecb_avgpool2x2 itself. */
+int lecb_conv3x3_pool_fusable(int B, int H, int Wd, int Cin, int Cout);
 
 /* ---- stem conv1: 3x3, stride 2, pad 1, 3 -> Cout channels, folded BN + ReLU (M:144-145,174-175) ----
  * x: NCHW fp32 [B,3,H,W] (the reference's input layout, T:401); w: fp32 [27][Cout] with row index

@@ -21,6 +21,7 @@ SIGNATURES = {
                                c_uint, c_void_p]),
     "lecb_conv3x3_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_uint, c_void_p]),
+    "lecb_conv3x3_pool_fusable": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "lecb_stem_conv1": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "lecb_avgpool2x2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "lecb_token_mean": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
@@ -60,7 +61,7 @@ SIGNATURES = {
                                    c_void_p]),
 }
 
-EPI_RELU, EPI_QUICKGELU, EPI_OUT_F32, EPI_RES_F32, GEMM_F16_OPERANDS = 1, 2, 4, 8, 16
+EPI_RELU, EPI_QUICKGELU, EPI_OUT_F32, EPI_RES_F32, GEMM_F16_OPERANDS, EPI_AVGPOOL2 = 1, 2, 4, 8, 16, 32
 
 
 class LecbError(RuntimeError):

@@ -72,6 +72,8 @@ struct GemmParams {
   // (th+2) x tw halo copies (one per horizontal tap, so every tap's A operand is a dense, 1024-byte aligned
   // [128][64] K-major tile at copy[kx] + ky * tw rows): each input pixel crosses L2 -> SM ~3.4x instead of 9x
   int halo, tw, th, tiles_x, tiles_y, copy_bytes, batch;
+  int pool;           // halo mode only: 2x2 average pool (M:147, M:27) fused into the epilogue — the four pixels of a window are
+                      // lanes l, l^1, l^tw, l^tw^1 of one epilogue warp; the staged block is the (th/2 x tw/2) pooled patch
   int halo_single;    // tw == 8: ONE (th+2) x (tw+2) halo copy per stage.  The swizzle of a K-major operand is a function of
                       // the absolute shared-memory address bits (measured: a descriptor may start on any 128-byte row
                       // with base_offset 0), so tap (ky,kx) is just start = copy + (ky*(tw+2) + kx) * 128 with an
@@ -343,7 +345,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int tx = m_blk % p.tiles_x;
           const int ty = (m_blk / p.tiles_x) % p.tiles_y;
           const int img = m_blk / (p.tiles_x * p.tiles_y);
-          tma_store_4d(&tmC, sC + buf * Cfg::kCBytes, n0, tx * p.tw, ty * p.th, img);     // clips ragged tiles
+          if (p.pool) tma_store_4d(&tmC, sC + buf * Cfg::kCBytes, n0, tx * (p.tw >> 1), ty * (p.th >> 1), img);
+          else tma_store_4d(&tmC, sC + buf * Cfg::kCBytes, n0, tx * p.tw, ty * p.th, img);     // clips ragged tiles
         } else {
           tma_store_2d(&tmC, sC + buf * Cfg::kCBytes, n0, m0);
         }
@@ -523,6 +526,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
             }
+            if (kConv && p.pool) {
+              // 2x2 average in fp32 before the bf16 rounding.  Patch row = y * tw + x (tw = 8 or 16), so the window is
+              // lanes {l, l^1, l^tw, l^tw^1}.  Each exchange step sends the half of the columns the lane gives up and
+              // keeps the other half (24 shuffles per 32 columns instead of 64); the lane ends up with 8 of the 32
+              // pooled columns = one 16-byte chunk of the pooled row, so all 32 lanes store.
+              const bool bx = (erow & 1u) != 0, by = (erow & static_cast<uint32_t>(p.tw)) != 0;
+              float s1[16], s2[8];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float send = bx ? v[j] : v[16 + j];
+                const float keep = bx ? v[16 + j] : v[j];
+                s1[j] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float send = by ? s1[j] : s1[8 + j];
+                const float keep = by ? s1[8 + j] : s1[j];
+                s2[j] = 0.25f * (keep + __shfl_xor_sync(0xffffffffu, send, p.tw));
+              }
+              const uint32_t px = erow & static_cast<uint32_t>(p.tw - 1), py = erow / static_cast<uint32_t>(p.tw);
+              const uint32_t wrow = (py >> 1) * static_cast<uint32_t>(p.tw >> 1) + (px >> 1);
+              uint4 u;
+              u.x = pack_bf16(s2[0], s2[1]);
+              u.y = pack_bf16(s2[2], s2[3]);
+              u.z = pack_bf16(s2[4], s2[5]);
+              u.w = pack_bf16(s2[6], s2[7]);
+              *reinterpret_cast<uint4*>(cbuf + swizzled_chunk_offset(wrow, half * 4 + (bx ? 2 : 0) + (by ? 1 : 0), kCCols * 2)) = u;
+              continue;
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               uint4 u;
@@ -646,7 +678,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
   if (p.staged) {
     const uint32_t ccols = p.out_f32 ? 32 : Cfg::kCCols;
     const uint32_t esz = p.out_f32 ? 4 : 2;
-    int st = p.halo ? encode_tiled_4d_nhwc(&tmC, p.out, p.batch, p.H, p.W, p.N, ccols, p.tw, p.th)
+    int st = p.halo ? (p.pool ? encode_tiled_4d_nhwc(&tmC, p.out, p.batch, p.H / 2, p.W / 2, p.N, ccols, p.tw / 2, p.th / 2)
+                              : encode_tiled_4d_nhwc(&tmC, p.out, p.batch, p.H, p.W, p.N, ccols, p.tw, p.th))
                     : encode_tiled_2d_ex(&tmC, p.out, static_cast<uint64_t>(p.M), static_cast<uint64_t>(p.N), kTileM, ccols, esz);
     if (st) return st;
     if (p.residual != nullptr) {
@@ -811,6 +844,37 @@ extern "C" int lecb_gemm_bf16(const void* A, const void* W, const float* bias, c
   return dispatch<false>(BN, BK, tmA, tmB, p, static_cast<cudaStream_t>(stream));
 }
 
+// Halo-tile eligibility and patch shape of a 3x3 conv (see lecb_conv3x3_bf16): Cin 32 / 64 (one K block per tap), one n
+// tile, at least two patches per SM, and a patch shape (16x8 or 8x16) that tiles the image with <= 15 % waste.
+static bool halo_plan(int B, int H, int Wd, int Cin, int BN, int& th, int& tw) {
+  const int sms = sm_count();
+  if (!((Cin == 64 || Cin == 32) && BN <= 128 && sms > 0) || getenv("LECB_NO_HALO")) return false;
+  auto waste = [&](int a, int b) {       // padded / real pixels for an a x b patch
+    return static_cast<double>(((H + a - 1) / a) * a) * (((Wd + b - 1) / b) * b) / (static_cast<double>(H) * Wd);
+  };
+  th = 16;
+  tw = 8;
+  if (waste(8, 16) < waste(16, 8)) {
+    th = 8;
+    tw = 16;
+  }
+  const int64_t tiles = static_cast<int64_t>(B) * ((Wd + tw - 1) / tw) * ((H + th - 1) / th);
+  return tiles >= 2 * sms && tiles < 0x7fffffff && waste(th, tw) <= 1.15;
+}
+
+static void conv_tile_shape(int Cin, int Cout, int& BN, int& BK) {
+  BK = (Cin % 64 == 0) ? 64 : 32;
+  BN = pick_bn(Cout);
+  if (BK == 32 && BN > 64) BN = 64;
+}
+
+extern "C" int lecb_conv3x3_pool_fusable(int B, int H, int Wd, int Cin, int Cout) {
+  if (B <= 0 || H <= 0 || Wd <= 0 || Cin % 32 != 0 || Cout % 8 != 0 || (H & 1) || (Wd & 1)) return 0;
+  int BN, BK, th, tw;
+  conv_tile_shape(Cin, Cout, BN, BK);
+  return ((Cout + BN - 1) / BN == 1 && halo_plan(B, H, Wd, Cin, BN, th, tw)) ? 1 : 0;
+}
+
 extern "C" int lecb_conv3x3_bf16(const void* x, const void* w, const float* bias, void* out, int B, int H, int Wd,
                                  int Cin, int Cout, unsigned flags, void* stream) {
   LECB_CHECK_ARG(x && w && out, "lecb_conv3x3_bf16: null pointer");
@@ -818,10 +882,11 @@ extern "C" int lecb_conv3x3_bf16(const void* x, const void* w, const float* bias
   LECB_CHECK_ARG(Cin % 32 == 0, "lecb_conv3x3_bf16: Cin=%d must be a multiple of 32", Cin);
   LECB_CHECK_ARG(Cout % 8 == 0, "lecb_conv3x3_bf16: Cout=%d must be a multiple of 8", Cout);
   LECB_CHECK_ARG((flags & (LECB_EPI_OUT_F32 | LECB_EPI_RES_F32 | LECB_GEMM_F16_OPERANDS)) == 0,
-                 "lecb_conv3x3_bf16: only LECB_EPI_RELU / LECB_EPI_QUICKGELU are supported");
-  const int BK = (Cin % 64 == 0) ? 64 : 32;
-  int BN = pick_bn(Cout);
-  if (BK == 32 && BN > 64) BN = 64;
+                 "lecb_conv3x3_bf16: only LECB_EPI_RELU / LECB_EPI_QUICKGELU / LECB_EPI_AVGPOOL2 are supported");
+  const bool want_pool = (flags & LECB_EPI_AVGPOOL2) != 0;
+  LECB_CHECK_ARG(!want_pool || (H % 2 == 0 && Wd % 2 == 0), "lecb_conv3x3_bf16: LECB_EPI_AVGPOOL2 needs even H and W (H=%d W=%d)", H, Wd);
+  int BN, BK;
+  conv_tile_shape(Cin, Cout, BN, BK);
   const int64_t M = static_cast<int64_t>(B) * H * Wd;
   GemmParams p{};
   p.bias = bias;
@@ -841,20 +906,13 @@ extern "C" int lecb_conv3x3_bf16(const void* x, const void* w, const float* bias
   if (st) return st;
   // Halo-tile mode for the 64-channel layers (the im2col path re-fetches every input pixel once per tap and those
   // layers are bound by that L2 -> SM fill): pick the patch shape that tiles the image with the least waste.
-  const int sms = sm_count();
-  if ((Cin == 64 || Cin == 32) && BN <= 128 && p.num_n_tiles == 1 && sms > 0 && !getenv("LECB_NO_HALO")) {
-    int th = 16, tw = 8;
-    auto waste = [&](int a, int b) {       // padded / real pixels for an a x b patch
-      return static_cast<double>(((H + a - 1) / a) * a) * (((Wd + b - 1) / b) * b) / (static_cast<double>(H) * Wd);
-    };
-    if (waste(8, 16) < waste(16, 8)) {
-      th = 8;
-      tw = 16;
-    }
+  int th = 0, tw = 0;
+  if (p.num_n_tiles == 1 && halo_plan(B, H, Wd, Cin, BN, th, tw)) {
     const int tiles_x = (Wd + tw - 1) / tw, tiles_y = (H + th - 1) / th;
     const int64_t tiles = static_cast<int64_t>(B) * tiles_x * tiles_y;
-    if (tiles >= 2 * sms && tiles < 0x7fffffff && waste(th, tw) <= 1.15) {
+    {
       p.halo = 1;
+      p.pool = want_pool ? 1 : 0;
       p.th = th;
       p.tw = tw;
       p.tiles_x = tiles_x;
@@ -876,6 +934,9 @@ extern "C" int lecb_conv3x3_bf16(const void* x, const void* w, const float* bias
       return dispatch<true>(BN, BK, tmA, tmB, p, static_cast<cudaStream_t>(stream));
     }
   }
+  if (want_pool)
+    return fail(LECB_ERR_UNSUPPORTED, "lecb_conv3x3_bf16: LECB_EPI_AVGPOOL2 is fused only in halo-tile mode "
+                "(Cin 32/64, one n tile, >= 2 patches per SM); see lecb_conv3x3_pool_fusable()");
   p.M = M;
   p.num_m_tiles = static_cast<int>((M + kTileM - 1) / kTileM);
   st = encode_im2col_3x3(&tmA, x, B, H, Wd, Cin, BK, kTileM);

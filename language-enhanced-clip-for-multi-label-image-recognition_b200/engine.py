@@ -94,9 +94,12 @@ class VisualRN:
         from . import prof
         prof.ALGO_FLOP_SCALE = 0.5 if self.stem_pairs else 1.0     # half of the packed MACs are structural zeros
         x = ops.conv3x3(x, *self.stem2)
-        x = ops.conv3x3(x, *self.stem3)
-        prof.ALGO_FLOP_SCALE = 1.0
-        x = ops.avgpool2x2(x.view(b, h, w, -1))
+        if self.stem_pairs:
+            x = ops.conv3x3(x, *self.stem3)
+            prof.ALGO_FLOP_SCALE = 1.0
+            x = ops.avgpool2x2(x.view(b, h, w, -1))
+        else:
+            x = ops.conv3x3(x, *self.stem3, pool=True)        # M:147 avgpool fused into the conv epilogue when it can be
         for blk in self.blocks:
             x = self._bottleneck(x, blk)
         return x

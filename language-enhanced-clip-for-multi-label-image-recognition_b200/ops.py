@@ -46,8 +46,10 @@ def gemm(a, w, bias=None, residual=None, relu=False, quick_gelu=False, out_f32=F
     return out
 
 
-def conv3x3(x, w, bias=None, relu=True, out=None):
-    """x NHWC bf16 [B,H,W,Cin]; w bf16 [Cout,3,3,Cin] (BN folded); -> NHWC bf16 [B,H,W,Cout]."""
+def conv3x3(x, w, bias=None, relu=True, out=None, pool=False):
+    """x NHWC bf16 [B,H,W,Cin]; w bf16 [Cout,3,3,Cin] (BN folded); -> NHWC bf16 [B,H,W,Cout].
+    pool=True appends the 2x2 average pool that follows the conv in the reference (M:147, M:27): fused into the conv
+    epilogue when the kernel supports it for this shape (lecb_conv3x3_pool_fusable), else a second kernel."""
     _need(x, torch.bfloat16, "x")
     _need(w, torch.bfloat16, "w")
     b, h, wd, cin = x.shape
@@ -55,10 +57,19 @@ def conv3x3(x, w, bias=None, relu=True, out=None):
     assert tuple(w.shape) == (cout, 3, 3, cin), w.shape
     if bias is not None:
         _need(bias, torch.float32, "bias")
-    if out is None:
-        out = torch.empty((b, h, wd, cout), device=x.device, dtype=torch.bfloat16)
-    check(lib.lecb_conv3x3_bf16(_ptr(x), _ptr(w), _ptr(bias), _ptr(out), b, h, wd, cin, cout,
-                                EPI_RELU if relu else 0, _stream()), "lecb_conv3x3_bf16")
+    flags = EPI_RELU if relu else 0
+    fused = bool(pool) and lib.lecb_conv3x3_pool_fusable(b, h, wd, cin, cout) == 1
+    if fused:
+        flags |= _lib.EPI_AVGPOOL2
+        out_shape = (b, h // 2, wd // 2, cout)
+    else:
+        out_shape = (b, h, wd, cout)
+    if out is None or pool:
+        out = torch.empty(out_shape, device=x.device, dtype=torch.bfloat16)
+    check(lib.lecb_conv3x3_bf16(_ptr(x), _ptr(w), _ptr(bias), _ptr(out), b, h, wd, cin, cout, flags, _stream()),
+          "lecb_conv3x3_bf16")
+    if pool and not fused:
+        out = avgpool2x2(out)
     return out
 
 

@@ -19,7 +19,7 @@ def _sig(name, a):
     if name == "lecb_gemm_bf16":
         return f"M={a[6]} N={a[7]} K={a[8]} flags={a[9]} res={int(bool(a[3]))}"
     if name == "lecb_conv3x3_bf16":
-        return f"B={a[4]} H={a[5]} W={a[6]} Cin={a[7]} Cout={a[8]}"
+        return f"B={a[4]} H={a[5]} W={a[6]} Cin={a[7]} Cout={a[8]}" + (" +pool" if a[9] & _lib.EPI_AVGPOOL2 else "")
     if name == "lecb_avgpool2x2":
         return f"B={a[2]} H={a[3]} W={a[4]} C={a[5]}"
     return ""
@@ -34,7 +34,8 @@ def _work(name, a):
         return 2.0 * m * n * k, 2.0 * (m * k + n * k) + m * n * (out_b + res_b)
     if name == "lecb_conv3x3_bf16":
         b, h, w, ci, co = a[4], a[5], a[6], a[7], a[8]
-        return 2.0 * b * h * w * co * 9 * ci * ALGO_FLOP_SCALE, 2.0 * (b * h * w * (ci + co) + 9 * ci * co)
+        out_px = b * h * w / (4.0 if a[9] & _lib.EPI_AVGPOOL2 else 1.0)      # fused 2x2 average pool writes a quarter
+        return 2.0 * b * h * w * co * 9 * ci * ALGO_FLOP_SCALE, 2.0 * (b * h * w * ci + out_px * co + 9 * ci * co)
     if name == "lecb_avgpool2x2":
         b, h, w, c = a[2], a[3], a[4], a[5]
         return 1.0 * b * h * w * c, 2.0 * b * h * w * c * 1.25

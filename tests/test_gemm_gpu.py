@@ -193,3 +193,23 @@ def test_conv3x3_halo_tile_mode_cin32(b, h, w, cout):
     torch.cuda.synchronize()
     want = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), bias, padding=1)
     _check(out, want.relu().permute(0, 2, 3, 1), f"halo conv cin32 {b}x{h}x{w}->{cout}")
+
+
+@pytest.mark.parametrize("b,h,w,cin,cout", [(4, 224, 224, 32, 64), (9, 112, 96, 32, 32), (8, 112, 112, 64, 64), (4, 224, 112, 64, 128),
+                                            (20, 50, 64, 64, 64), (6, 112, 112, 32, 40), (2, 8, 8, 64, 64), (2, 56, 56, 128, 128)])
+def test_conv3x3_fused_avgpool(b, h, w, cin, cout):
+    """conv3x3 + ReLU + 2x2 average pool (M:147 stem avgpool, M:27/46 Bottleneck avgpool): fused epilogue in halo-tile
+    mode (both patch shapes, ragged H, Cout tail, two-block tiles), two kernels elsewhere (last two shapes); the pooled
+    fp32 reference is rounded to bf16 once."""
+    from lecb200 import _lib, ops
+    x = _rand((b, h, w, cin), 71).bfloat16()
+    wt = _rand((cout, 3, 3, cin), 72, (9 * cin) ** -0.5).bfloat16()
+    bias = _rand((cout,), 73, 0.1)
+    out = ops.conv3x3(x, wt, bias, relu=True, pool=True)
+    torch.cuda.synchronize()
+    assert tuple(out.shape) == (b, h // 2, w // 2, cout)
+    fus = _lib.lib.lecb_conv3x3_pool_fusable(b, h, w, cin, cout)
+    assert fus == (1 if (cin <= 64 and b * h * w >= 128 * 2 * 148) else 0)
+    want = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), bias, padding=1).relu()
+    want = torch.nn.functional.avg_pool2d(want, 2).permute(0, 2, 3, 1)
+    _check(out, want, f"conv+pool {b}x{h}x{w} {cin}->{cout}")

@@ -1,4 +1,4 @@
-"""Summarise where the warp roles of a warp-specialised kernel wait: python tools/ncu_waits.py report.ncu-rep
+"""Summarise where the warp roles of a warp-specialised kernel wait: python tools/ncu_waits.py report.ncu-rep [launch index]
 Prints every mbarrier try-wait / async-op SASS instruction with its stall samples (next instruction included)."""
 import csv
 import io
@@ -6,10 +6,15 @@ import subprocess
 import sys
 
 rep = sys.argv[1]
+which = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
-h = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
-hdr, data = rows[h], rows[h + 1:]
+heads = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+h = heads[which]
+end = heads[which + 1] - 1 if which + 1 < len(heads) else len(rows)
+hdr = rows[h]
+data = [r for r in rows[h + 1:end] if len(r) == len(hdr)]
+rows = rows[h - 1:]
 isrc, isamp, iex = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
 tot = sum(int(r[isamp] or 0) for r in data)
 print(rows[0][1][:120], "total samples", tot)
