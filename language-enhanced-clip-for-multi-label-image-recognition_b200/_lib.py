@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "liblecb.so")
+LIB_PATH = os.environ.get("LECB_LIB_PATH") or os.path.join(_HERE, "csrc", "liblecb.so")   # override: A/B runs of two builds
 
 c_void_p, c_int, c_i64, c_uint, c_float = C.c_void_p, C.c_int, C.c_int64, C.c_uint, C.c_float
 

@@ -16,10 +16,11 @@
 // TMA-stores it — every HBM access of the epilogue is a full-line bulk transfer, overlapped with the
 // next tile's MMAs.  fp32 outputs (small / final GEMMs) use direct vector stores instead.
 //
-// Roles (352 threads): warps 0-7 epilogue in two groups of four (TMEM lane quarter = warp id % 4; the
-// groups take alternate 64-column blocks so two blocks are always in flight per SM), warp 8 TMA producer,
-// warp 9 MMA issuer + TMEM owner, warp 10 epilogue DMA.  mbarrier rings: smem full/empty (operands),
-// TMEM full/empty (accumulators), staging free/full (epilogue blocks).
+// Roles (32 * (kEpiWarps + 3) = 352 threads): warps 0-7 epilogue in groups of four (TMEM lane quarter = warp id % 4;
+// staged blocks are dealt round-robin to the groups, so two blocks are in flight per SM), warp 8 TMA producer, warp 9
+// MMA issuer + TMEM owner, warp 10 epilogue DMA.  Single-thread roles run on one elected lane (elect.sync) so their
+// code stays on the uniform datapath.  mbarrier rings: smem full/empty (operands), TMEM full/empty (accumulators),
+// staging free/full (epilogue blocks).
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -29,8 +30,15 @@
 namespace lecb {
 
 constexpr int kTileM = 128;
-constexpr int kNumThreads = 352;
-constexpr int kWarpTma = 8, kWarpMma = 9, kWarpDma = 10;
+constexpr int kEpiWarps = 8;                       // groups of four (a warp reads TMEM lane quarter warp % 4).  Measured with
+                                                   // 12: no faster on the short-K residual GEMMs and 3-20 % slower on the convs
+                                                   // (the 128-register cap of 480 threads costs more than the third group hides)
+constexpr int kGroups = kEpiWarps / 4;
+constexpr int kTFull = (kGroups % 2 == 0) ? kGroups : 2 * kGroups;
+constexpr int kNumThreads = 32 * (kEpiWarps + 3);
+constexpr int kWarpTma = kEpiWarps, kWarpMma = kEpiWarps + 1, kWarpDma = kEpiWarps + 2;
+constexpr int kBiasBytes = 2048;                   // [2][256] floats: a tile's bias slice, double-buffered by tile parity
+constexpr int kBarBytes = 512;
 constexpr int kMaxStages = 8;
 
 template <int BN, int BK, int NB>
@@ -41,10 +49,10 @@ struct GemmCfg {
   static constexpr int kCCols = BN >= 64 ? 64 : BN;               // columns per staged epilogue block
   static constexpr int kCBlocks = BN / kCCols;
   static constexpr int kCBytes = kTileM * kCCols * 2;             // 16 KB (8 KB for BN = 32)
-  static constexpr int kStagesRaw = (227 * 1024 - NB * kCBytes - 2560) / kStageBytes;
+  static constexpr int kStagesRaw = (227 * 1024 - NB * kCBytes - kBarBytes - kBiasBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = (2 * BN) < 32 ? 32 : (2 * BN);
-  static constexpr int kSmemBytes = kStages * kStageBytes + NB * kCBytes + 512 /*barriers*/ + 2048 /*bias, 2 tiles*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + NB * kCBytes + kBarBytes + kBiasBytes;
   static_assert(kStages >= 2, "need at least a double-buffered operand ring");
 };
 
@@ -95,17 +103,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* bars = reinterpret_cast<uint64_t*>(sC + NB * Cfg::kCBytes);
   uint64_t* full = bars;                       // [kMaxStages] (the resident-W mode may run a deeper A ring)
   uint64_t* empty = bars + kMaxStages;
+  // tfull: one barrier per (tile mod kTFull), kTFull = lcm(2 accumulators, kGroups): successive phases of one barrier
+  // then belong to the same accumulator AND the same owner groups, so every waiter sees every phase of the barriers it
+  // waits on (a group that skipped phases, or lagged two behind, would alias on the phase parity)
   uint64_t* tfull = bars + 2 * kMaxStages;
-  uint64_t* tempty = tfull + 2;
+  uint64_t* tempty = tfull + kTFull;
   // staging barriers: one (free, full) pair per buffer — but never fewer than two pairs: with a single buffer the two
   // epilogue groups would share one barrier and a group could be two phases ahead of it (parity aliasing), so the
   // barrier index (block % kNBar) is decoupled from the buffer index (block % NB)
-  constexpr int kNBar = NB < 2 ? 2 : NB;
+  constexpr int kNBar = NB < kGroups ? kGroups : NB;
   uint64_t* cfree = tempty + 2;
   uint64_t* cfull = cfree + kNBar;
   uint64_t* bres = cfull + kNBar;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres + 1);
-  float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);      // [2][256]: bias slice of a tile
+  float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);      // [2][256]: bias slice of a tile
   // b_resident: [ W k-blocks (num_kb * kBBytes) | A ring (res_stages * kABytes) ] inside the operand region
   const int nstages = p.b_resident ? p.res_stages : kStages;
   uint8_t* sA_ring = p.b_resident ? smem + p.num_kb * Cfg::kBBytes : sA;
@@ -140,11 +151,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
+    for (int i = 0; i < kTFull; ++i) mbar_init(&tfull[i], 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull[i], 1);
       // staged path: both epilogue groups read every accumulator (8 warps) unless a tile is a single block,
       // in which case the groups alternate tiles (4 warps); direct fp32 path: group 0 only
-      mbar_init(&tempty[i], (p.staged && p.cblocks > 1) ? 8 : 4);
+      mbar_init(&tempty[i], p.staged ? 4 * p.cblocks : 4);
     }
     for (int i = 0; i < kNBar; ++i) {
       mbar_init(&cfree[i], 1);
@@ -281,7 +292,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             stage = 0;
             phase ^= 1;
           }
-          umma_commit(&tfull[acc]);
+          umma_commit(&tfull[ti % kTFull]);
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
           continue;
@@ -304,7 +315,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[acc]);
+        umma_commit(&tfull[ti % kTFull]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -369,19 +380,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tma_store_wait_all();
     }
   } else {
-    // ------------------------------- epilogue (warps 0-7) -----------------------
-    const int group = warp >> 2;                 // 0 or 1
+    // ------------------------------- epilogue (warps 0 .. kEpiWarps-1) ----------
+    const int group = warp >> 2;                 // 0 .. kGroups-1
     const int quarter = warp & 3;                // TMEM lane quarter this warp may read
     const bool relu = p.flags & LECB_EPI_RELU;
     const bool gelu = p.flags & LECB_EPI_QUICKGELU;
     const bool res_f32 = p.flags & LECB_EPI_RES_F32;
     const uint32_t erow = static_cast<uint32_t>(quarter * 32 + lane);   // row inside the tile == TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    int bias_n_blk = -1;
     for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq) {
       int m_blk, n_blk;
       tile_coords(tile_seq, m_blk, n_blk);
       const int acc = tile_seq & 1;
-      const uint32_t acc_phase = (tile_seq >> 1) & 1;
+      const uint32_t tf_phase = static_cast<uint32_t>(tile_seq / kTFull) & 1u;
       const int64_t row = static_cast<int64_t>(m_blk) * kTileM + erow;
       const bool row_ok = row < p.M;
       float ssq = 0.f;
@@ -389,64 +401,69 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // no L1 left, so per-block __ldg of the bias cost an exposed L2 round trip per 64 columns (measured: -20 % on
       // K = 768 GEMMs).  One element per epilogue thread, requested before the accumulator wait; double-buffered by
       // tile parity (the named barrier of tile i+1 orders every reader of tile i-1's slice before its overwrite).
-      // Narrow tiles (BN <= 64, where the two epilogue groups alternate tiles) use a private 64-float slice per warp
-      // and need no cross-warp barrier.
-      const float* sb = BN <= 64 ? sbias + warp * 64 : sbias + acc * 256;
+      // Narrow tiles (BN <= 64) keep ONE slice that is reloaded only when the n tile changes (every epilogue warp walks
+      // the same tile sequence, so the reload and its two barriers are warp-uniform; with a single n tile — the halo
+      // convs, N <= 64 GEMMs — it happens once per CTA).
+      const float* sb = BN <= 64 ? sbias : sbias + acc * 256;
       if (p.bias != nullptr) {
         if (BN <= 64) {
-          __syncwarp();                                       // the warp's previous tile is done with its slice
-#pragma unroll
-          for (int c = lane; c < BN; c += 32) {
-            const int col = n_blk * BN + c;
-            sbias[warp * 64 + c] = col < p.N ? __ldg(p.bias + col) : 0.f;
+          if (n_blk != bias_n_blk) {
+            bias_n_blk = n_blk;
+            const int tid = static_cast<int>(threadIdx.x);
+            const int col = n_blk * BN + tid;
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");      // everyone is done with the old slice
+            if (tid < BN) sbias[tid] = col < p.N ? __ldg(p.bias + col) : 0.f;
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
           }
-          __syncwarp();
         } else {
-          const int tid = static_cast<int>(threadIdx.x);      // 0..255: the eight epilogue warps
+          const int tid = static_cast<int>(threadIdx.x);      // 0..383: the epilogue warps
           const int col = n_blk * BN + tid;
           if (tid < BN) sbias[acc * 256 + tid] = col < p.N ? __ldg(p.bias + col) : 0.f;
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
         }
       }
       if (p.staged && p.out_f32) {
         // fp32 output (+ fp32 residual): 32-column blocks (128-byte rows), same buffer ring and DMA protocol
         const int cblocks = p.cblocks;
+        // block g = tile_seq * cblocks + cb belongs to group g % kGroups
         const uint32_t g0 = static_cast<uint32_t>(tile_seq) * cblocks;
-        int cb_first = (cblocks > 1) ? group : (((g0 & 1) == static_cast<uint32_t>(group)) ? 0 : cblocks);
+        const int cb_first = (group + kGroups - static_cast<int>(g0 % kGroups)) % kGroups;
         if (cb_first >= cblocks) continue;
-        mbar_wait(&tfull[acc], acc_phase);
+        mbar_wait(&tfull[tile_seq % kTFull], tf_phase);
         tc_fence_after();
 #pragma unroll 1
-        for (int cb = cb_first; cb < cblocks; cb += 2) {
+        for (int cb = cb_first; cb < cblocks; cb += kGroups) {
           const uint32_t gblk = g0 + cb;
           const int buf = gblk % NB;
           uint8_t* cbuf = sC + buf * Cfg::kCBytes;
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + lane_base + static_cast<uint32_t>(acc * BN + cb * 32), r);
           tmem_ld_wait();
-          if (cb + 2 >= cblocks) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-          }
+          tc_fence_before();                     // tempty counts one arrival per (block, warp)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
           mbar_wait(&cfree[gblk % kNBar], (gblk / kNBar) & 1);
           const int n0 = n_blk * BN + cb * 32;
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias != nullptr) {
+          if (p.bias != nullptr) {              // packed FADD2: see the bf16 path below
             const float4* bp = reinterpret_cast<const float4*>(sb + (n0 - n_blk * BN));
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 b = bp[j / 4];
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              const float2 lo = fadd2(make_float2(v[j], v[j + 1]), make_float2(b.x, b.y));
+              const float2 hi = fadd2(make_float2(v[j + 2], v[j + 3]), make_float2(b.z, b.w));
+              v[j] = lo.x; v[j + 1] = lo.y; v[j + 2] = hi.x; v[j + 3] = hi.y;
             }
           }
           if (p.residual != nullptr) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const float4 f = *reinterpret_cast<const float4*>(cbuf + swizzled_chunk_offset(erow, q, 128));
-              v[q * 4 + 0] += f.x; v[q * 4 + 1] += f.y; v[q * 4 + 2] += f.z; v[q * 4 + 3] += f.w;
+              const float2 lo = fadd2(make_float2(v[q * 4], v[q * 4 + 1]), make_float2(f.x, f.y));
+              const float2 hi = fadd2(make_float2(v[q * 4 + 2], v[q * 4 + 3]), make_float2(f.z, f.w));
+              v[q * 4] = lo.x; v[q * 4 + 1] = lo.y; v[q * 4 + 2] = hi.x; v[q * 4 + 3] = hi.y;
             }
           }
           if (relu) {
@@ -470,14 +487,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (lane == 0) mbar_arrive(&cfull[gblk % kNBar]);
         }
       } else if (p.staged) {
-        // block g = tile_seq * kCBlocks + cb belongs to group g % 2
         const uint32_t g0 = static_cast<uint32_t>(tile_seq) * kCBlocks;
-        int cb_first = (kCBlocks > 1) ? group : (((g0 & 1) == static_cast<uint32_t>(group)) ? 0 : kCBlocks);
-        if (cb_first >= kCBlocks) continue;       // single-block tile owned by the other group
-        mbar_wait(&tfull[acc], acc_phase);
+        const int cb_first = (group + kGroups - static_cast<int>(g0 % kGroups)) % kGroups;
+        if (cb_first >= kCBlocks) continue;       // no block of this tile belongs to this group
+        mbar_wait(&tfull[tile_seq % kTFull], tf_phase);
         tc_fence_after();
 #pragma unroll 1
-        for (int cb = cb_first; cb < kCBlocks; cb += 2) {
+        for (int cb = cb_first; cb < kCBlocks; cb += kGroups) {
           const uint32_t gblk = g0 + cb;
           const int buf = gblk % NB;
           uint8_t* cbuf = sC + buf * Cfg::kCBytes;
@@ -487,11 +503,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int half = 0; half < kCCols / 32; ++half)
             tmem_ld_32x32(tmem_base + lane_base + static_cast<uint32_t>(acc * BN + cb * kCCols + half * 32), r[half]);
           tmem_ld_wait();
-          if (cb + 2 >= kCBlocks) {      // last TMEM read of this accumulator by this warp: hand it back early
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-          }
+          tc_fence_before();             // the block is in registers: hand its share of the accumulator back
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
           mbar_wait(&cfree[gblk % kNBar], (gblk / kNBar) & 1);
 #pragma unroll
           for (int half = 0; half < kCCols / 32; ++half) {
@@ -589,7 +603,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       } else {
         if (group != 0) continue;                 // direct fp32 stores: one group is plenty (small GEMMs)
-        mbar_wait(&tfull[acc], acc_phase);
+        mbar_wait(&tfull[tile_seq % kTFull], tf_phase);
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
@@ -709,7 +723,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
   int grid = tiles < sms ? tiles : sms;
   if (p.b_resident) {                     // planned by dispatch(): W tile + A ring + NB staging buffers fit
     p.operand_bytes = p.num_kb * Cfg::kBBytes + p.res_stages * (p.halo ? (p.halo_single ? 1 : 3) * p.copy_bytes : Cfg::kABytes);
-    smem_bytes = p.operand_bytes + NB * Cfg::kCBytes + 512 + 2048;
+    smem_bytes = p.operand_bytes + NB * Cfg::kCBytes + kBarBytes + kBiasBytes;
     grid = (sms / p.num_n_tiles) * p.num_n_tiles;
   }
   kern<<<grid, kNumThreads, smem_bytes, stream>>>(tmA, tmB, tmC, tmR, p);
@@ -745,7 +759,7 @@ static int dispatch_nb(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap
 // A ring depth the resident-W mode would get with `nb` staging buffers (0 = does not fit).
 static int resident_ring(int BN, int BK, int num_kb, int nb) {
   const int ccols = BN >= 64 ? 64 : BN;
-  const int budget = 227 * 1024 - nb * (kTileM * ccols * 2) - 512 - 2048;
+  const int budget = 227 * 1024 - nb * (kTileM * ccols * 2) - kBarBytes - kBiasBytes;
   const int wbytes = num_kb * BN * BK * 2;
   if (wbytes > 128 * 1024) return 0;
   int ring = (budget - wbytes) / (kTileM * BK * 2);
@@ -772,7 +786,7 @@ static int dispatch(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& t
   const int sms = sm_count();
   if (kConv && p.halo) {                  // halo-tile conv: W resident (9 x BN x 64), stages of three halo copies
     auto stages_with = [&](int nbuf) {
-      const int budget = 227 * 1024 - nbuf * (kTileM * (BN >= 64 ? 64 : BN) * 2) - 512 - 2048 - 9 * BN * BK * 2;
+      const int budget = 227 * 1024 - nbuf * (kTileM * (BN >= 64 ? 64 : BN) * 2) - kBarBytes - kBiasBytes - 9 * BN * BK * 2;
       const int st = budget / ((p.halo_single ? 1 : 3) * p.copy_bytes);
       return st > kMaxStages ? kMaxStages : st;
     };

@@ -262,8 +262,6 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
-// x * sigmoid(1.702 x) (M:202-204) with two MUFU ops (ex2 + rcp) and no IEEE-division slow path; both
-// approximations are good to ~2 ulp of fp32, far below the bf16 rounding of every consumer.
 // Packed fp32 add (FADD2: two lanes per issue slot) and ReLU on a packed bf16 pair (HMNMX2): the epilogues of the
 // HBM-bound GEMMs are issue-bound on the eight epilogue warps, so instruction count per output element matters.
 __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
@@ -284,6 +282,8 @@ __device__ __forceinline__ uint32_t relu_bf16x2(uint32_t a) {
   asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(0u));
   return d;
 }
+// x * sigmoid(1.702 x) (M:202-204) with two MUFU ops (ex2 + rcp) and no IEEE-division slow path; both
+// approximations are good to ~2 ulp of fp32, far below the bf16 rounding of every consumer.
 __device__ __forceinline__ float quick_gelu(float x) {
   float e, r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.702f * 1.4426950408889634f * x));
