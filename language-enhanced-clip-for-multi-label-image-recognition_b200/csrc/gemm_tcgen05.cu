@@ -80,6 +80,9 @@ struct GemmParams {
   // (th+2) x tw halo copies (one per horizontal tap, so every tap's A operand is a dense, 1024-byte aligned
   // [128][64] K-major tile at copy[kx] + ky * tw rows): each input pixel crosses L2 -> SM ~3.4x instead of 9x
   int halo, tw, th, tiles_x, tiles_y, copy_bytes, batch;
+  int mt;             // 1, or 2 = paired m tiles (BN <= 128, im2col convs): a stage holds TWO A tiles and one W tile, the W
+                      // tile feeds two accumulators (four 128-column accumulators, still double-buffered), so W crosses
+                      // L2 -> SM once per 256 pixels; the epilogue / DMA still see a sequence of 128-row tiles
   int pool;           // halo mode only: 2x2 average pool (M:147, M:27) fused into the epilogue — the four pixels of a window are
                       // lanes l, l^1, l^tw, l^tw^1 of one epilogue warp; the staged block is the (th/2 x tw/2) pooled patch
   int halo_single;    // tw == 8: ONE (th+2) x (tw+2) halo copy per stage.  The swizzle of a K-major operand is a function of
@@ -97,8 +100,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr int kCCols = Cfg::kCCols;
   constexpr int kCBlocks = Cfg::kCBlocks;
   extern __shared__ __align__(1024) uint8_t smem[];     // swizzled tiles need 1024-byte alignment (checked below)
+  const int nstages = (p.b_resident || p.mt == 2) ? p.res_stages : kStages;
+  const int a_stride = p.mt * Cfg::kABytes;            // bytes of A per stage
   uint8_t* sA = smem;
-  uint8_t* sB = smem + kStages * Cfg::kABytes;
+  uint8_t* sB = smem + nstages * a_stride;
   uint8_t* sC = smem + p.operand_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sC + NB * Cfg::kCBytes);
   uint64_t* full = bars;                       // [kMaxStages] (the resident-W mode may run a deeper A ring)
@@ -112,30 +117,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   // epilogue groups would share one barrier and a group could be two phases ahead of it (parity aliasing), so the
   // barrier index (block % kNBar) is decoupled from the buffer index (block % NB)
   constexpr int kNBar = NB < kGroups ? kGroups : NB;
-  uint64_t* cfree = tempty + 2;
+  uint64_t* cfree = tempty + 4;                // tempty[4]: one per accumulator (two are used unless mt == 2)
   uint64_t* cfull = cfree + kNBar;
   uint64_t* bres = cfull + kNBar;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres + 1);
   float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);      // [2][256]: bias slice of a tile
   // b_resident: [ W k-blocks (num_kb * kBBytes) | A ring (res_stages * kABytes) ] inside the operand region
-  const int nstages = p.b_resident ? p.res_stages : kStages;
   uint8_t* sA_ring = p.b_resident ? smem + p.num_kb * Cfg::kBBytes : sA;
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  // mt == 2: the schedule below runs over PAIRS of m tiles (num_m_tiles is even); sub-tile i belongs to pair i >> 1
+  const int num_tiles = (p.num_m_tiles / p.mt) * p.num_n_tiles;
   // Tile schedule.  Default: tile t = blockIdx.x + i * gridDim.x, n fastest.  b_resident: the CTA keeps n tile
   // blockIdx.x % num_n_tiles and walks m tiles blockIdx.x / num_n_tiles + i * (gridDim.x / num_n_tiles).
   const int res_n = p.b_resident ? static_cast<int>(blockIdx.x) % p.num_n_tiles : 0;
   const int res_m0 = p.b_resident ? static_cast<int>(blockIdx.x) / p.num_n_tiles : 0;
   const int res_ms = p.b_resident ? static_cast<int>(gridDim.x) / p.num_n_tiles : 1;
-  const int my_tiles = p.b_resident
+  const int my_tiles = p.mt * (p.b_resident
                            ? (res_m0 < p.num_m_tiles ? (p.num_m_tiles - res_m0 + res_ms - 1) / res_ms : 0)
-                           : (static_cast<int>(blockIdx.x) < num_tiles ? (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0);
+                           : (static_cast<int>(blockIdx.x) < num_tiles ? (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0));
   auto tile_coords = [&](int i, int& m_blk, int& n_blk) {
     if (p.b_resident) {
       m_blk = res_m0 + i * res_ms;
       n_blk = res_n;
+    } else if (p.mt == 2) {
+      const int tile = static_cast<int>(blockIdx.x) + (i >> 1) * static_cast<int>(gridDim.x);
+      const int mp = tile / p.num_n_tiles;
+      n_blk = tile - mp * p.num_n_tiles;
+      m_blk = 2 * mp + (i & 1);
     } else {
       const int tile = static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x);
       m_blk = tile / p.num_n_tiles;
@@ -152,7 +162,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < kTFull; ++i) mbar_init(&tfull[i], 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       // staged path: both epilogue groups read every accumulator (8 warps) unless a tile is a single block,
       // in which case the groups alternate tiles (4 warps); direct fp32 path: group 0 only
       mbar_init(&tempty[i], p.staged ? 4 * p.cblocks : 4);
@@ -165,7 +175,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     fence_barrier_init();
   }
   if (warp == kWarpMma) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_alloc(tmem_slot, static_cast<uint32_t>(p.mt * Cfg::kTmemCols));
     tmem_relinquish();
   }
   tc_fence_before();
@@ -182,10 +192,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         mbar_arrive_expect_tx(bres, static_cast<uint32_t>(p.num_kb) * Cfg::kBBytes);
         for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(&tmB, bres, smem + kb * Cfg::kBBytes, kb * BK, res_n * BN);
       }
-      for (int ti = 0; ti < my_tiles; ++ti) {
+      for (int ti = 0; ti < my_tiles; ti += p.mt) {
         int m_blk, n_blk;
         tile_coords(ti, m_blk, n_blk);
-        int pw = 0, ph = 0, pn = 0;
+        int pw[2] = {0, 0}, ph[2] = {0, 0}, pn[2] = {0, 0};
         if (kConv && p.halo) {
           const int tx = m_blk % p.tiles_x;
           const int ty = (m_blk / p.tiles_x) % p.tiles_y;
@@ -212,24 +222,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           continue;
         }
         if (kConv) {
-          const int64_t m0 = static_cast<int64_t>(m_blk) * kTileM;
-          const int hw = p.H * p.W;
-          pn = static_cast<int>(m0 / hw);
-          const int rem = static_cast<int>(m0 - static_cast<int64_t>(pn) * hw);
-          ph = rem / p.W;
-          pw = rem - ph * p.W;
+          for (int sub = 0; sub < p.mt; ++sub) {
+            const int64_t m0 = static_cast<int64_t>(m_blk + sub) * kTileM;
+            const int hw = p.H * p.W;
+            pn[sub] = static_cast<int>(m0 / hw);
+            const int rem = static_cast<int>(m0 - static_cast<int64_t>(pn[sub]) * hw);
+            ph[sub] = rem / p.W;
+            pw[sub] = rem - ph[sub] * p.W;
+          }
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], p.b_resident ? Cfg::kABytes : Cfg::kStageBytes);
+          mbar_arrive_expect_tx(&full[stage], p.b_resident ? Cfg::kABytes : p.mt * Cfg::kABytes + Cfg::kBBytes);
           if (kConv) {
             const int tap = kb / p.kb_per_tap;
             const int cb = kb - tap * p.kb_per_tap;
             const int ky = tap / 3, kx = tap - ky * 3;
-            tma_load_im2col_4d(&tmA, &full[stage], sA_ring + stage * Cfg::kABytes, cb * BK, pw - 1, ph - 1, pn,
-                               static_cast<uint16_t>(kx), static_cast<uint16_t>(ky));
+            for (int sub = 0; sub < p.mt; ++sub)
+              tma_load_im2col_4d(&tmA, &full[stage], sA_ring + stage * a_stride + sub * Cfg::kABytes, cb * BK, pw[sub] - 1,
+                                 ph[sub] - 1, pn[sub], static_cast<uint16_t>(kx), static_cast<uint16_t>(ky));
           } else {
-            tma_load_2d(&tmA, &full[stage], sA_ring + stage * Cfg::kABytes, kb * BK, m_blk * kTileM);
+            tma_load_2d(&tmA, &full[stage], sA_ring + stage * a_stride, kb * BK, m_blk * kTileM);
           }
           if (!p.b_resident) tma_load_2d(&tmB, &full[stage], sB + stage * Cfg::kBBytes, kb * BK, n_blk * BN);
           if (++stage == nstages) {
@@ -245,8 +258,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t idesc = make_idesc_f16(BN, (p.flags & LECB_GEMM_F16_OPERANDS) == 0);
       int stage = 0;
       uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
+      const int nacc = 2 * p.mt;               // accumulators: sub-tile t lives in accumulator t % nacc
       if (p.b_resident && my_tiles > 0) mbar_wait(bres, 0);
       // halo-tile conv: descriptor pieces that do not change from tile to tile
       uint32_t halo_off[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -265,10 +277,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         halo_a0 = d0 & 0xFFFFFFFFull;                 // low word without the address field (LBO bits)
         halo_b0 = make_kmajor_desc(smem_u32(smem), BK * 2);
       }
-      for (int ti = 0; ti < my_tiles; ++ti) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
+      for (int ti = 0; ti < my_tiles; ti += p.mt) {
+        for (int sub = 0; sub < p.mt; ++sub) {
+          const int t = ti + sub;
+          mbar_wait(&tempty[t & (nacc - 1)], ((static_cast<uint32_t>(t / nacc) & 1u) ^ 1u));
+        }
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((ti & (nacc - 1)) * BN);
         if (kConv && p.halo) {
           // The nine taps are issued from a fully unrolled sequence: every operand descriptor is the stage's base
           // descriptor plus a per-tap offset (16-byte units) computed once per CTA.  With N <= 128 an MMA lasts only
@@ -293,14 +308,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             phase ^= 1;
           }
           umma_commit(&tfull[ti % kTFull]);
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1;
           continue;
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint64_t adesc = make_kmajor_desc(smem_u32(sA_ring + stage * Cfg::kABytes), BK * 2);
+          const uint64_t adesc = make_kmajor_desc(smem_u32(sA_ring + stage * a_stride), BK * 2);
           const uint64_t bdesc = make_kmajor_desc(
               smem_u32(p.b_resident ? smem + kb * Cfg::kBBytes : sB + stage * Cfg::kBBytes), BK * 2);
 #pragma unroll
@@ -309,6 +322,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             umma_f16(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
                      (kb | k) != 0 ? 1u : 0u);
           }
+          if (p.mt == 2) {                     // second m tile of the pair: next A tile of the stage, next accumulator
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_f16(d_tmem + BN, adesc + static_cast<uint64_t>((Cfg::kABytes >> 4) + 2 * k),
+                       bdesc + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
           umma_commit(&empty[stage]);
           if (++stage == nstages) {
             stage = 0;
@@ -316,8 +335,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
         umma_commit(&tfull[ti % kTFull]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (p.mt == 2) umma_commit(&tfull[(ti + 1) % kTFull]);
       }
     }
   } else if (warp == kWarpDma) {
@@ -392,7 +410,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq) {
       int m_blk, n_blk;
       tile_coords(tile_seq, m_blk, n_blk);
-      const int acc = tile_seq & 1;
+      const int acc = tile_seq & (2 * p.mt - 1);        // accumulator of this (sub-)tile
+      const int par = tile_seq & 1;                     // bias slice parity
       const uint32_t tf_phase = static_cast<uint32_t>(tile_seq / kTFull) & 1u;
       const int64_t row = static_cast<int64_t>(m_blk) * kTileM + erow;
       const bool row_ok = row < p.M;
@@ -404,7 +423,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // Narrow tiles (BN <= 64) keep ONE slice that is reloaded only when the n tile changes (every epilogue warp walks
       // the same tile sequence, so the reload and its two barriers are warp-uniform; with a single n tile — the halo
       // convs, N <= 64 GEMMs — it happens once per CTA).
-      const float* sb = BN <= 64 ? sbias : sbias + acc * 256;
+      const float* sb = BN <= 64 ? sbias : sbias + par * 256;
       if (p.bias != nullptr) {
         if (BN <= 64) {
           if (n_blk != bias_n_blk) {
@@ -418,7 +437,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         } else {
           const int tid = static_cast<int>(threadIdx.x);      // 0..383: the epilogue warps
           const int col = n_blk * BN + tid;
-          if (tid < BN) sbias[acc * 256 + tid] = col < p.N ? __ldg(p.bias + col) : 0.f;
+          if (tid < BN) sbias[par * 256 + tid] = col < p.N ? __ldg(p.bias + col) : 0.f;
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
         }
       }
@@ -679,7 +698,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   if (warp == kWarpMma) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    tmem_dealloc(tmem_base, static_cast<uint32_t>(p.mt * Cfg::kTmemCols));
   }
 }
 
@@ -721,7 +740,16 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
   p.operand_bytes = Cfg::kStages * Cfg::kStageBytes;
   int smem_bytes = Cfg::kSmemBytes;
   int grid = tiles < sms ? tiles : sms;
-  if (p.b_resident) {                     // planned by dispatch(): W tile + A ring + NB staging buffers fit
+  if (p.mt == 2) {                        // paired m tiles: stages of two A tiles + one W tile
+    const int stage_bytes = 2 * Cfg::kABytes + Cfg::kBBytes;
+    p.res_stages = (227 * 1024 - NB * Cfg::kCBytes - kBarBytes - kBiasBytes) / stage_bytes;
+    if (p.res_stages > kMaxStages) p.res_stages = kMaxStages;
+    if (p.res_stages < 2 || 4 * BN > 512) return fail(LECB_ERR_UNSUPPORTED, "paired-tile mode does not fit (BN=%d BK=%d)", BN, BK);
+    p.operand_bytes = p.res_stages * stage_bytes;
+    smem_bytes = p.operand_bytes + NB * Cfg::kCBytes + kBarBytes + kBiasBytes;
+    const int pairs = (p.num_m_tiles / 2) * p.num_n_tiles;
+    grid = pairs < sms ? pairs : sms;
+  } else if (p.b_resident) {              // planned by dispatch(): W tile + A ring + NB staging buffers fit
     p.operand_bytes = p.num_kb * Cfg::kBBytes + p.res_stages * (p.halo ? (p.halo_single ? 1 : 3) * p.copy_bytes : Cfg::kABytes);
     smem_bytes = p.operand_bytes + NB * Cfg::kCBytes + kBarBytes + kBiasBytes;
     grid = (sms / p.num_n_tiles) * p.num_n_tiles;
@@ -801,7 +829,7 @@ static int dispatch(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& t
     if (stages < 1) return fail(LECB_ERR_UNSUPPORTED, "halo conv does not fit shared memory (BN=%d copy=%d)", BN, p.copy_bytes);
     p.b_resident = 1;
     p.res_stages = stages;
-  } else if (p.num_kb >= (getenv("LECB_RES_K1") ? 1 : 2) && p.num_n_tiles <= 8 && sms > 0 && p.num_m_tiles >= 4 * sms && !getenv("LECB_NO_RESIDENT")) {
+  } else if (p.mt == 1 && p.num_kb >= (getenv("LECB_RES_K1") ? 1 : 2) && p.num_n_tiles <= 8 && sms > 0 && p.num_m_tiles >= 4 * sms && !getenv("LECB_NO_RESIDENT")) {
     const int ring = resident_ring(BN, BK, p.num_kb, nb);
     if (ring >= (getenv("LECB_RING_MIN") ? atoi(getenv("LECB_RING_MIN")) : 3)) {
       p.b_resident = 1;
@@ -855,6 +883,7 @@ extern "C" int lecb_gemm_bf16(const void* A, const void* W, const float* bias, c
   p.residual = residual;
   p.out = out;
   p.row_sumsq = row_sumsq;
+  p.mt = 1;
   p.M = M;
   p.N = N;
   p.num_kb = K / BK;
@@ -918,6 +947,7 @@ extern "C" int lecb_conv3x3_bf16(const void* x, const void* w, const float* bias
   p.residual = nullptr;
   p.out = out;
   p.row_sumsq = nullptr;
+  p.mt = 1;
   p.N = Cout;
   p.kb_per_tap = Cin / BK;
   p.num_kb = 9 * p.kb_per_tap;
@@ -964,6 +994,14 @@ extern "C" int lecb_conv3x3_bf16(const void* x, const void* w, const float* bias
                 "(Cin 32/64, one n tile, >= 2 patches per SM); see lecb_conv3x3_pool_fusable()");
   p.M = M;
   p.num_m_tiles = static_cast<int>((M + kTileM - 1) / kTileM);
+  // 128-wide convs (Cin >= 128: the halo mode does not apply, W is too large to stay resident) are bound by the
+  // L2 -> SM fill of A (once per tap) plus W (once per m tile): pairing m tiles halves the W share
+  {
+    const int sms = sm_count();
+    if (BN == 128 && BK == 64 && p.num_n_tiles == 1 && p.num_m_tiles % 2 == 0 && sms > 0 && p.num_m_tiles >= 4 * sms &&
+        !getenv("LECB_NO_MT2"))
+      p.mt = 2;
+  }
   st = encode_im2col_3x3(&tmA, x, B, H, Wd, Cin, BK, kTileM);
   if (st) return st;
   return dispatch<true>(BN, BK, tmA, tmB, p, static_cast<cudaStream_t>(stream));

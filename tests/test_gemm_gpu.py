@@ -213,3 +213,17 @@ def test_conv3x3_fused_avgpool(b, h, w, cin, cout):
     want = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), bias, padding=1).relu()
     want = torch.nn.functional.avg_pool2d(want, 2).permute(0, 2, 3, 1)
     _check(out, want, f"conv+pool {b}x{h}x{w} {cin}->{cout}")
+
+
+@pytest.mark.parametrize("b,h,w,cin,cout", [(8, 112, 112, 128, 128), (27, 56, 56, 128, 128), (8, 112, 112, 128, 96), (7, 112, 112, 256, 128)])
+def test_conv3x3_paired_m_tiles(b, h, w, cin, cout):
+    """128-wide im2col convs with an even number (>= 4 per SM) of m tiles run in paired-tile mode (two A tiles and one W
+    tile per stage, four accumulators): exact and ragged M, Cout tail, Cin 128 / 256."""
+    from lecb200 import ops
+    x = _rand((b, h, w, cin), 81).bfloat16()
+    wt = _rand((cout, 3, 3, cin), 82, (9 * cin) ** -0.5).bfloat16()
+    bias = _rand((cout,), 83, 0.1)
+    out = ops.conv3x3(x, wt, bias, relu=True)
+    torch.cuda.synchronize()
+    want = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), bias, padding=1)
+    _check(out, want.relu().permute(0, 2, 3, 1), f"paired conv {b}x{h}x{w} {cin}->{cout}")
