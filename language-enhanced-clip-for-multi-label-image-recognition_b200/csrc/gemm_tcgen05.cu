@@ -91,7 +91,9 @@ struct GemmParams {
                       // 8-row-group stride of (tw+2) * 128 bytes: every input pixel crosses L2 -> SM 1.4x instead of 9x
 };
 
-template <int BN, int BK, int NB, bool kConv>
+// MT = m tiles per stage (1, or 2 = paired tiles: see GemmParams::mt); a template parameter so the single-tile kernels
+// carry none of the paired-tile code (as a runtime switch it cost the short-tile kernels 5-30 %)
+template <int BN, int BK, int NB, bool kConv, int MT>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
@@ -100,8 +102,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr int kCCols = Cfg::kCCols;
   constexpr int kCBlocks = Cfg::kCBlocks;
   extern __shared__ __align__(1024) uint8_t smem[];     // swizzled tiles need 1024-byte alignment (checked below)
-  const int nstages = (p.b_resident || p.mt == 2) ? p.res_stages : kStages;
-  const int a_stride = p.mt * Cfg::kABytes;            // bytes of A per stage
+  const int nstages = (p.b_resident || MT == 2) ? p.res_stages : kStages;
+  const int a_stride = MT * Cfg::kABytes;            // bytes of A per stage
   uint8_t* sA = smem;
   uint8_t* sB = smem + nstages * a_stride;
   uint8_t* sC = smem + p.operand_bytes;
@@ -128,20 +130,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   // mt == 2: the schedule below runs over PAIRS of m tiles (num_m_tiles is even); sub-tile i belongs to pair i >> 1
-  const int num_tiles = (p.num_m_tiles / p.mt) * p.num_n_tiles;
+  const int num_tiles = (p.num_m_tiles / MT) * p.num_n_tiles;
   // Tile schedule.  Default: tile t = blockIdx.x + i * gridDim.x, n fastest.  b_resident: the CTA keeps n tile
   // blockIdx.x % num_n_tiles and walks m tiles blockIdx.x / num_n_tiles + i * (gridDim.x / num_n_tiles).
   const int res_n = p.b_resident ? static_cast<int>(blockIdx.x) % p.num_n_tiles : 0;
   const int res_m0 = p.b_resident ? static_cast<int>(blockIdx.x) / p.num_n_tiles : 0;
   const int res_ms = p.b_resident ? static_cast<int>(gridDim.x) / p.num_n_tiles : 1;
-  const int my_tiles = p.mt * (p.b_resident
+  const int my_tiles = MT * (p.b_resident
                            ? (res_m0 < p.num_m_tiles ? (p.num_m_tiles - res_m0 + res_ms - 1) / res_ms : 0)
                            : (static_cast<int>(blockIdx.x) < num_tiles ? (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0));
   auto tile_coords = [&](int i, int& m_blk, int& n_blk) {
     if (p.b_resident) {
       m_blk = res_m0 + i * res_ms;
       n_blk = res_n;
-    } else if (p.mt == 2) {
+    } else if (MT == 2) {
       const int tile = static_cast<int>(blockIdx.x) + (i >> 1) * static_cast<int>(gridDim.x);
       const int mp = tile / p.num_n_tiles;
       n_blk = tile - mp * p.num_n_tiles;
@@ -175,7 +177,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     fence_barrier_init();
   }
   if (warp == kWarpMma) {
-    tmem_alloc(tmem_slot, static_cast<uint32_t>(p.mt * Cfg::kTmemCols));
+    tmem_alloc(tmem_slot, static_cast<uint32_t>(MT * Cfg::kTmemCols));
     tmem_relinquish();
   }
   tc_fence_before();
@@ -192,10 +194,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         mbar_arrive_expect_tx(bres, static_cast<uint32_t>(p.num_kb) * Cfg::kBBytes);
         for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(&tmB, bres, smem + kb * Cfg::kBBytes, kb * BK, res_n * BN);
       }
-      for (int ti = 0; ti < my_tiles; ti += p.mt) {
+      for (int ti = 0; ti < my_tiles; ti += MT) {
         int m_blk, n_blk;
         tile_coords(ti, m_blk, n_blk);
-        int pw[2] = {0, 0}, ph[2] = {0, 0}, pn[2] = {0, 0};
         if (kConv && p.halo) {
           const int tx = m_blk % p.tiles_x;
           const int ty = (m_blk / p.tiles_x) % p.tiles_y;
@@ -221,26 +222,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           continue;
         }
+        // base pixel of the tile (and of its pair partner): scalars, not arrays — a runtime-indexed local array lives
+        // in local memory, and with the whole carve-out given to shared memory every such load is an L2 round trip
+        // on the producer's critical path (measured: +13 % on the 256-channel convs)
+        int pw0 = 0, ph0 = 0, pn0 = 0, pw1 = 0, ph1 = 0, pn1 = 0;
         if (kConv) {
-          for (int sub = 0; sub < p.mt; ++sub) {
-            const int64_t m0 = static_cast<int64_t>(m_blk + sub) * kTileM;
-            const int hw = p.H * p.W;
-            pn[sub] = static_cast<int>(m0 / hw);
-            const int rem = static_cast<int>(m0 - static_cast<int64_t>(pn[sub]) * hw);
-            ph[sub] = rem / p.W;
-            pw[sub] = rem - ph[sub] * p.W;
+          const int hw = p.H * p.W;
+          const int64_t m0 = static_cast<int64_t>(m_blk) * kTileM;
+          pn0 = static_cast<int>(m0 / hw);
+          const int rem0 = static_cast<int>(m0 - static_cast<int64_t>(pn0) * hw);
+          ph0 = rem0 / p.W;
+          pw0 = rem0 - ph0 * p.W;
+          if (MT == 2) {
+            const int64_t m1 = m0 + kTileM;
+            pn1 = static_cast<int>(m1 / hw);
+            const int rem1 = static_cast<int>(m1 - static_cast<int64_t>(pn1) * hw);
+            ph1 = rem1 / p.W;
+            pw1 = rem1 - ph1 * p.W;
           }
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], p.b_resident ? Cfg::kABytes : p.mt * Cfg::kABytes + Cfg::kBBytes);
+          mbar_arrive_expect_tx(&full[stage], p.b_resident ? Cfg::kABytes : MT * Cfg::kABytes + Cfg::kBBytes);
           if (kConv) {
             const int tap = kb / p.kb_per_tap;
             const int cb = kb - tap * p.kb_per_tap;
             const int ky = tap / 3, kx = tap - ky * 3;
-            for (int sub = 0; sub < p.mt; ++sub)
-              tma_load_im2col_4d(&tmA, &full[stage], sA_ring + stage * a_stride + sub * Cfg::kABytes, cb * BK, pw[sub] - 1,
-                                 ph[sub] - 1, pn[sub], static_cast<uint16_t>(kx), static_cast<uint16_t>(ky));
+            tma_load_im2col_4d(&tmA, &full[stage], sA_ring + stage * a_stride, cb * BK, pw0 - 1, ph0 - 1, pn0,
+                               static_cast<uint16_t>(kx), static_cast<uint16_t>(ky));
+            if (MT == 2)
+              tma_load_im2col_4d(&tmA, &full[stage], sA_ring + stage * a_stride + Cfg::kABytes, cb * BK, pw1 - 1, ph1 - 1,
+                                 pn1, static_cast<uint16_t>(kx), static_cast<uint16_t>(ky));
           } else {
             tma_load_2d(&tmA, &full[stage], sA_ring + stage * a_stride, kb * BK, m_blk * kTileM);
           }
@@ -258,7 +270,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t idesc = make_idesc_f16(BN, (p.flags & LECB_GEMM_F16_OPERANDS) == 0);
       int stage = 0;
       uint32_t phase = 0;
-      const int nacc = 2 * p.mt;               // accumulators: sub-tile t lives in accumulator t % nacc
+      const int nacc = 2 * MT;               // accumulators: sub-tile t lives in accumulator t % nacc
       if (p.b_resident && my_tiles > 0) mbar_wait(bres, 0);
       // halo-tile conv: descriptor pieces that do not change from tile to tile
       uint32_t halo_off[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -277,11 +289,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         halo_a0 = d0 & 0xFFFFFFFFull;                 // low word without the address field (LBO bits)
         halo_b0 = make_kmajor_desc(smem_u32(smem), BK * 2);
       }
-      for (int ti = 0; ti < my_tiles; ti += p.mt) {
-        for (int sub = 0; sub < p.mt; ++sub) {
-          const int t = ti + sub;
-          mbar_wait(&tempty[t & (nacc - 1)], ((static_cast<uint32_t>(t / nacc) & 1u) ^ 1u));
-        }
+      for (int ti = 0; ti < my_tiles; ti += MT) {
+        // sub-tile t uses accumulator t % nacc in round t / nacc (nacc = 2 or 4)
+        const uint32_t round_par = (static_cast<uint32_t>(ti) >> (MT == 2 ? 2 : 1)) & 1u;
+        mbar_wait(&tempty[ti & (nacc - 1)], round_par ^ 1u);
+        if (MT == 2) mbar_wait(&tempty[(ti + 1) & (nacc - 1)], round_par ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((ti & (nacc - 1)) * BN);
         if (kConv && p.halo) {
@@ -322,7 +334,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             umma_f16(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
                      (kb | k) != 0 ? 1u : 0u);
           }
-          if (p.mt == 2) {                     // second m tile of the pair: next A tile of the stage, next accumulator
+          if (MT == 2) {                     // second m tile of the pair: next A tile of the stage, next accumulator
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
               umma_f16(d_tmem + BN, adesc + static_cast<uint64_t>((Cfg::kABytes >> 4) + 2 * k),
@@ -335,7 +347,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
         umma_commit(&tfull[ti % kTFull]);
-        if (p.mt == 2) umma_commit(&tfull[(ti + 1) % kTFull]);
+        if (MT == 2) umma_commit(&tfull[(ti + 1) % kTFull]);
       }
     }
   } else if (warp == kWarpDma) {
@@ -410,7 +422,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq) {
       int m_blk, n_blk;
       tile_coords(tile_seq, m_blk, n_blk);
-      const int acc = tile_seq & (2 * p.mt - 1);        // accumulator of this (sub-)tile
+      const int acc = tile_seq & (2 * MT - 1);        // accumulator of this (sub-)tile
       const int par = tile_seq & 1;                     // bias slice parity
       const uint32_t tf_phase = static_cast<uint32_t>(tile_seq / kTFull) & 1u;
       const int64_t row = static_cast<int64_t>(m_blk) * kTileM + erow;
@@ -698,20 +710,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   if (warp == kWarpMma) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, static_cast<uint32_t>(p.mt * Cfg::kTmemCols));
+    tmem_dealloc(tmem_base, static_cast<uint32_t>(MT * Cfg::kTmemCols));
   }
 }
 
 template <int BN, int BK, int NB, bool kConv>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, BK, NB>;
+  constexpr bool kPairable = kConv && BN == 128 && BK == 64 && NB == 2;      // the one instantiation of MT = 2
   static bool configured = false;
-  auto kern = gemm_kernel<BN, BK, NB, kConv>;
+  auto kern = gemm_kernel<BN, BK, NB, kConv, 1>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess && kPairable)
+      e = cudaFuncSetAttribute(gemm_kernel<BN, BK, NB, kConv, kPairable ? 2 : 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail(LECB_ERR_CUDA, "cudaFuncSetAttribute(smem=227K): %s", cudaGetErrorString(e));
     configured = true;
   }
+  if (p.mt == 2 && !kPairable) p.mt = 1;
   CUtensorMap tmC = tmA, tmR = tmA;      // placeholders when the staged path is off
   const bool want_f32 = (p.flags & LECB_EPI_OUT_F32) != 0;
   if (!want_f32 && (p.flags & LECB_EPI_RES_F32)) return fail(LECB_ERR_ARG, "fp32 residual requires LECB_EPI_OUT_F32");
@@ -754,7 +770,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
     smem_bytes = p.operand_bytes + NB * Cfg::kCBytes + kBarBytes + kBiasBytes;
     grid = (sms / p.num_n_tiles) * p.num_n_tiles;
   }
-  kern<<<grid, kNumThreads, smem_bytes, stream>>>(tmA, tmB, tmC, tmR, p);
+  if (p.mt == 2) gemm_kernel<BN, BK, NB, kConv, kPairable ? 2 : 1><<<grid, kNumThreads, smem_bytes, stream>>>(tmA, tmB, tmC, tmR, p);
+  else kern<<<grid, kNumThreads, smem_bytes, stream>>>(tmA, tmB, tmC, tmR, p);
   count_launch();
   return check_launch("gemm_kernel");
 }
