@@ -40,9 +40,6 @@ enum lecb_status {
 #define LECB_EPI_OUT_F32 4u     /* store fp32 instead of bf16                                 */
 #define LECB_EPI_RES_F32 8u     /* `residual` is fp32 [M,N] instead of bf16                   */
 #define LECB_GEMM_F16_OPERANDS 16u /* A and W hold IEEE fp16 instead of bf16 (retrieval, T:445)  */
-#define LECB_GEMM_M_DESCENDING 64u /* lecb_gemm_bf16 only: process row tiles last-to-first.  Pure scheduling hint (results  */
-                                   /* are identical): a GEMM reading what the previous kernel wrote first-to-last then     */
-                                   /* starts on the rows still resident in the 126 MB L2                                   */
 #define LECB_EPI_AVGPOOL2 32u   /* lecb_conv3x3_bf16 only: 2x2 average pool after the activation (M:147,177 stem avgpool; */
                                 /* M:27,46 Bottleneck avgpool) fused into the epilogue; out is [B,H/2,W/2,Cout]            */
 

@@ -61,7 +61,7 @@ SIGNATURES = {
                                    c_void_p]),
 }
 
-EPI_RELU, EPI_QUICKGELU, EPI_OUT_F32, EPI_RES_F32, GEMM_F16_OPERANDS, EPI_AVGPOOL2, GEMM_M_DESCENDING = 1, 2, 4, 8, 16, 32, 64
+EPI_RELU, EPI_QUICKGELU, EPI_OUT_F32, EPI_RES_F32, GEMM_F16_OPERANDS, EPI_AVGPOOL2 = 1, 2, 4, 8, 16, 32
 
 
 class LecbError(RuntimeError):

@@ -153,9 +153,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       m_blk = tile / p.num_n_tiles;
       n_blk = tile - m_blk * p.num_n_tiles;
     }
-    // LECB_GEMM_M_DESCENDING: walk the m tiles from the end, so a kernel that consumes what the previous kernel has just
-    // written (ascending) starts on the rows that are still in L2
-    if (p.flags & LECB_GEMM_M_DESCENDING) m_blk = p.num_m_tiles - 1 - m_blk;
   };
 
   if (warp == kWarpTma && lane == 0) {
@@ -955,7 +952,7 @@ extern "C" int lecb_conv3x3_bf16(const void* x, const void* w, const float* bias
   LECB_CHECK_ARG(B > 0 && H > 0 && Wd > 0, "lecb_conv3x3_bf16: empty problem");
   LECB_CHECK_ARG(Cin % 32 == 0, "lecb_conv3x3_bf16: Cin=%d must be a multiple of 32", Cin);
   LECB_CHECK_ARG(Cout % 8 == 0, "lecb_conv3x3_bf16: Cout=%d must be a multiple of 8", Cout);
-  LECB_CHECK_ARG((flags & (LECB_EPI_OUT_F32 | LECB_EPI_RES_F32 | LECB_GEMM_F16_OPERANDS | LECB_GEMM_M_DESCENDING)) == 0,
+  LECB_CHECK_ARG((flags & (LECB_EPI_OUT_F32 | LECB_EPI_RES_F32 | LECB_GEMM_F16_OPERANDS)) == 0,
                  "lecb_conv3x3_bf16: only LECB_EPI_RELU / LECB_EPI_QUICKGELU / LECB_EPI_AVGPOOL2 are supported");
   const bool want_pool = (flags & LECB_EPI_AVGPOOL2) != 0;
   LECB_CHECK_ARG(!want_pool || (H % 2 == 0 && Wd % 2 == 0), "lecb_conv3x3_bf16: LECB_EPI_AVGPOOL2 needs even H and W (H=%d W=%d)", H, Wd);

@@ -29,9 +29,6 @@ def _w1x1(w):
     return w.reshape(w.shape[0], w.shape[1]).to(torch.bfloat16).contiguous()
 
 
-_DESCENDING_C1 = not os.environ.get("LECB_NO_DESCENDING")
-
-
 def _w3x3(w):
     return w.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()          # [Cout,3,3,Cin]
 
@@ -110,9 +107,7 @@ class VisualRN:
     @staticmethod
     def _bottleneck(x, blk):
         b, h, w, c = x.shape
-        # conv1 reads what the previous block's conv3 has just written first-to-last: walking it last-to-first starts on
-        # the ~100 MB of rows still in L2, and leaves the FIRST rows of x there for this block's own conv3 (residual)
-        y = ops.gemm(x.view(-1, c), *blk["c1"], relu=True, descending=_DESCENDING_C1)
+        y = ops.gemm(x.view(-1, c), *blk["c1"], relu=True)
         y = ops.conv3x3(y.view(b, h, w, -1), *blk["c2"])
         idn = x
         if blk["stride"] > 1:

@@ -26,10 +26,8 @@ def _need(t, dtype, name):
         raise _lib.LecbError(f"{name} must be contiguous")
 
 
-def gemm(a, w, bias=None, residual=None, relu=False, quick_gelu=False, out_f32=False, row_sumsq=None, out=None,
-         descending=False):
-    """out[M,N] = epi(a[M,K] @ w[N,K]^T + bias (+ residual)); a, w bf16; bias fp32.
-    descending=True walks the row tiles last-to-first (scheduling hint for L2 reuse; same result)."""
+def gemm(a, w, bias=None, residual=None, relu=False, quick_gelu=False, out_f32=False, row_sumsq=None, out=None):
+    """out[M,N] = epi(a[M,K] @ w[N,K]^T + bias (+ residual)); a, w bf16; bias fp32."""
     _need(a, torch.bfloat16, "a")
     _need(w, torch.bfloat16, "w")
     m, k = a.shape
@@ -43,8 +41,6 @@ def gemm(a, w, bias=None, residual=None, relu=False, quick_gelu=False, out_f32=F
     if out is None:
         out = torch.empty((m, n), device=a.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
     flags = (EPI_RELU if relu else 0) | (EPI_QUICKGELU if quick_gelu else 0) | (EPI_OUT_F32 if out_f32 else 0)
-    if descending:
-        flags |= _lib.GEMM_M_DESCENDING
     check(lib.lecb_gemm_bf16(_ptr(a), _ptr(w), _ptr(bias), _ptr(residual), _ptr(out), _ptr(row_sumsq), m, n, k,
                              flags, _stream()), "lecb_gemm_bf16")
     return out

@@ -227,17 +227,3 @@ def test_conv3x3_paired_m_tiles(b, h, w, cin, cout):
     torch.cuda.synchronize()
     want = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), bias, padding=1)
     _check(out, want.relu().permute(0, 2, 3, 1), f"paired conv {b}x{h}x{w} {cin}->{cout}")
-
-
-@pytest.mark.parametrize("m,n,k,res", [(100003, 256, 1024, False), (80000, 256, 64, True), (333, 512, 128, True), (90000, 64, 256, False)])
-def test_gemm_descending_row_tiles(m, n, k, res):
-    """LECB_GEMM_M_DESCENDING is a pure scheduling hint: bit-identical output in the streaming and resident-W schedules."""
-    from lecb200 import ops
-    a = _rand((m, k), 91).bfloat16()
-    w = _rand((n, k), 92, k ** -0.5).bfloat16()
-    bias = _rand((n,), 93, 0.1)
-    r = _rand((m, n), 94).bfloat16() if res else None
-    up = ops.gemm(a, w, bias, residual=r, relu=True)
-    down = ops.gemm(a, w, bias, residual=r, relu=True, descending=True)
-    torch.cuda.synchronize()
-    assert torch.equal(up, down)
