@@ -21,7 +21,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from . import ops
+from . import checkpoint, ops
 from .clip_model import describe
 from .engine import TextTower, VisualRN, VisualViT
 
@@ -177,6 +177,9 @@ class DenseCLIPB200(nn.Module):
         super().__init__()
         kw = dict(tokenizer=tokenizer, tokenized_prompts=tokenized_prompts)
         self.prompt_learner = PromptLearner(cfg, classnames, clip_model, nctx, **kw)
+        # checkpoint.load_model() / load_pretrained_weights() receive the prompt learner alone (the trainer registers it,
+        # T:774) and must drop this module's cached text features: a weak back-reference, invisible to nn.Module
+        checkpoint.register_owner(self.prompt_learner, self)
         self.prompt_learner_m = PromptLearner(cfg, classnames, clip_model, nctx, **kw)
         self.tokenized_prompts = self.prompt_learner.tokenized_prompts
         self.text_encoder = TextEncoder(clip_model)

@@ -133,6 +133,28 @@ def loss_functions():
     return ns
 
 
+def checkpoint_functions():
+    """-> namespace with the reference `save_checkpoint`, `load_checkpoint`, `load_pretrained_weights`
+    (Dassl.pytorch-master/dassl/utils/torchtools.py:27-120, 266-320).  torch >= 2.6 made weights_only=True the default
+    of torch.load, which cannot read the optimizer state these files hold: the namespace's `torch.load` passes False."""
+    import pickle
+    import shutil
+    import types
+    import warnings
+    from collections import OrderedDict
+    from functools import partial
+    import torch
+    path = os.path.join(MC, "Dassl.pytorch-master", "dassl", "utils", "torchtools.py")
+    code = _extract(path, ["save_checkpoint", "load_checkpoint", "load_pretrained_weights"])
+    tshim = types.SimpleNamespace(save=torch.save, cuda=torch.cuda,
+                                  load=lambda *a, **k: torch.load(*a, **{"weights_only": False, **k}))
+    ns = {"torch": tshim, "osp": os.path, "pickle": pickle, "shutil": shutil, "warnings": warnings, "partial": partial,
+          "OrderedDict": OrderedDict, "mkdir_if_missing": lambda d: os.makedirs(d, exist_ok=True),
+          "__name__": "_lecb_ref_torchtools"}
+    exec(code, ns)
+    return ns
+
+
 def fusion_functions(sims_scores):
     """-> namespace with the reference `fuse` / `fuse6` of gen_final_ans.py:18-71 (they read the module global
     `sims_scores`, provided here) and `adjust_predictions`, the helper nested in Caption_distill_double.test (T:611-615)."""

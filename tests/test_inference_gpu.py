@@ -146,3 +146,26 @@ def test_no_cpu_path():
     from lecb200 import LecbError, ops
     with pytest.raises(LecbError):
         ops.gemm(torch.zeros((128, 64), dtype=torch.bfloat16), torch.zeros((64, 64), dtype=torch.bfloat16))
+
+
+def test_prompt_checkpoint_roundtrip_refreshes_scores(tmp_path):
+    """save_model / load_model in the reference's layout (T:906-938, trainer.py:119-143) through the real module: loading
+    other prompt contexts into `prompt_learner` must change the scores (the cached text features are dropped), and
+    loading the saved ones back must reproduce the first scores bit for bit."""
+    from lecb200 import checkpoint
+    c = C.head_case("small")
+    model = build_model(c, use_evidence=True)
+    img = c["image"].cuda()
+    first = [t.clone() for t in model(img, if_test=True)[:2]]
+    checkpoint.save_model({"double": model.prompt_learner}, epoch=0, directory=str(tmp_path), model_name="model.pth.tar")
+    with torch.no_grad():
+        for p in (model.prompt_learner.ctx, model.prompt_learner.ctx_double, model.prompt_learner.ctx_evidence):
+            p.add_(0.05 * torch.randn_like(p))
+    model.reset_prompt_cache()
+    moved = model(img, if_test=True)[:2]
+    assert (moved[0] - first[0]).abs().max().item() > 1e-4
+    assert checkpoint.load_model({"double": model.prompt_learner}, str(tmp_path)) == {"double": 1}
+    again = model(img, if_test=True)[:2]                   # no explicit reset: load_model invalidated the cache
+    torch.cuda.synchronize()
+    for a, b in zip(first, again):
+        assert torch.equal(a, b)
