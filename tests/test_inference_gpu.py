@@ -151,7 +151,7 @@ def test_no_cpu_path():
 def test_prompt_checkpoint_roundtrip_refreshes_scores(tmp_path):
     """save_model / load_model in the reference's layout (T:906-938, trainer.py:119-143) through the real module: loading
     other prompt contexts into `prompt_learner` must change the scores (the cached text features are dropped), and
-    loading the saved ones back must reproduce the first scores bit for bit."""
+    loading the saved ones back must reproduce the first scores."""
     from lecb200 import checkpoint
     c = C.head_case("small")
     model = build_model(c, use_evidence=True)
@@ -168,4 +168,5 @@ def test_prompt_checkpoint_roundtrip_refreshes_scores(tmp_path):
     again = model(img, if_test=True)[:2]                   # no explicit reset: load_model invalidated the cache
     torch.cuda.synchronize()
     for a, b in zip(first, again):
-        assert torch.equal(a, b)
+        # not bit-exact: the row sum-of-squares behind the L2 normalisation is accumulated with atomics across n tiles
+        assert (a - b).abs().max().item() <= 1e-5
