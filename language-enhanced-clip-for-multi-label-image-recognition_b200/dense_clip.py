@@ -180,6 +180,10 @@ class DenseCLIPB200(nn.Module):
         # checkpoint.load_model() / load_pretrained_weights() receive the prompt learner alone (the trainer registers it,
         # T:774) and must drop this module's cached text features: a weak back-reference, invisible to nn.Module
         checkpoint.register_owner(self.prompt_learner, self)
+        # Opt-in (not in the reference): True or a process group splits the 2-3 x K prompt sequences of
+        # the prompt-tuning step over the ranks instead of replicating them (train_path.py, dist.py); gradients after
+        # dist.allreduce_mean_grads are those of the replicated branch
+        self.shard_prompt_branch = False
         self.prompt_learner_m = PromptLearner(cfg, classnames, clip_model, nctx, **kw)
         self.tokenized_prompts = self.prompt_learner.tokenized_prompts
         self.text_encoder = TextEncoder(clip_model)

@@ -4,7 +4,13 @@ Inference shards by image batch: every rank scores its own contiguous slice with
 weights, then ONE all-gather of a packed [B_local, 2K] fp32 tile (global logits | local logits)
 assembles the global result — the only exchange on the path (the reference itself never
 shards inference, §2a).  Prompt tuning shards by caption batch and all-reduces (averages) one flat
-prompt-gradient buffer, the semantics of the reference's DDP wrapper (T:786-787)."""
+prompt-gradient buffer, the semantics of the reference's DDP wrapper (T:786-787).
+
+Class-sharded prompt branch (SURVEY §8e "optional later", §8f-2; opt-in, `DenseCLIPB200.shard_prompt_branch`): the
+2-3 x K prompt sequences are split over the ranks instead of replicated — `gather_rows` assembles the [n*K, D] text
+features after each rank has run the text tower on its own rows, `sum_over_ranks` adds up the per-rank feature gradients
+before each rank back-propagates its rows only.  With the flat gradient average above the result is the replicated one:
+mean_r( J_r^T (sum_r' dT_r')[rows_r] ) = (1/G) J^T sum_r' dT_r'."""
 from __future__ import annotations
 
 import torch
@@ -62,3 +68,38 @@ def allreduce_mean_grads(params, group=None):
         else:
             p.grad.copy_(g)
         off += n
+
+
+def multi_rank(group=None) -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
+def my_chunk(n_rows: int, group=None):
+    """chunk_range of the calling rank."""
+    return chunk_range(n_rows, dist.get_rank(group), dist.get_world_size(group))
+
+
+def chunk_range(n_rows: int, rank: int, world: int):
+    """Equal chunks of ceil(n_rows / world) rows (the last ranks may get fewer, or none): the layout
+    all_gather_into_tensor needs.  -> (lo, hi, rows per chunk)."""
+    per = -(-n_rows // world)
+    lo = min(rank * per, n_rows)
+    return lo, min(lo + per, n_rows), per
+
+
+def gather_rows(own: torch.Tensor, n_rows: int, group=None) -> torch.Tensor:
+    """own = this rank's chunk (chunk_range) of an [n_rows, D] matrix -> the whole matrix on every rank."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    lo, hi, per = chunk_range(n_rows, rank, world)
+    assert own.shape[0] == hi - lo, (own.shape, lo, hi)
+    buf = own.new_zeros((per,) + tuple(own.shape[1:]))
+    buf[:hi - lo] = own
+    out = own.new_empty((world * per,) + tuple(own.shape[1:]))
+    dist.all_gather_into_tensor(out, buf.contiguous(), group=group)
+    return out[:n_rows].contiguous()
+
+
+def sum_over_ranks(t: torch.Tensor, group=None) -> torch.Tensor:
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import torch
 
-from . import ops
+from . import dist, ops
 
 
 def _cfg(model, path, default=None):
@@ -21,7 +21,7 @@ def _cfg(model, path, default=None):
 class _DualPromptHead(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pack, logit_scale_t, *prompts):
-        tower, (tok_prompts, l_eff), local, ssq, mask, g_unit, b, l, logit_scale, spatial = pack
+        tower, (tok_prompts, l_eff), local, ssq, mask, g_unit, b, l, logit_scale, spatial, shard_group = pack
         n_txt = len(prompts)
         k = prompts[0].shape[0]
         # The mask is causal (M:364-370) and only the EOT row of a prompt is used (T:100), so positions after the
@@ -30,7 +30,18 @@ class _DualPromptHead(torch.autograd.Function):
         ctx.full_len = prompts[0].shape[1]
         x = (torch.cat([p.detach().float() for p in prompts], 0) + tower.pos)[:, :l_eff].contiguous()   # [n*K, l_eff, W]
         eot = tok_prompts.repeat(n_txt)          # EOT index per prompt sequence, already on the device
-        t_raw, saved = tower.forward_train(x, eot)                                                # [n*K, D] fp32
+        ctx.rows = None
+        if shard_group is None:
+            t_raw, saved = tower.forward_train(x, eot)                                            # [n*K, D] fp32
+        else:
+            # class-sharded prompt branch (dist.py): the tower runs on this rank's rows, the features are all-gathered
+            group = None if shard_group is True else shard_group
+            lo, hi, _ = dist.my_chunk(x.shape[0], group)
+            if hi <= lo:
+                raise RuntimeError(f"shard_prompt_branch: {x.shape[0]} prompt sequences cannot feed every rank")
+            t_own, saved = tower.forward_train(x[lo:hi].contiguous(), eot[lo:hi].contiguous())
+            t_raw = dist.gather_rows(t_own, x.shape[0], group)
+            ctx.rows = (lo, hi, group, x.shape[0], x.shape[1], x.shape[2])
         t_hat = ops.l2norm_rows(t_raw)
         pad = (-t_hat.shape[0]) % 8
         t_cat = t_hat if not pad else torch.cat([t_hat, t_hat.new_zeros((pad, t_hat.shape[1]))], 0)
@@ -58,7 +69,16 @@ class _DualPromptHead(torch.autograd.Function):
         if d_tpos is not None:
             d_that[:k] += d_tpos.float()
         d_traw = ops.l2norm_bwd(t_raw, d_that)
-        dx = tower.backward(saved, d_traw)                                                          # [n*K, l_eff, W]
+        if ctx.rows is None:
+            dx = tower.backward(saved, d_traw)                                                      # [n*K, l_eff, W]
+        else:
+            # every rank's loss depends on every text feature: sum the feature gradients over ranks, then back-propagate
+            # this rank's rows only (the other rows of dx stay zero; the flat gradient average completes the sum)
+            lo, hi, group, n_all, l_run, w_run = ctx.rows
+            d_traw = dist.sum_over_ranks(d_traw.contiguous(), group)
+            dx_own = tower.backward(saved, d_traw[lo:hi].contiguous())
+            dx = dx_own.new_zeros((n_all, l_run, w_run))
+            dx[lo:hi] = dx_own
         if dx.shape[1] < ctx.full_len:           # positions past the last EOT carry exactly zero gradient
             dx = torch.nn.functional.pad(dx, (0, 0, 0, ctx.full_len - dx.shape[1]))
         grads = tuple(dx[i * k:(i + 1) * k] for i in range(n_txt))
@@ -129,7 +149,11 @@ def forward_train(model, captions):
         eot = model.tokenized_prompts.argmax(dim=-1)
         # cached (EOT indices on the device, live prompt length): keeps the step free of host syncs / graph-capturable
         model._eot_dev = (eot.to(local.device), int(eot.max()) + 1)
-    pack = (model.text_encoder.tower(), model._eot_dev, local, ssq, mask, g_unit, b, l, logit_scale, spatial)
+    shard = getattr(model, "shard_prompt_branch", False)
+    if shard and not dist.multi_rank(None if shard is True else shard):
+        shard = False                    # single process: nothing to shard over
+    pack = (model.text_encoder.tower(), model._eot_dev, local, ssq, mask, g_unit, b, l, logit_scale, spatial,
+            (True if shard is True else shard) if shard else None)
     plist = (prompts, prompts_double, prompts_evidence) if use_evidence else (prompts, prompts_double)
     logits, logits_local, text_features = _DualPromptHead.apply(pack, temperature if learn else None, *plist)
     with torch.no_grad():

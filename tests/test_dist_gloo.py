@@ -60,7 +60,59 @@ def _check_grad_mean(rank, world):
     assert torch.allclose(p3.grad, torch.tensor(10.0 / world))
 
 
-@pytest.mark.parametrize("fn", ["_check_gather", "_check_grad_mean"])
+class _ShardedRows(torch.autograd.Function):
+    """The protocol of train_path._DualPromptHead with a differentiable stand-in for the text tower: forward runs the
+    per-row function on this rank's chunk and gathers the rows; backward sums the row gradients over ranks, then
+    back-propagates this rank's chunk only (zeros elsewhere)."""
+
+    @staticmethod
+    def forward(ctx, D, x, w):
+        lo, hi, _ = D.my_chunk(x.shape[0])
+        ctx.D, ctx.rows = D, (lo, hi, x.shape)
+        ctx.save_for_backward(x[lo:hi], w)
+        return D.gather_rows(torch.tanh(x[lo:hi] @ w), x.shape[0])
+
+    @staticmethod
+    def backward(ctx, d_t):
+        own, w = ctx.saved_tensors
+        lo, hi, shape = ctx.rows
+        d_t = ctx.D.sum_over_ranks(d_t.contiguous())
+        d_pre = d_t[lo:hi] * (1 - torch.tanh(own @ w) ** 2)
+        dx = torch.zeros(shape)
+        dx[lo:hi] = d_pre @ w.t()
+        return None, dx, None
+
+
+def _check_sharded_prompt_branch(rank, world):
+    """Class-sharded prompt branch: gradients of the shared context after the flat average equal the
+    replicated branch's, for a row count the ranks share unevenly (7 rows, chunks of 4 + 3)."""
+    D = _load_dist_module()
+    g = torch.Generator().manual_seed(5)
+    n_rows, n_ctx, width, dim = 7, 3, 6, 5
+    ctx0 = torch.randn((n_ctx, width), generator=g)
+    cls = torch.randn((n_rows, width), generator=g)             # per-class token embeddings (frozen)
+    w = torch.randn((width, dim), generator=g)                  # the frozen "tower"
+    caps = torch.randn((4, dim), generator=torch.Generator().manual_seed(100 + rank))      # this rank's captions
+    y = (torch.rand((4, n_rows), generator=torch.Generator().manual_seed(200 + rank)) < 0.3).float()
+
+    def run(sharded):
+        ctx = torch.nn.Parameter(ctx0.clone())
+        x = ctx.sum(0, keepdim=True) + cls                      # the shared context enters every row (CSC = False)
+        t = _ShardedRows.apply(D, x, w) if sharded else torch.tanh(x @ w)
+        logits = caps @ torch.nn.functional.normalize(t, dim=-1).t()
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, y)      # mean over the LOCAL batch (SURVEY 8e)
+        loss.backward()
+        D.allreduce_mean_grads([ctx])
+        return logits.detach(), ctx.grad.clone()
+
+    lg_rep, g_rep = run(False)
+    lg_sh, g_sh = run(True)
+    assert torch.allclose(lg_sh, lg_rep, atol=1e-6)
+    assert torch.allclose(g_sh, g_rep, atol=1e-6), (g_sh - g_rep).abs().max()
+    assert D.chunk_range(7, 0, 2) == (0, 4, 4) and D.chunk_range(7, 1, 2) == (4, 7, 4) and D.chunk_range(5, 3, 4) == (5, 5, 2)
+
+
+@pytest.mark.parametrize("fn", ["_check_gather", "_check_grad_mean", "_check_sharded_prompt_branch"])
 def test_two_rank_gloo(fn):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), fn), nprocs=world, join=True)

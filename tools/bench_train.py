@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--per-gpu-batch", type=int, default=64)
     ap.add_argument("--evidence", action="store_true")
     ap.add_argument("--loss", default="asl", choices=["asl", "ranking"])
+    ap.add_argument("--shard-prompts", action="store_true",
+                    help="split the prompt sequences over the ranks instead of replicating them (DenseCLIPB200.shard_prompt_branch)")
     ap.add_argument("--graph", action="store_true", help="capture forward+loss+backward+allreduce+SGD in one CUDA graph")
     args = ap.parse_args()
     rank, local_rank, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
@@ -47,6 +49,7 @@ def main():
     model = DenseCLIPB200(make_cfg(224, n_ctx, args.evidence), names, clip, tokenized_prompts=toks).to(dev)
     for n_, p in model.named_parameters():
         p.requires_grad_("prompt_learner." in n_ and "prompt_learner_m" not in n_)
+    model.shard_prompt_branch = bool(args.shard_prompts)
     params = [p for p in model.prompt_learner.parameters()]
     opt = torch.optim.SGD(params, lr=0.002, momentum=0.9)
     b = args.per_gpu_batch
@@ -104,7 +107,7 @@ def main():
     if rank == 0:
         print(json.dumps({"metric": "prompt_tuning_captions_per_sec", "value": world * b / (ms * 1e-3), "unit": "captions/s",
                           "n_gpus": world, "ms_per_step": ms, "per_gpu_batch": b, "global_batch": world * b,
-                          "prompt_sequences": n_seq * len(names), "loss": args.loss, "cuda_graph": bool(args.graph), "final_loss": float(loss),
+                          "prompt_sequences": n_seq * len(names), "loss": args.loss, "cuda_graph": bool(args.graph), "shard_prompts": bool(args.shard_prompts), "final_loss": float(loss),
                           "approx_tflops_per_rank": tf / (ms * 1e-3), "gpu_launches_per_step": (lecb200.launch_count() - n0) // args.steps,
                           "config": "BASELINE configs[3] shape: RN50 text tower, 77 tokens, real caption-length distribution"}))
     if world > 1:

@@ -1,0 +1,98 @@
+"""Class-sharded prompt branch (DenseCLIPB200.shard_prompt_branch) against the replicated one, under torchrun:
+same logits, same averaged prompt gradients, and the step time of both (BASELINE configs[3] shape, RN50 text tower).
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_sharded_prompts.py [--evidence]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--evidence", action="store_true")
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--per-gpu-batch", type=int, default=64)
+    args = ap.parse_args()
+    rank, local_rank, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
+    assert world > 1, "run under torchrun with at least two ranks"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=dev)
+    import lecb200  # noqa: F401
+    from bench import load_tokens, make_cfg
+    from lecb200 import losses, synth
+    from lecb200.clip_model import CLIPParams
+    from lecb200.dense_clip import DenseCLIPB200
+    from lecb200.dist import allreduce_mean_grads
+
+    arch = synth.RN50(224)
+    toks, n_ctx, names = load_tokens()
+    clip = CLIPParams(*arch.ctor_args())
+    clip.load_state_dict(synth.clip_state_dict(arch, 0), strict=False)
+    clip = clip.float().to(dev).eval()
+    model = DenseCLIPB200(make_cfg(224, n_ctx, args.evidence), names, clip, tokenized_prompts=toks).to(dev)
+    for n_, p in model.named_parameters():
+        p.requires_grad_("prompt_learner." in n_ and "prompt_learner_m" not in n_)
+    params = list(model.prompt_learner.parameters())
+    b = args.per_gpu_batch
+    caps = synth.captions(b, 100 + rank, vocab=arch.vocab_size).to(dev)
+    y = synth.labels(b, len(names), 100 + rank).to(dev)
+
+    def fwd_bwd():
+        for p in params:
+            p.grad = None
+        out = model(None, caps)
+        loss = losses.ASL_loss(out[0], y) + losses.ASL_loss(out[1], y)
+        loss.backward()
+        allreduce_mean_grads(params)
+        return out, loss
+
+    res = {}
+    grads = {}
+    for mode in (False, True):
+        model.shard_prompt_branch = mode
+        out, loss = fwd_bwd()
+        torch.cuda.synchronize()
+        grads[mode] = ([o.detach().float().clone() for o in out[:2]], [p.grad.detach().float().clone() for p in params])
+        for _ in range(3):
+            fwd_bwd()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            fwd_bwd()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res["ms_sharded" if mode else "ms_replicated"] = float(t.item())
+    (lg_r, g_r), (lg_s, g_s) = grads[False], grads[True]
+    logit_err = max((a - b_).abs().max().item() for a, b_ in zip(lg_r, lg_s))
+    names_p = [n for n, _ in model.prompt_learner.named_parameters()]
+    grad_rel = {n: ((a - b_).abs().max() / (a.abs().max() + 1e-20)).item() for n, a, b_ in zip(names_p, g_r, g_s) if a.abs().max() > 0}
+    ok = logit_err <= 1e-4 and all(v <= 2e-3 for v in grad_rel.values())
+    errs = torch.tensor([0.0 if ok else 1.0], device=dev)
+    dist.all_reduce(errs)
+    if rank == 0:
+        n_seq = (3 if args.evidence else 2) * len(names)
+        print(json.dumps({"check": "class-sharded prompt branch vs replicated", "n_gpus": world, "prompt_sequences": n_seq,
+                          "per_gpu_batch": b, "max_abs_logit_diff": logit_err, "grad_rel_err": grad_rel,
+                          "pass_all_ranks": bool(errs.item() == 0), **res,
+                          "captions_per_sec_replicated": world * b / (res["ms_replicated"] * 1e-3),
+                          "captions_per_sec_sharded": world * b / (res["ms_sharded"] * 1e-3)}))
+    dist.destroy_process_group()
+    sys.exit(0 if errs.item() == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()
