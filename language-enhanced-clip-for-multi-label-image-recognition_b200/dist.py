@@ -70,6 +70,17 @@ def allreduce_mean_grads(params, group=None):
         off += n
 
 
+def broadcast_params(params, src: int = 0, group=None):
+    """DDP's construction-time broadcast (T:786-787): every rank starts from rank `src`'s prompt
+    parameters — `ctx*` are drawn from each process's own RNG (T:134-151).  Required by the class-sharded prompt branch,
+    where a rank consumes text features computed from another rank's copy of the parameters."""
+    if not multi_rank(group):
+        return
+    with torch.no_grad():
+        for p in params:
+            dist.broadcast(p.data, src=src, group=group)
+
+
 def multi_rank(group=None) -> bool:
     return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
 

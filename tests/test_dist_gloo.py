@@ -46,6 +46,13 @@ def _check_gather(rank, world):
     assert torch.equal(lg, full) and torch.equal(ll, -full)
 
 
+def _check_broadcast(rank, world):
+    D = _load_dist_module()
+    p = [torch.nn.Parameter(torch.full((2, 3), float(rank + 1))), torch.nn.Parameter(torch.tensor(float(10 * rank)))]
+    D.broadcast_params(p)
+    assert torch.equal(p[0].data, torch.ones(2, 3)) and p[1].item() == 0.0 and p[0].requires_grad
+
+
 def _check_grad_mean(rank, world):
     D = _load_dist_module()
     torch.manual_seed(0)
@@ -112,7 +119,7 @@ def _check_sharded_prompt_branch(rank, world):
     assert D.chunk_range(7, 0, 2) == (0, 4, 4) and D.chunk_range(7, 1, 2) == (4, 7, 4) and D.chunk_range(5, 3, 4) == (5, 5, 2)
 
 
-@pytest.mark.parametrize("fn", ["_check_gather", "_check_grad_mean", "_check_sharded_prompt_branch"])
+@pytest.mark.parametrize("fn", ["_check_gather", "_check_broadcast", "_check_grad_mean", "_check_sharded_prompt_branch"])
 def test_two_rank_gloo(fn):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), fn), nprocs=world, join=True)

@@ -39,7 +39,7 @@ def main():
     from lecb200 import losses, synth
     from lecb200.clip_model import CLIPParams
     from lecb200.dense_clip import DenseCLIPB200
-    from lecb200.dist import allreduce_mean_grads
+    from lecb200.dist import allreduce_mean_grads, broadcast_params
 
     arch = synth.RN50(224)
     toks, n_ctx, names = load_tokens()
@@ -51,6 +51,7 @@ def main():
         p.requires_grad_("prompt_learner." in n_ and "prompt_learner_m" not in n_)
     model.shard_prompt_branch = bool(args.shard_prompts)
     params = [p for p in model.prompt_learner.parameters()]
+    broadcast_params(params)                 # DDP's construction-time broadcast (T:786-787)
     opt = torch.optim.SGD(params, lr=0.002, momentum=0.9)
     b = args.per_gpu_batch
     caps = synth.captions(b, 100 + rank, vocab=arch.vocab_size).to(dev)

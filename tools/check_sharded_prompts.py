@@ -32,7 +32,7 @@ def main():
     from lecb200 import losses, synth
     from lecb200.clip_model import CLIPParams
     from lecb200.dense_clip import DenseCLIPB200
-    from lecb200.dist import allreduce_mean_grads
+    from lecb200.dist import allreduce_mean_grads, broadcast_params
 
     arch = synth.RN50(224)
     toks, n_ctx, names = load_tokens()
@@ -43,6 +43,7 @@ def main():
     for n_, p in model.named_parameters():
         p.requires_grad_("prompt_learner." in n_ and "prompt_learner_m" not in n_)
     params = list(model.prompt_learner.parameters())
+    broadcast_params(params)                 # DDP semantics: all ranks start from rank 0's contexts
     b = args.per_gpu_batch
     caps = synth.captions(b, 100 + rank, vocab=arch.vocab_size).to(dev)
     y = synth.labels(b, len(names), 100 + rank).to(dev)
