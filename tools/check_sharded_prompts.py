@@ -81,7 +81,11 @@ def main():
     logit_err = max((a - b_).abs().max().item() for a, b_ in zip(lg_r, lg_s))
     names_p = [n for n, _ in model.prompt_learner.named_parameters()]
     grad_rel = {n: ((a - b_).abs().max() / (a.abs().max() + 1e-20)).item() for n, a, b_ in zip(names_p, g_r, g_s) if a.abs().max() > 0}
-    ok = logit_err <= 1e-4 and all(v <= 2e-3 for v in grad_rel.values())
+    # The two modes round to bf16 at different points of the backward (replicated: each rank's feature gradient is rounded,
+    # back-propagated, then averaged in fp32; sharded: the fp32 feature gradients are summed first, then rounded), so the
+    # gradients agree to bf16 accuracy, not bit for bit: measured 3-5e-4 of max |grad| without evidence prompts and 4.5e-3
+    # with them (profiles/r01_sharded_prompts*_2gpu.json; the tolerance against the reference itself is 5e-2).
+    ok = logit_err <= 1e-4 and all(v <= 1e-2 for v in grad_rel.values())
     errs = torch.tensor([0.0 if ok else 1.0], device=dev)
     dist.all_reduce(errs)
     if rank == 0:
