@@ -815,8 +815,8 @@ template <bool kConv>
 static int dispatch(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t s) {
   int nb = 2;
   if (!kConv) {
-    if (p.num_kb <= 2) nb = getenv("LECB_NB_K2") ? atoi(getenv("LECB_NB_K2")) : 8;
-    else if (p.num_kb <= 4) nb = getenv("LECB_NB_K4") ? atoi(getenv("LECB_NB_K4")) : 5;
+    if (p.num_kb <= 2) nb = 8;               // measured 6 / 8: equal
+    else if (p.num_kb <= 4) nb = 5;          // measured 4 / 5 / 8 on layer3's expand conv: 4.91 / 4.56 / 4.52 ms per 23 launches
     else if (p.num_kb <= 8) nb = 4;
     // fp32 output / residual moves twice the bytes per element: keep four blocks in flight up to K = 1024
     else if ((p.flags & LECB_EPI_OUT_F32) && p.num_kb <= 16) nb = 4;
@@ -837,7 +837,7 @@ static int dispatch(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& t
     };
     // Cin = 32 (stem convs, 64-byte rows): a tile is 24 KB of HBM traffic against ~0.5 us of MMAs, so the output
     // blocks need the deeper store pipeline more than the halo ring needs a fifth stage
-    if (BK == 32) nb = getenv("LECB_NB_HALO32") ? atoi(getenv("LECB_NB_HALO32")) : 4;
+    if (BK == 32) nb = 4;                     // measured 2 / 3 / 4 on the stem convs: 4 is 10-25 % faster
     int stages = stages_with(nb);
     if (stages < 2 && stages_with(1) >= 1) {       // Cout = 128: 144 KB of weights leave room for ONE halo stage and
       nb = 1;                                      // one staging buffer; still ~3x faster than re-fetching per tap
@@ -846,9 +846,9 @@ static int dispatch(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& t
     if (stages < 1) return fail(LECB_ERR_UNSUPPORTED, "halo conv does not fit shared memory (BN=%d copy=%d)", BN, p.copy_bytes);
     p.b_resident = 1;
     p.res_stages = stages;
-  } else if (p.mt == 1 && p.num_kb >= (getenv("LECB_RES_K1") ? 1 : 2) && p.num_n_tiles <= 8 && sms > 0 && p.num_m_tiles >= 4 * sms && !getenv("LECB_NO_RESIDENT")) {
+  } else if (p.mt == 1 && p.num_kb >= 2 && p.num_n_tiles <= 8 && sms > 0 && p.num_m_tiles >= 4 * sms && !getenv("LECB_NO_RESIDENT")) {
     const int ring = resident_ring(BN, BK, p.num_kb, nb);
-    if (ring >= (getenv("LECB_RING_MIN") ? atoi(getenv("LECB_RING_MIN")) : 3)) {
+    if (ring >= 3) {                          // a two-stage A ring next to a resident 128 KB W tile measured slower than streaming
       p.b_resident = 1;
       p.res_stages = ring;
     }
@@ -856,7 +856,6 @@ static int dispatch(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& t
   if (kConv && nb == 1) return dispatch_nb<kConv, 1>(BN, BK, tmA, tmB, p, s);
   switch (nb) {
     case 8: return dispatch_nb<kConv, 8>(BN, BK, tmA, tmB, p, s);
-    case 6: return dispatch_nb<kConv, 6>(BN, BK, tmA, tmB, p, s);
     case 5: return dispatch_nb<kConv, 5>(BN, BK, tmA, tmB, p, s);
     case 4: return dispatch_nb<kConv, 4>(BN, BK, tmA, tmB, p, s);
     case 3: return dispatch_nb<kConv, 3>(BN, BK, tmA, tmB, p, s);
@@ -892,9 +891,6 @@ extern "C" int lecb_gemm_bf16(const void* A, const void* W, const float* bias, c
       if (e128 > 1.15 * e256) BN = 128;
     }
   }
-  // experiment knob: narrower tiles for the short-K expand convs so the W tile (BN x K) can stay resident next to a
-  // full staging ring
-  if (BN == 256 && K <= 256 && N >= 512 && getenv("LECB_EXPAND_BN128")) BN = 128;
   GemmParams p{};
   p.bias = bias;
   p.residual = residual;
