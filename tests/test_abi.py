@@ -55,6 +55,12 @@ def test_argument_errors_are_reported_without_a_gpu(built):
     assert st == -1 and b"null" in lib.lecb_last_error()
     st = lib.lecb_head_aggregate(1, 240, 0, 0, 1, 0, 0, 1, 1, 500, 3, 4.0, 50.0, 0)
     assert st == -1 and b"K" in lib.lecb_last_error()
+    # the fused average pool needs even H and W (checked before any CUDA call); the planning query never launches
+    st = lib.lecb_conv3x3_bf16(1, 1, 0, 1, 2, 7, 8, 64, 64, _lib.EPI_RELU | _lib.EPI_AVGPOOL2, 0)
+    assert st == -1 and b"even" in lib.lecb_last_error()
+    assert lib.lecb_conv3x3_pool_fusable(256, 223, 224, 32, 64) == 0                   # odd H
+    assert lib.lecb_conv3x3_pool_fusable(256, 224, 224, 48, 64) == 0                   # Cin not a multiple of 32
+    assert lib.lecb_conv3x3_pool_fusable(256, 224, 224, 32, 64) in (0, 1)              # 1 on a GPU box, 0 without a device
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
