@@ -155,6 +155,23 @@ def checkpoint_functions():
     return ns
 
 
+def window_transform():
+    """-> the reference `DatasetWrapperWithBlock._transform_image` (dassl/data/data_manager.py:348-492) as a plain function
+    `f(self, tfm, img0)`; it only needs `self.k_tfm`, `self.multi_scale`, torch and torchvision's functional transforms."""
+    import torch
+    import torchvision.transforms.functional as F
+    path = os.path.join(MC, "Dassl.pytorch-master", "dassl", "data", "data_manager.py")
+    with open(path, "r") as f:
+        tree = ast.parse(f.read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "DatasetWrapperWithBlock")
+    fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "_transform_image")
+    mod = ast.Module(body=[fn], type_ignores=[])
+    ast.fix_missing_locations(mod)
+    ns = {"torch": torch, "F": F, "__name__": "_lecb_ref_windows"}
+    exec(compile(mod, path, "exec"), ns)
+    return ns["_transform_image"]
+
+
 def fusion_functions(sims_scores):
     """-> namespace with the reference `fuse` / `fuse6` of gen_final_ans.py:18-71 (they read the module global
     `sims_scores`, provided here) and `adjust_predictions`, the helper nested in Caption_distill_double.test (T:611-615)."""
