@@ -182,6 +182,18 @@ int lecb_block_fuse(const float* data, const float* sims, int sims_ld, const flo
                     int K, int mode, float threshold, float weight, void* stream);
 int lecb_cooc_adjust(const float* pred, const float* P, float* out, int B, int K, float weight, void* stream);
 
+/* ---- test-time window pipeline, host side: Pillow-compatible resampling taps ----
+ * The reference resizes the image and every sliding window with PIL (transforms.py:384-394 via data_manager.py:348-492).
+ * lecb_resize_plan fills, for resizing one axis of in_size pixels to out_size, bounds int32 [out_size][2] = (first source
+ * index, tap count) and coeffs int32 [out_size][ksize] = the taps in 22-bit fixed point (zero padded), exactly as Pillow's
+ * 8-bit resampler computes them (Resample.c precompute_coeffs / normalize_coeffs_8bpc): an output byte is then
+ * clamp((2^21 + sum_t coeffs[t] * src[first + t]) >> 22, 0, 255), horizontal pass first.  HOST pointers, no CUDA call.
+ * lecb_resize_ksize returns the taps per output pixel a plan needs (> 0), or a negative status. */
+#define LECB_RESIZE_BILINEAR 0
+#define LECB_RESIZE_BICUBIC 1
+int lecb_resize_ksize(int in_size, int out_size, int filter);
+int lecb_resize_plan(int in_size, int out_size, int filter, int* bounds, int* coeffs, int ksize);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,8 @@ SIGNATURES = {
     "lecb_block_fuse": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float,
                                 c_void_p]),
     "lecb_cooc_adjust": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
+    "lecb_resize_ksize": (c_int, [c_int, c_int, c_int]),
+    "lecb_resize_plan": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_int]),
     "lecb_tn_gemm_small": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_float, c_int,
                                    c_void_p]),
 }

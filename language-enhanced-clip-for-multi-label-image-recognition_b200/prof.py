@@ -63,7 +63,7 @@ class KernelTimer:
     def __enter__(self):
         lib = _lib.lib
         for name in _lib.SIGNATURES:
-            if name in ("lecb_abi_version", "lecb_last_error", "lecb_launch_count", "lecb_conv3x3_pool_fusable"):      # host-only queries
+            if name in ("lecb_abi_version", "lecb_last_error", "lecb_launch_count", "lecb_conv3x3_pool_fusable", "lecb_resize_ksize", "lecb_resize_plan"):      # host-only
                 continue
             fn = getattr(lib, name)
             self._saved[name] = fn

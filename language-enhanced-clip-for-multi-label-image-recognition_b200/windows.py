@@ -109,3 +109,21 @@ def source_rows_cols(win: Window, h: int, w: int):
     rows = [padded_row_source(win.top + y, h, win.pad_top, win.pad_bottom) for y in range(win.height)]
     cols = [win.left + x for x in range(win.width)]
     return rows, cols
+
+
+def resize_plan(in_size: int, out_size: int, filt: str = "bicubic"):
+    """Pillow-compatible taps for resizing one axis (lecb_resize_plan, host code of liblecb.so) ->
+    (bounds int32 [out,2] = (first source index, tap count), coeffs int32 [out, ksize] in 22-bit fixed point)."""
+    import ctypes
+
+    import numpy as np
+
+    from . import _lib
+    f = {"bilinear": 0, "bicubic": 1}[filt]
+    ksize = _lib.lib.lecb_resize_ksize(in_size, out_size, f)
+    _lib.check(min(ksize, 0), "lecb_resize_ksize")
+    bounds = np.zeros((out_size, 2), dtype=np.int32)
+    coeffs = np.zeros((out_size, ksize), dtype=np.int32)
+    _lib.check(_lib.lib.lecb_resize_plan(in_size, out_size, f, bounds.ctypes.data_as(ctypes.c_void_p),
+                                         coeffs.ctypes.data_as(ctypes.c_void_p), ksize), "lecb_resize_plan")
+    return bounds, coeffs

@@ -39,3 +39,31 @@ def test_transform_matches_torchvision():
     want = tfm(Image.fromarray(img)).numpy()
     got = PR.test_transform(img, (448, 448), mean, std)
     assert np.abs(got - want).max() <= 1e-6
+
+
+@pytest.mark.parametrize("filt", ["bicubic", "bilinear"])
+@pytest.mark.parametrize("n_in,n_out", [(375, 448), (640, 224), (93, 448), (1024, 448), (224, 224), (17, 96), (500, 7), (3, 448)])
+def test_library_taps_equal_the_oracle(n_in, n_out, filt):
+    """lecb_resize_plan (host code of liblecb.so, the taps a GPU resize will consume) == oracle/pil_resize.precompute_coeffs,
+    integer for integer; and applying the library's plan along one axis reproduces Pillow's bytes."""
+    from lecb200 import windows
+    bounds, coeffs = windows.resize_plan(n_in, n_out, filt)
+    want_b, want_k = PR.precompute_coeffs(n_in, 0.0, float(n_in), n_out, filt)
+    assert coeffs.shape == want_k.shape and np.array_equal(bounds, want_b) and np.array_equal(coeffs, want_k)
+    rng = np.random.default_rng(n_in + n_out)
+    img = rng.integers(0, 256, size=(n_in, 5, 3), dtype=np.uint8)
+    acc = np.full((n_out, 5, 3), 1 << 21, dtype=np.int64)
+    for t in range(coeffs.shape[1]):
+        idx = np.minimum(bounds[:, 0] + t, n_in - 1)                 # taps past the count are zero: the index is irrelevant
+        acc += coeffs[:, t, None, None].astype(np.int64) * img[idx].astype(np.int64)
+    got = np.clip(acc >> 22, 0, 255).astype(np.uint8)
+    want = np.asarray(Image.fromarray(img).resize((5, n_out), resample=getattr(Image, filt.upper())))
+    assert np.array_equal(got, want)
+
+
+def test_library_plan_rejects_bad_arguments():
+    from lecb200 import LecbError, _lib, windows
+    assert _lib.lib.lecb_resize_ksize(0, 10, 1) < 0 and _lib.lib.lecb_resize_ksize(10, 10, 7) < 0
+    assert _lib.lib.lecb_resize_plan(10, 10, 1, 0, 0, 5) == -1 and b"null" in _lib.lib.lecb_last_error()
+    with pytest.raises(LecbError):
+        windows.resize_plan(0, 4)
