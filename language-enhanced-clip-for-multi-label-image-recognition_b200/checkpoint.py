@@ -8,12 +8,10 @@ from __future__ import annotations
 
 import os
 import os.path as osp
-import pickle
 import shutil
 import warnings
 import weakref
 from collections import OrderedDict
-from functools import partial
 
 import torch
 
@@ -53,11 +51,8 @@ def load_checkpoint(fpath):
     map_location = None if torch.cuda.is_available() else "cpu"
     try:
         return torch.load(fpath, map_location=map_location, weights_only=False)
-    except UnicodeDecodeError:
-        pk = type("_Latin1Pickle", (), {})()
-        pk.load = partial(pickle.load, encoding="latin1")
-        pk.Unpickler = partial(pickle.Unpickler, encoding="latin1")
-        return torch.load(fpath, pickle_module=pk, map_location=map_location, weights_only=False)
+    except UnicodeDecodeError:          # python2-era pickle: the reference retries with latin1 (torchtools.py:108-114)
+        return torch.load(fpath, map_location=map_location, weights_only=False, encoding="latin1")
 
 
 def load_pretrained_weights(model, weight_path):
