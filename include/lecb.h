@@ -74,6 +74,12 @@ int lecb_conv3x3_pool_fusable(int B, int H, int Wd, int Cin, int Cout);
  * ci*9+ky*3+kx; out: NHWC bf16 [B,H/2,W/2,Cout].  Cout in {8, 32, 48}. */
 int lecb_stem_conv1(const float* x, const float* w, const float* bias, void* out, int B, int H, int W, int Cout,
                     void* stream);
+/* The same convolution reading RAW uint8 pixels, NHWC [B,H,W,3] (the output of lecb_crop_resize_u8, or a host batch that
+ * skips the float conversion: 4x fewer bytes over PCIe and HBM).  ToTensor + Normalize (transforms.py:396-402: v / 255 then
+ * (x - mean) / std, fp32) is applied on the fly from a 3 x 256 table built with those very operations, so the bf16 operand
+ * equals the one lecb_stem_conv1 forms from the reference's float tensor.  mean / std: HOST float[3].  Cout = 32. */
+int lecb_stem_conv1_u8(const uint8_t* x, const float* w, const float* bias, const float* mean, const float* stdv, void* out,
+                       int B, int H, int W, int Cout, void* stream);
 
 /* ---- 2x2 average pool, NHWC bf16 (M:150 stem avgpool, M:23,35 anti-aliased stride) ---- */
 int lecb_avgpool2x2(const void* x, void* out, int B, int H, int W, int C, void* stream);
@@ -144,8 +150,45 @@ int lecb_asl_fwd_bwd(const float* logits, const float* targets, float* grad, flo
 int lecb_ranking_fwd_bwd(const float* logits, const float* targets, float* grad, float* loss, int B, int K,
                          float scale, float margin, void* stream);
 
-/* ---- caption retrieval helpers (T:444-448); the similarity matrix itself is lecb_gemm_bf16 with
- * LECB_GEMM_F16_OPERANDS run twice (hi, lo halves of the query) against the fp16 bank ---- */
+/* ---- co-occurrence weighted ranking hinge (U:95-110, called at T:842-850): pair (i, j) weighted by pair_weights[i*K + j]
+ * (fp32 [K,K]: the normalised log inverse co-occurrence the caller derives from freq_stats.pkl, U:99-102) ---- */
+int lecb_ranking_cooc_fwd_bwd(const float* logits, const float* targets, const float* pair_weights, float* grad,
+                              float* loss, int B, int K, float scale, float margin, void* stream);
+
+/* ---- EMA consistency term (T:809-813): weight * KLDivLoss(batchmean)(log_softmax(logits), softmax(logits_target)) and
+ * its gradient w.r.t. logits, weight * (softmax(logits) - softmax(logits_target)) / B; the target is a constant ---- */
+int lecb_kl_softmax_fwd_bwd(const float* logits, const float* logits_target, float* grad, float* loss, int64_t B, int K,
+                            float weight, void* stream);
+
+/* ---- multi-tensor updates over the prompt-learner parameter list: HOST arrays of `count` (<= 16) device pointers and
+ * element counts, one launch each ----
+ * lecb_ema_update: twin_i <- momentum * twin_i + (1 - momentum) * live_i                     (_momentum_update, T:554-559)
+ * lecb_pack_f32: flat <- concat_i src_i (a NULL source contributes zeros: a parameter without gradient, what DDP's
+ *   find_unused_parameters=True covers at T:787); lecb_unpack_scale_f32: dst_i <- scale * its slice of flat — the flat
+ *   gradient bucket that is all-reduced once per step (T:786-787)
+ * lecb_sgd_step: p_i <- p_i - lr * (buf_i <- momentum * buf_i + grad_scale * flat_i + weight_decay * p_i), torch.optim.SGD
+ *   with zero-initialised momentum buffers (the optimiser built at T:773) */
+int lecb_ema_update(const float* const* live, float* const* twin, const long long* n, int count, float momentum,
+                    void* stream);
+int lecb_pack_f32(const float* const* src, const long long* n, int count, float* flat, void* stream);
+int lecb_unpack_scale_f32(const float* flat, float* const* dst, const long long* n, int count, float scale, void* stream);
+int lecb_sgd_step(const float* flat_grad, float* const* params, float* const* momentum_buf, const long long* n, int count,
+                  float grad_scale, float lr, float momentum, float weight_decay, void* stream);
+
+/* ---- caption retrieval (T:444-448) ----
+ * Fused path: lecb_split_f16_hilo writes the exact fp16 pair q = hi + lo of the fp32 queries as one [B, 2D] operand;
+ * lecb_gemm_topk10 multiplies both halves against the fp16 bank [N, D] on tcgen05 (each bank tile is staged once per
+ * query block and used for both halves) and keeps, per query row and per CTA, the ten largest similarities in registers:
+ * part_val / part_idx [B][slots][10] (slots >= *slots_used = the grid size; reset inside the call) — the [B, N] fp32
+ * similarity matrix of T:445 (225 MB at 256 x 220 000) is never written; lecb_topk10_merge reduces the partial lists to the
+ * row's top-10 (descending; of equal values the lower index first); lecb_gather_mean10 averages the selected rows (T:447).
+ * N is arbitrary (>= 10).  The unfused helpers (lecb_split_f16 + two lecb_gemm_bf16 with LECB_GEMM_F16_OPERANDS into an
+ * explicit similarity matrix + lecb_topk10) remain as the cross-check. */
+int lecb_split_f16_hilo(const float* x, void* out, int64_t rows, int D, void* stream);
+int lecb_gemm_topk10(const void* A_hilo, const void* bank, int64_t M, int N, int K, float* part_val, int* part_idx, int slots,
+                     int* slots_used, void* stream);
+int lecb_topk10_merge(const float* part_val, const int* part_idx, int slots, int B, float* out_val, int* out_idx,
+                      void* stream);
 int lecb_split_f16(const float* x, void* hi, void* lo, int64_t n, void* stream);   /* x = hi + lo, fp16 each */
 int lecb_topk10(const float* sim, int64_t ld, int B, int N, float* out_val, int* out_idx, void* stream);
 int lecb_gather_mean10(const void* bank, int bank_is_f16, const int* idx, float* out, int B, int D, void* stream);
@@ -193,6 +236,21 @@ int lecb_cooc_adjust(const float* pred, const float* P, float* out, int B, int K
 #define LECB_RESIZE_BICUBIC 1
 int lecb_resize_ksize(int in_size, int out_size, int filter);
 int lecb_resize_plan(int in_size, int out_size, int filter, int* bounds, int* coeffs, int ksize);
+
+/* ---- test-time window pipeline, device side: crop + Pillow-compatible resize + ToTensor + Normalize of `n` windows of
+ * ONE decoded image (data_manager.py:348-492 `_transform_image` + transforms.py:379-411), bit-exact against Pillow ----
+ * wins: HOST int32 [n][6] = (top, left, height, width, pad_top, pad_bottom) per window (lecb200.windows.Window: group-1
+ *   rows counted through the reflect padding / crop of the image, F.pad quirk included).
+ * lecb_window_plan_size -> ints of the plan blob and bytes of the [height, S, 3] intermediates;
+ * lecb_window_plan fills the HOST blob (window records + both axes' lecb_resize_plan arrays); the caller uploads it.
+ * lecb_crop_resize_u8: img uint8 [H,W,3], plan and tmp in device memory -> out_u8 [n,S,S,3] (NHWC, the operand of
+ *   lecb_stem_conv1_u8) and / or out_f32 [n,3,S,S] = ((v / 255) - mean) / std (the reference's tensor); mean / std: HOST
+ *   float[3].  Two launches (horizontal pass rounded to uint8, then vertical, like Resample.c). */
+int lecb_window_plan_size(const int* wins, int n, int H, int W, int S, int filter, long long* plan_ints,
+                          long long* tmp_bytes);
+int lecb_window_plan(const int* wins, int n, int H, int W, int S, int filter, int* plan, long long plan_ints);
+int lecb_crop_resize_u8(const uint8_t* img, int H, int W, const int* plan, int n, int S, uint8_t* tmp, uint8_t* out_u8,
+                        float* out_f32, const float* mean, const float* stdv, void* stream);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,7 @@ SIGNATURES = {
                                   c_uint, c_void_p]),
     "lecb_conv3x3_pool_fusable": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "lecb_stem_conv1": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "lecb_stem_conv1_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "lecb_avgpool2x2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "lecb_token_mean": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "lecb_l2norm_rows": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_void_p]),
@@ -42,6 +43,20 @@ SIGNATURES = {
                                  c_float, c_float, c_float, c_int, c_void_p]),
     "lecb_ranking_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float,
                                      c_void_p]),
+    "lecb_ranking_cooc_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float,
+                                          c_void_p]),
+    "lecb_kl_softmax_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_float, c_void_p]),
+    "lecb_ema_update": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p]),
+    "lecb_pack_f32": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "lecb_unpack_scale_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p]),
+    "lecb_sgd_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_float, c_void_p]),
+    "lecb_split_f16_hilo": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p]),
+    "lecb_gemm_topk10": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "lecb_topk10_merge": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "lecb_window_plan_size": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "lecb_window_plan": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, C.c_longlong]),
+    "lecb_crop_resize_u8": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p]),
     "lecb_split_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
     "lecb_topk10": (c_int, [c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "lecb_gather_mean10": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),

@@ -264,7 +264,8 @@ extern "C" int lecb_attn_causal_bwd(const void* qkv, const void* dout, void* dqk
   LECB_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0,
                  "lecb_attn_causal_bwd: operands must be 16-byte aligned");
-  static bool configured = false;
+  static DeviceOnce once;                    // the attribute is per device: one flag per device ordinal
+  bool& configured = once.flag();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmemBytes);
     if (e != cudaSuccess) return fail(LECB_ERR_CUDA, "cudaFuncSetAttribute(attn bwd smem=%d): %s", kAbSmemBytes, cudaGetErrorString(e));

@@ -380,7 +380,8 @@ extern "C" int lecb_attn_fwd(const void* qkv, void* out, int B, int T, int W, in
   LECB_CHECK_ARG(B <= 65535 && heads <= 65535, "lecb_attn_fwd: grid too large");
   LECB_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                  "lecb_attn_fwd: operands must be 16-byte aligned");
-  static bool configured = false;
+  static DeviceOnce once;                    // the attribute is per device: one flag per device ordinal
+  bool& configured = once.flag();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes);
     if (e != cudaSuccess) return fail(LECB_ERR_CUDA, "cudaFuncSetAttribute(attn smem=%d): %s", kAtSmemBytes, cudaGetErrorString(e));

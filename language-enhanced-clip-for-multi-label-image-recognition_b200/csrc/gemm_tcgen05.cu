@@ -85,6 +85,12 @@ struct GemmParams {
                       // L2 -> SM once per 256 pixels; the epilogue / DMA still see a sequence of 128-row tiles
   int pool;           // halo mode only: 2x2 average pool (M:147, M:27) fused into the epilogue — the four pixels of a window are
                       // lanes l, l^1, l^tw, l^tw^1 of one epilogue warp; the staged block is the (th/2 x tw/2) pooled patch
+  int hilo;           // A is [M, 2K] = [hi | lo] (an exact fp16 split of an fp32 query, T:445): k block kb multiplies columns
+                      // (kb & 1) * K + (kb >> 1) * BK of A with k block kb >> 1 of W, so both halves accumulate against the
+                      // same W tile (its second fetch is an L2 hit) and the fp32 product needs no second pass over W
+  float* topk_val;    // fused per-row top-10 epilogue (caption retrieval, T:446): instead of storing the tile, every epilogue
+  int* topk_idx;      // thread keeps the 10 largest values of its row over the n tiles this CTA processes and writes them
+  int topk_slots;     // to slot blockIdx.x of [rows][topk_slots][10]; a merge kernel finishes (retrieval.cu)
   int halo_single;    // tw == 8: ONE (th+2) x (tw+2) halo copy per stage.  The swizzle of a K-major operand is a function of
                       // the absolute shared-memory address bits (measured: a descriptor may start on any 128-byte row
                       // with base_offset 0), so tap (ky,kx) is just start = copy + (ky*(tw+2) + kx) * 128 with an
@@ -254,9 +260,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tma_load_im2col_4d(&tmA, &full[stage], sA_ring + stage * a_stride + Cfg::kABytes, cb * BK, pw1 - 1, ph1 - 1,
                                  pn1, static_cast<uint16_t>(kx), static_cast<uint16_t>(ky));
           } else {
-            tma_load_2d(&tmA, &full[stage], sA_ring + stage * a_stride, kb * BK, m_blk * kTileM);
+            const int a_col = p.hilo ? (kb & 1) * (p.num_kb >> 1) * BK + (kb >> 1) * BK : kb * BK;
+            tma_load_2d(&tmA, &full[stage], sA_ring + stage * a_stride, a_col, m_blk * kTileM);
           }
-          if (!p.b_resident) tma_load_2d(&tmB, &full[stage], sB + stage * Cfg::kBBytes, kb * BK, n_blk * BN);
+          if (!p.b_resident)
+            tma_load_2d(&tmB, &full[stage], sB + stage * Cfg::kBBytes, (p.hilo ? (kb >> 1) : kb) * BK, n_blk * BN);
           if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
@@ -419,6 +427,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t erow = static_cast<uint32_t>(quarter * 32 + lane);   // row inside the tile == TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     int bias_n_blk = -1;
+    // fused top-10 state (p.topk_val != nullptr): the thread's row keeps its ten best (value, column) pairs, sorted
+    float tk_val[10];
+    int tk_idx[10];
+    int tk_m_blk = -1;
+    auto topk_flush = [&](int mb) {
+      const int64_t row = static_cast<int64_t>(mb) * kTileM + erow;
+      if (row < p.M) {
+        float* pv = p.topk_val + (row * p.topk_slots + blockIdx.x) * 10;
+        int* pi = p.topk_idx + (row * p.topk_slots + blockIdx.x) * 10;
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+          pv[j] = tk_val[j];
+          pi[j] = tk_idx[j];
+        }
+      }
+    };
     for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq) {
       int m_blk, n_blk;
       tile_coords(tile_seq, m_blk, n_blk);
@@ -632,6 +656,47 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           __syncwarp();
           if (lane == 0) mbar_arrive(&cfull[gblk % kNBar]);
         }
+      } else if (p.topk_val != nullptr) {
+        // ---- fused per-row top-10 (caption retrieval): no output tile at all ----
+        if (group != 0) continue;
+        if (m_blk != tk_m_blk) {                  // tiles arrive in increasing order: the m block changes at most once or twice
+          if (tk_m_blk >= 0) topk_flush(tk_m_blk);
+          tk_m_blk = m_blk;
+#pragma unroll
+          for (int j = 0; j < 10; ++j) {
+            tk_val[j] = -INFINITY;
+            tk_idx[j] = -1;
+          }
+        }
+        mbar_wait(&tfull[tile_seq % kTFull], tf_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + lane_base + static_cast<uint32_t>(acc * BN + c * 32), r);
+          tmem_ld_wait();
+          const int n0 = n_blk * BN + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float v = __uint_as_float(r[j]);
+            if (v > tk_val[9] && n0 + j < p.N) {           // strict: of equal values the lower index (seen first) stays
+              int pos = 9;
+#pragma unroll
+              for (int q = 8; q >= 0; --q) {
+                if (v > tk_val[q]) {
+                  tk_val[q + 1] = tk_val[q];
+                  tk_idx[q + 1] = tk_idx[q];
+                  pos = q;
+                }
+              }
+              tk_val[pos] = v;
+              tk_idx[pos] = n0 + j;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
       } else {
         if (group != 0) continue;                 // direct fp32 stores: one group is plenty (small GEMMs)
         mbar_wait(&tfull[tile_seq % kTFull], tf_phase);
@@ -704,6 +769,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       if (p.row_sumsq != nullptr && row_ok) atomicAdd(p.row_sumsq + row, ssq);
     }
+    if (p.topk_val != nullptr && group == 0 && tk_m_blk >= 0) topk_flush(tk_m_blk);
   }
 
   tc_fence_before();
@@ -718,7 +784,8 @@ template <int BN, int BK, int NB, bool kConv>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, BK, NB>;
   constexpr bool kPairable = kConv && BN == 128 && BK == 64 && NB == 2;      // the one instantiation of MT = 2
-  static bool configured = false;
+  static DeviceOnce once;                    // the attribute is per device: one flag per device ordinal
+  bool& configured = once.flag();
   auto kern = gemm_kernel<BN, BK, NB, kConv, 1>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -734,6 +801,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
   // fp32 output is staged too (32-column blocks) when the tile is wide enough and the residual, if any, is fp32
   p.out_f32 = (want_f32 && BN >= 64 && (p.residual == nullptr || (p.flags & LECB_EPI_RES_F32))) ? 1 : 0;
   p.staged = (!want_f32 || p.out_f32) ? 1 : 0;
+  if (p.topk_val != nullptr) p.staged = p.out_f32 = 0;      // nothing is stored: the direct-path barrier counts apply
   p.cblocks = p.out_f32 ? BN / 32 : Cfg::kCBlocks;
   if (p.staged) {
     const uint32_t ccols = p.out_f32 ? 32 : Cfg::kCCols;
@@ -907,6 +975,61 @@ extern "C" int lecb_gemm_bf16(const void* A, const void* W, const float* bias, c
   int st = encode_tiled_2d(&tmA, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), kTileM, BK);
   if (st) return st;
   st = encode_tiled_2d(&tmB, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), BN, BK);
+  if (st) return st;
+  return dispatch<false>(BN, BK, tmA, tmB, p, static_cast<cudaStream_t>(stream));
+}
+
+// Similarity GEMM with the per-row top-10 fused into the epilogue (caption retrieval, T:444-446):
+//   sim[m, n] = <q_m, bank_n> with q given as an exact fp16 pair q = hi + lo (A = [hi | lo], fp16 [M, 2K]) against the
+//   fp16 bank [N, K]; instead of the [M, N] matrix (225 MB at 256 x 220 000) each CTA writes the ten best (value, index)
+//   pairs of every row over the n tiles it processed to slot blockIdx.x of part_val / part_idx [M][slots][10]
+//   (slots >= the grid size returned through *slots_used; every slot is first reset to -inf / -1 by a fill kernel here,
+//   so slots a CTA never touches for a row block drop out of the merge).
+namespace lecb {
+__global__ void __launch_bounds__(256) topk_partial_fill_kernel(float* __restrict__ v, int* __restrict__ i, int64_t n) {
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    v[t] = -INFINITY;
+    i[t] = -1;
+  }
+}
+}  // namespace lecb
+
+extern "C" int lecb_gemm_topk10(const void* A_hilo, const void* bank, int64_t M, int N, int K, float* part_val, int* part_idx,
+                                int slots, int* slots_used, void* stream) {
+  LECB_CHECK_ARG(A_hilo && bank && part_val && part_idx, "lecb_gemm_topk10: null pointer");
+  LECB_CHECK_ARG(M > 0 && N >= 10 && K > 0 && K % 64 == 0, "lecb_gemm_topk10: need M > 0, N >= 10, K %% 64 == 0 (M=%lld N=%d K=%d)",
+                 (long long)M, N, K);
+  LECB_CHECK_ARG((reinterpret_cast<uintptr_t>(A_hilo) & 15) == 0 && (reinterpret_cast<uintptr_t>(bank) & 15) == 0,
+                 "lecb_gemm_topk10: operands must be 16-byte aligned");
+  const int sms = sm_count();
+  if (sms <= 0) return fail(LECB_ERR_CUDA, "no CUDA device");
+  const int BN = 256, BK = 64;
+  GemmParams p{};
+  p.mt = 1;
+  p.M = M;
+  p.N = N;
+  p.hilo = 1;
+  p.num_kb = 2 * (K / BK);
+  p.num_m_tiles = static_cast<int>((M + kTileM - 1) / kTileM);
+  p.num_n_tiles = (N + BN - 1) / BN;
+  p.flags = LECB_GEMM_F16_OPERANDS;
+  p.topk_val = part_val;
+  p.topk_idx = part_idx;
+  p.topk_slots = slots;
+  const int64_t tiles = static_cast<int64_t>(p.num_m_tiles) * p.num_n_tiles;
+  const int grid = static_cast<int>(tiles < sms ? tiles : sms);
+  if (slots_used) *slots_used = grid;
+  LECB_CHECK_ARG(slots >= grid, "lecb_gemm_topk10: %d partial slots, the launch needs %d", slots, grid);
+  CUtensorMap tmA, tmB;
+  int st = encode_tiled_2d(&tmA, A_hilo, static_cast<uint64_t>(M), static_cast<uint64_t>(2) * K, kTileM, BK);
+  if (st) return st;
+  st = encode_tiled_2d(&tmB, bank, static_cast<uint64_t>(N), static_cast<uint64_t>(K), BN, BK);
+  if (st) return st;
+  const int64_t nfill = M * slots * 10;
+  topk_partial_fill_kernel<<<static_cast<unsigned>((nfill + 255) / 256 < 1024 ? (nfill + 255) / 256 : 1024), 256, 0,
+                             static_cast<cudaStream_t>(stream)>>>(part_val, part_idx, nfill);
+  count_launch();
+  st = check_launch("topk_partial_fill_kernel");
   if (st) return st;
   return dispatch<false>(BN, BK, tmA, tmB, p, static_cast<cudaStream_t>(stream));
 }

@@ -13,6 +13,22 @@ void count_launch(unsigned n = 1);
 int sm_count();                                       // SMs of the current device (cached per device)
 int check_launch(const char* what);                   // cudaGetLastError -> status
 
+// cudaFuncSetAttribute is a per-DEVICE setting: a `static DeviceOnce once; bool& done = once.flag();` at the call site keeps
+// one "configured" flag per device ordinal (a process that drives several GPUs configures each of them once).  A race
+// between host threads only repeats the idempotent attribute call.
+struct DeviceOnce {
+  bool done[64] = {};
+  bool scratch = false;
+  bool& flag() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+      scratch = false;
+      return scratch;
+    }
+    return done[dev];
+  }
+};
+
 // cuTensorMapEncode* resolved at run time through cudaGetDriverEntryPoint (no link-time libcuda).
 // 2-D row-major bf16 matrix [rows, cols]; box = box_rows x box_cols elements; swizzle = box_cols*2 bytes.
 int encode_tiled_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,

@@ -94,6 +94,74 @@ topk10_kernel(const float* __restrict__ sim, int64_t ld, int N, float* __restric
   }
 }
 
+// Merge of the per-CTA partial top-10 lists written by lecb_gemm_topk10: one CTA per query row, candidates
+// [slots][10] (each slot sorted descending, unused entries -inf / -1) -> the row's global top-10, descending; of equal
+// values the lower bank index wins.
+__global__ void __launch_bounds__(256)
+topk10_merge_kernel(const float* __restrict__ part_val, const int* __restrict__ part_idx, int slots, float* __restrict__ out_val,
+                    int* __restrict__ out_idx) {
+  extern __shared__ uint8_t sm_raw[];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const int n = slots * kTopK;
+  float* c_val = reinterpret_cast<float*>(sm_raw);
+  int* c_idx = reinterpret_cast<int*>(c_val + n);
+  __shared__ float r_val[8];
+  __shared__ int r_pos[8];
+  for (int i = t; i < n; i += 256) {
+    c_val[i] = part_val[static_cast<int64_t>(b) * n + i];
+    c_idx[i] = part_idx[static_cast<int64_t>(b) * n + i];
+  }
+  __syncthreads();
+  for (int r = 0; r < kTopK; ++r) {
+    float v = -INFINITY;
+    int pos = -1, id = 0x7fffffff;
+    for (int i = t; i < n; i += 256) {
+      const float cv = c_val[i];
+      const int ci = c_idx[i];
+      if (ci >= 0 && (cv > v || (cv == v && ci < id))) {
+        v = cv;
+        pos = i;
+        id = ci;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int op = __shfl_xor_sync(0xffffffffu, pos, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, id, o);
+      if (op >= 0 && (pos < 0 || ov > v || (ov == v && oi < id))) {
+        v = ov;
+        pos = op;
+        id = oi;
+      }
+    }
+    if ((t & 31) == 0) {
+      r_val[t >> 5] = v;
+      r_pos[t >> 5] = pos;
+    }
+    __syncthreads();
+    if (t == 0) {
+      float bv = -INFINITY;
+      int bp = -1, bi = 0x7fffffff;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const int wp = r_pos[w];
+        if (wp < 0) continue;
+        const int wi = c_idx[wp];
+        if (bp < 0 || r_val[w] > bv || (r_val[w] == bv && wi < bi)) {
+          bv = r_val[w];
+          bp = wp;
+          bi = wi;
+        }
+      }
+      out_val[b * kTopK + r] = bv;
+      out_idx[b * kTopK + r] = bp >= 0 ? bi : -1;
+      if (bp >= 0) c_idx[bp] = -1;                // taken
+    }
+    __syncthreads();
+  }
+}
+
 // g_add[b,:] = mean of the 10 selected bank rows, rounded to the bank's dtype like the reference's
 // `caption_text_feats[idx].view(-1, topk, D).mean(1)` on an fp16 tensor.
 template <typename TBank>
@@ -118,6 +186,28 @@ gather_mean_kernel(const TBank* __restrict__ bank, const int* __restrict__ idx, 
 
 using namespace lecb;
 
+// [rows, 2D] = [hi | lo]: the A operand of lecb_gemm_topk10
+__global__ void __launch_bounds__(256)
+split_f16_hilo_kernel(const float* __restrict__ x, __half* __restrict__ out, int64_t rows, int D) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * D) return;
+  const int64_t r = i / D;
+  const int d = static_cast<int>(i - r * D);
+  const float v = x[i];
+  const __half h = __float2half_rn(v);
+  out[r * 2 * D + d] = h;
+  out[r * 2 * D + D + d] = __float2half_rn(v - __half2float(h));
+}
+
+extern "C" int lecb_split_f16_hilo(const float* x, void* out, int64_t rows, int D, void* stream) {
+  LECB_CHECK_ARG(x && out && rows > 0 && D > 0, "lecb_split_f16_hilo: bad argument");
+  const int64_t n = rows * D;
+  split_f16_hilo_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__half*>(out), rows, D);
+  count_launch();
+  return check_launch("split_f16_hilo_kernel");
+}
+
 extern "C" int lecb_split_f16(const float* x, void* hi, void* lo, int64_t n, void* stream) {
   LECB_CHECK_ARG(x && hi && lo && n > 0, "lecb_split_f16: bad argument");
   split_f16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -132,6 +222,26 @@ extern "C" int lecb_topk10(const float* sim, int64_t ld, int B, int N, float* ou
   topk10_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(sim, ld, N, out_val, out_idx);
   count_launch();
   return check_launch("topk10_kernel");
+}
+
+extern "C" int lecb_topk10_merge(const float* part_val, const int* part_idx, int slots, int B, float* out_val, int* out_idx,
+                                 void* stream) {
+  LECB_CHECK_ARG(part_val && part_idx && out_val && out_idx, "lecb_topk10_merge: null pointer");
+  LECB_CHECK_ARG(B > 0 && slots > 0 && slots <= 1024, "lecb_topk10_merge: need 0 < slots <= 1024 (slots=%d)", slots);
+  const size_t smem = static_cast<size_t>(slots) * kTopK * 8;
+  static bool big_smem[64] = {};
+  if (smem > 48 * 1024) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !big_smem[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(topk10_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * kTopK * 8);
+      if (e != cudaSuccess) return fail(LECB_ERR_CUDA, "lecb_topk10_merge: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      big_smem[dev] = true;
+    }
+  }
+  topk10_merge_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(part_val, part_idx, slots, out_val, out_idx);
+  count_launch();
+  return check_launch("topk10_merge_kernel");
 }
 
 extern "C" int lecb_gather_mean10(const void* bank, int bank_is_f16, const int* idx, float* out, int B, int D,

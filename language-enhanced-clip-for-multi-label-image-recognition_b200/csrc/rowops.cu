@@ -7,8 +7,8 @@
 
 namespace lecb {
 
-int launch_stem_conv1_tc(const float* x, const float* w, const float* bias, void* out, int B, int H, int W,
-                         cudaStream_t s);      // stem_tc.cu
+int launch_stem_conv1_tc(const void* x, int x_is_u8, const float* w, const float* bias, const float* mean, const float* stdv,
+                         void* out, int B, int H, int W, cudaStream_t s);      // stem_tc.cu
 
 // ------------------------------------------------------------------------------------------------
 // Stem conv1: NCHW fp32 [B,3,H,W] -> NHWC bf16 [B,H/2,W/2,CO], 3x3 stride 2 pad 1, folded BN + ReLU.
@@ -282,7 +282,7 @@ extern "C" int lecb_stem_conv1(const float* x, const float* w, const float* bias
   const unsigned grid = static_cast<unsigned>((total + 127) / 128);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (Cout == 32 && !getenv("LECB_STEM_CUDA_CORES"))      // the real CLIP ResNets (width 64): tensor-core implicit GEMM
-    return launch_stem_conv1_tc(x, w, bias, out, B, H, W, s);
+    return launch_stem_conv1_tc(x, 0, w, bias, nullptr, nullptr, out, B, H, W, s);
   if (Cout == 32)
     stem_conv1_kernel<32><<<grid, 128, 0, s>>>(x, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W);
   else if (Cout == 48)
@@ -293,6 +293,15 @@ extern "C" int lecb_stem_conv1(const float* x, const float* w, const float* bias
     return fail(LECB_ERR_UNSUPPORTED, "lecb_stem_conv1: Cout=%d (supported: 8, 32, 48)", Cout);
   count_launch();
   return check_launch("stem_conv1_kernel");
+}
+
+extern "C" int lecb_stem_conv1_u8(const uint8_t* x, const float* w, const float* bias, const float* mean, const float* stdv,
+                                  void* out, int B, int H, int W, int Cout, void* stream) {
+  LECB_CHECK_ARG(x && w && bias && out && mean && stdv, "lecb_stem_conv1_u8: null pointer");
+  LECB_CHECK_ARG(B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "lecb_stem_conv1_u8: H, W must be even and positive");
+  LECB_CHECK_ARG(stdv[0] != 0.f && stdv[1] != 0.f && stdv[2] != 0.f, "lecb_stem_conv1_u8: zero std");
+  if (Cout != 32) return fail(LECB_ERR_UNSUPPORTED, "lecb_stem_conv1_u8: Cout=%d (only the CLIP ResNet stem width 32)", Cout);
+  return launch_stem_conv1_tc(x, 1, w, bias, mean, stdv, out, B, H, W, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int lecb_avgpool2x2(const void* x, void* out, int B, int H, int W, int C, void* stream) {

@@ -1,12 +1,20 @@
 // Stem conv1 (3x3, stride 2, pad 1, 3 -> 32 channels, folded BN + ReLU; M:144-145,174-175) on tcgen05.
 //
-// The CUDA-core version is bound by fp32 FMA issue (27 x 32 FMAs per output pixel); as an implicit GEMM the
-// arithmetic is trivial (M = pixels, N = 32, K = 27 padded to 32) and the kernel becomes a streaming transform:
-// each thread gathers the 27 input values of one output pixel from the NCHW fp32 image, packs them to bf16 and
-// writes one 64-byte im2col row of a 128 x 32 K-major (64B-swizzled) A tile in shared memory; two tcgen05.mma
-// (M=128, N=32, K=16) against the 32 x 32 weight tile produce the 128 x 32 outputs in TMEM; the same thread reads
-// its pixel's 32 channels back (tcgen05.ld), adds the bias, applies ReLU and stores 64 contiguous bytes of the
-// NHWC bf16 output.  Persistent CTAs (weights, TMEM and barrier set up once), several CTAs per SM for overlap.
+// As an implicit GEMM the arithmetic is trivial (M = pixels, N = 32, K = 27 padded to 32): the kernel is a streaming
+// transform bound by how it touches memory.  Round 1 gathered the 27 taps of every output pixel with scalar loads
+// straight from the NCHW fp32 image (0.37 of HBM peak: every input value was requested 2.25 times, as 4-byte sectors).
+// Now a CTA owns an 8 x 16 patch of output pixels, stages the 17 x 33 x 3 input patch it needs ONCE through shared
+// memory (coalesced row segments, converted to bf16 on the way, conv padding = zeros), each thread then builds the
+// 64-byte im2col row of its pixel from shared memory, two tcgen05.mma (M=128, N=32, K=16) against the 32 x 32 weight tile
+// produce the outputs in TMEM and the same thread stores its pixel's 32 channels (64 contiguous bytes, NHWC bf16).
+//
+// Two input formats:
+//   * fp32 NCHW, already normalised — the tensor the reference's DataLoader hands to DenseCLIP.forward (T:401-403);
+//   * uint8 NHWC raw pixels — what the test-time window kernel (window_resize.cu) produces and what a host that skips
+//     the float conversion uploads (4x fewer bytes over PCIe and HBM).  ToTensor + Normalize (transforms.py:396-402:
+//     v / 255, then (x - mean) / std in fp32) is applied on the fly through a 3 x 256 entry table built with exactly
+//     those fp32 operations, so the bf16 operand is bit-identical to converting the reference's float tensor.
+// K order inside a row: k = ky*9 + kx*3 + ci (the patch is pixel-interleaved), weights permuted to match.
 #include "lecb_common.cuh"
 #include "lecb_host.h"
 
@@ -14,26 +22,47 @@ namespace lecb {
 
 constexpr int kStemCo = 32;
 constexpr int kStemK = 32;          // 27 taps + 5 zero columns
+constexpr int kTileH = 8, kTileW = 16;                    // output pixels per CTA tile (128 = TMEM lanes)
+constexpr int kPatchH = 2 * kTileH + 1, kPatchW = 2 * kTileW + 1;      // 17 x 33 input pixels
+constexpr int kPatchPitch = 100;                          // bf16 elements per patch row (33 * 3 = 99, even pitch: 4-byte rows)
 
+struct StemNorm {
+  float mean[3], std[3];
+};
+
+template <bool kU8>
 __global__ void __launch_bounds__(128)
-stem_conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w27, const float* __restrict__ bias,
-                     __nv_bfloat16* __restrict__ out, int B, int H, int W, int num_tiles) {
+stem_conv1_tc_kernel(const void* __restrict__ xin, const float* __restrict__ w27, const float* __restrict__ bias,
+                     __nv_bfloat16* __restrict__ out, int B, int H, int W, int tiles_x, int tiles_y, int num_tiles, StemNorm nrm) {
   __shared__ __align__(1024) uint8_t sA[128 * kStemK * 2];        // 8 KB, rows of 64 bytes
   __shared__ __align__(1024) uint8_t sW[kStemCo * kStemK * 2];    // 2 KB
+  __shared__ __align__(16) __nv_bfloat16 patch[kPatchH * kPatchPitch];
+  __shared__ __nv_bfloat16 lut[kU8 ? 3 * 256 : 1];
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ float sbias[kStemCo];
   const int t = threadIdx.x;
   const int warp = t >> 5;
   const int HO = H / 2, WO = W / 2;
-  const int64_t total = static_cast<int64_t>(B) * HO * WO;
 
-  // weights: W[co][k] = w27[k][co] (k = ci*9 + ky*3 + kx), K-major rows of 64 bytes, 64B swizzle
+  // weights: sW[co][k], k = ky*9 + kx*3 + ci  <-  w27[(ci*9 + ky*3 + kx)][co]; K-major rows of 64 bytes, 64B swizzle
   for (int i = t; i < kStemCo * kStemK; i += 128) {
     const int co = i / kStemK, k = i % kStemK;
-    const float v = k < 27 ? w27[k * kStemCo + co] : 0.f;
+    float v = 0.f;
+    if (k < 27) {
+      const int ky = k / 9, kx = (k % 9) / 3, ci = k % 3;
+      v = w27[(ci * 9 + ky * 3 + kx) * kStemCo + co];
+    }
     const uint32_t off = swizzled_chunk_offset(co, k / 8, 64) + (k % 8) * 2;
     *reinterpret_cast<__nv_bfloat16*>(sW + off) = __float2bfloat16(v);
+  }
+  if (kU8) {
+    // ToTensor: byte / 255 (fp32 division), Normalize: (x - mean) / std, both correctly rounded like ATen's CPU ops
+    for (int i = t; i < 3 * 256; i += 128) {
+      const int c = i >> 8;
+      const float v = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(i & 255), 255.0f), nrm.mean[c]), nrm.std[c]);
+      lut[i] = __float2bfloat16(v);
+    }
   }
   if (t < kStemCo) sbias[t] = bias[t];
   if (t == 0) {
@@ -51,46 +80,62 @@ stem_conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w27,
   const uint32_t tmem_base = tmem_slot;
   const uint32_t idesc = make_idesc_f16(kStemCo, true);
   uint32_t phase = 0;
+  const int py = t / kTileW, px = t % kTileW;
 
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int64_t pix = static_cast<int64_t>(tile) * 128 + t;
-    const bool live = pix < total;
-    // ---- gather the 3x3x3 patch of this output pixel -> one bf16 im2col row ----
-    float v[kStemK];
-#pragma unroll
-    for (int k = 27; k < kStemK; ++k) v[k] = 0.f;
-    if (live) {
-      const int wo = static_cast<int>(pix % WO);
-      const int ho = static_cast<int>((pix / WO) % HO);
-      const int b = static_cast<int>(pix / (static_cast<int64_t>(WO) * HO));
-      const int wi0 = 2 * wo - 1, hi0 = 2 * ho - 1;
-#pragma unroll
-      for (int ci = 0; ci < 3; ++ci) {
-        const float* xp = x + (static_cast<int64_t>(b) * 3 + ci) * H * W;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          const int hi = hi0 + ky;
-          const bool hok = hi >= 0 && hi < H;
-          const float* rp = xp + static_cast<int64_t>(hi) * W + wi0;
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const int wi = wi0 + kx;
-            v[ci * 9 + ky * 3 + kx] = (hok && wi >= 0 && wi < W) ? __ldg(rp + kx) : 0.f;
-          }
-        }
+    const int tx = tile % tiles_x;
+    const int ty = (tile / tiles_x) % tiles_y;
+    const int b = tile / (tiles_x * tiles_y);
+    const int ho0 = ty * kTileH, wo0 = tx * kTileW;
+    const int hi0 = 2 * ho0 - 1, wi0 = 2 * wo0 - 1;
+    // ---- stage the input patch: [17][33][3] bf16, zeros outside the image (conv padding, ragged tiles) ----
+    if (kU8) {
+      const uint8_t* x = static_cast<const uint8_t*>(xin) + static_cast<int64_t>(b) * H * W * 3;
+      for (int i = t; i < kPatchH * kPatchW * 3; i += 128) {
+        const int r = i / (kPatchW * 3), cc = i - r * (kPatchW * 3);        // cc = col * 3 + ci: contiguous bytes of one row
+        const int c = cc / 3, ci = cc - c * 3;
+        const int hi = hi0 + r, wi = wi0 + c;
+        __nv_bfloat16 v = __float2bfloat16(0.f);
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = lut[ci * 256 + __ldg(x + (static_cast<int64_t>(hi) * W + wi) * 3 + ci)];
+        patch[r * kPatchPitch + cc] = v;
       }
     } else {
-#pragma unroll
-      for (int k = 0; k < 27; ++k) v[k] = 0.f;
+      const float* x = static_cast<const float*>(xin) + static_cast<int64_t>(b) * 3 * H * W;
+      for (int i = t; i < 3 * kPatchH * kPatchW; i += 128) {
+        const int ci = i / (kPatchH * kPatchW), rc = i - ci * (kPatchH * kPatchW);
+        const int r = rc / kPatchW, c = rc - r * kPatchW;                  // c fastest: coalesced row segments per plane
+        const int hi = hi0 + r, wi = wi0 + c;
+        float v = 0.f;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = __ldg(x + (static_cast<int64_t>(ci) * H + hi) * W + wi);
+        patch[r * kPatchPitch + c * 3 + ci] = __float2bfloat16(v);
+      }
     }
+    __syncthreads();
+    // ---- this thread's im2col row: three runs of 9 consecutive patch elements (ky = 0, 1, 2) ----
+    {
+      uint16_t v[kStemK];
 #pragma unroll
-    for (int c = 0; c < kStemK / 8; ++c) {
-      uint4 u;
-      u.x = pack_bf16(v[c * 8 + 0], v[c * 8 + 1]);
-      u.y = pack_bf16(v[c * 8 + 2], v[c * 8 + 3]);
-      u.z = pack_bf16(v[c * 8 + 4], v[c * 8 + 5]);
-      u.w = pack_bf16(v[c * 8 + 6], v[c * 8 + 7]);
-      *reinterpret_cast<uint4*>(sA + swizzled_chunk_offset(t, c, 64)) = u;
+      for (int k = 27; k < kStemK; ++k) v[k] = 0;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        // element offset (2py+ky)*100 + 6px is even: five aligned 32-bit words cover the nine values
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(patch + (2 * py + ky) * kPatchPitch + 6 * px);
+#pragma unroll
+        for (int wd = 0; wd < 5; ++wd) {
+          const uint32_t u = src[wd];
+          v[ky * 9 + 2 * wd] = static_cast<uint16_t>(u & 0xffffu);
+          if (2 * wd + 1 < 9) v[ky * 9 + 2 * wd + 1] = static_cast<uint16_t>(u >> 16);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < kStemK / 8; ++c) {
+        uint4 u;
+        u.x = v[c * 8 + 0] | (static_cast<uint32_t>(v[c * 8 + 1]) << 16);
+        u.y = v[c * 8 + 2] | (static_cast<uint32_t>(v[c * 8 + 3]) << 16);
+        u.z = v[c * 8 + 4] | (static_cast<uint32_t>(v[c * 8 + 5]) << 16);
+        u.w = v[c * 8 + 6] | (static_cast<uint32_t>(v[c * 8 + 7]) << 16);
+        *reinterpret_cast<uint4*>(sA + swizzled_chunk_offset(t, c, 64)) = u;
+      }
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -111,8 +156,9 @@ stem_conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w27,
     tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16), r);
     tmem_ld_wait();
     tc_fence_before();
-    if (live) {
-      uint4* op = reinterpret_cast<uint4*>(out + pix * kStemCo);
+    const int ho = ho0 + py, wo = wo0 + px;
+    if (ho < HO && wo < WO) {
+      uint4* op = reinterpret_cast<uint4*>(out + ((static_cast<int64_t>(b) * HO + ho) * WO + wo) * kStemCo);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint4 u;
@@ -123,8 +169,9 @@ stem_conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w27,
         op[c] = u;
       }
     }
-    // the next iteration's __syncthreads (after the A tile is rebuilt) orders these TMEM reads before the next MMA;
-    // the A tile itself may be overwritten right away: the MMA that read it has completed (mma_bar)
+    // The next iteration's first __syncthreads (after the patch is rebuilt) orders these TMEM reads before the next MMA
+    // and every thread's reads of `patch` (done before the MMA above) before its overwrite; the A tile may be
+    // overwritten once the MMA that read it has completed (mma_bar).
   }
   tc_fence_before();
   __syncthreads();
@@ -134,16 +181,27 @@ stem_conv1_tc_kernel(const float* __restrict__ x, const float* __restrict__ w27,
   }
 }
 
-int launch_stem_conv1_tc(const float* x, const float* w, const float* bias, void* out, int B, int H, int W,
-                         cudaStream_t s) {
-  const int64_t total = static_cast<int64_t>(B) * (H / 2) * (W / 2);
-  const int64_t tiles = (total + 127) / 128;
+int launch_stem_conv1_tc(const void* x, int x_is_u8, const float* w, const float* bias, const float* mean, const float* stdv,
+                         void* out, int B, int H, int W, cudaStream_t s) {
+  const int HO = H / 2, WO = W / 2;
+  const int tiles_x = (WO + kTileW - 1) / kTileW, tiles_y = (HO + kTileH - 1) / kTileH;
+  const int64_t tiles = static_cast<int64_t>(B) * tiles_x * tiles_y;
   if (tiles > 0x7fffffff) return fail(LECB_ERR_ARG, "lecb_stem_conv1: problem too large");
   const int sms = sm_count();
   if (sms <= 0) return fail(LECB_ERR_CUDA, "no CUDA device");
   const int64_t cap = static_cast<int64_t>(sms) * 12;
   const int grid = static_cast<int>(tiles < cap ? tiles : cap);
-  stem_conv1_tc_kernel<<<grid, 128, 0, s>>>(x, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W, static_cast<int>(tiles));
+  StemNorm nrm{};
+  for (int c = 0; c < 3; ++c) {
+    nrm.mean[c] = mean ? mean[c] : 0.f;
+    nrm.std[c] = stdv ? stdv[c] : 1.f;
+  }
+  if (x_is_u8)
+    stem_conv1_tc_kernel<true><<<grid, 128, 0, s>>>(x, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W, tiles_x, tiles_y,
+                                                    static_cast<int>(tiles), nrm);
+  else
+    stem_conv1_tc_kernel<false><<<grid, 128, 0, s>>>(x, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W, tiles_x, tiles_y,
+                                                     static_cast<int>(tiles), nrm);
   count_launch();
   return check_launch("stem_conv1_tc_kernel");
 }

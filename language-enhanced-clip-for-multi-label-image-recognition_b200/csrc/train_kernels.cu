@@ -554,7 +554,8 @@ extern "C" int lecb_causal_attn_bwd(const void* qkv, const void* dout, void* dqk
   LECB_CHECK_ARG(N > 0 && L > 0 && L <= kLMaxB, "lecb_causal_attn_bwd: need 0 < L <= %d (L=%d)", kLMaxB, L);
   LECB_CHECK_ARG(W == heads * kDh, "lecb_causal_attn_bwd: head dim must be 64");
   const size_t smem = 4 * kLMaxB * kPitch * sizeof(__nv_bfloat16) + (kLMaxB * (kLMaxB + 1) + kLMaxB) * sizeof(float);
-  static bool configured = false;
+  static DeviceOnce once;                    // the attribute is per device: one flag per device ordinal
+  bool& configured = once.flag();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(causal_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(LECB_ERR_CUDA, "lecb_causal_attn_bwd: smem attr: %s", cudaGetErrorString(e));

@@ -145,6 +145,10 @@ class PromptLearner(nn.Module):
         self.register_buffer("token_suffix_nocls", embedding_nocls[:, 1 + n_ctx:, :].clone())
         self.n_cls, self.n_ctx = n_cls, n_ctx
         self.tokenized_prompts = tokenized_prompts
+        # T:173 `name_lens = [len(_tokenizer.encode(name)) ...]`: the tokens between the context and the final "."
+        # (the BPE splits punctuation off first, so the class name tokenises the same inside the prompt)
+        eot = tokenized_prompts.argmax(dim=-1)
+        self.name_lens = [int(e) - 2 - n_ctx for e in eot]
         self.class_token_position = _cfg_get(cfg, "TRAINER.Caption.CLASS_TOKEN_POSITION", "end")
 
     def forward(self, neg_prompt_wcls=True):
@@ -167,7 +171,8 @@ class DenseCLIPB200(nn.Module):
 
     forward(image=None, captions=None, if_test=False, model_name='ema'):
       test  : image [B,3,H,W] float -> (logits_ [B,K], logits_local [B,K], logits_neg [P,B,K],
-              feats·T_posᵀ [P,B,K], topk_scores [B,10] | None)                               (T:472)
+              feats·T_posᵀ [P,B,K], topk_scores [B,10] (zeros without a caption bank))        (T:472)
+              `image` may also be a uint8 NHWC batch [B,H,W,3] of raw pixels (normalised inside the stem kernel)
       train : captions [B,77] int64 -> (logits_, logits_local, image_features [L,B,D],
               text_features [K,D], logits_m_ | None, logits_local_m | None)                  (T:545)
     """
@@ -272,7 +277,13 @@ class DenseCLIPB200(nn.Module):
                 self._cls_mask = m.view(-1)
             row_mask = self._cls_mask
         else:
-            feat = eng.trunk(image.float())
+            # additive: a uint8 NHWC batch [B,H,W,3] of raw pixels (what lecb_crop_resize_u8 produces) is normalised inside
+            # the stem kernel with cfg.INPUT.PIXEL_MEAN / PIXEL_STD; a float batch is the reference's normalised NCHW tensor
+            if image.dtype == torch.uint8:
+                feat = eng.trunk(image, mean=_cfg_get(self.cfg, "INPUT.PIXEL_MEAN", ops.CLIP_PIXEL_MEAN),
+                                 std=_cfg_get(self.cfg, "INPUT.PIXEL_STD", ops.CLIP_PIXEL_STD))
+            else:
+                feat = eng.trunk(image.float())
             b, h, w, _ = feat.shape
             p = h * w
             local, ssq, g = eng.pooled(feat)
@@ -294,10 +305,14 @@ class DenseCLIPB200(nn.Module):
         if row_mask is not None:
             neg_map, pos_map = neg_map[1:], pos_map[1:]          # drop the class-token row: [P,B,K] patch maps
         g_unit = ops.l2norm_rows(g)
-        g_add, topk_scores = None, None
+        g_add = None
         if self.caption_bank is not None:
             from .retrieval import retrieve_mean
             g_add, topk_scores = retrieve_mean(g_unit, self.caption_bank)
+        else:
+            # no bank: the global feature is used as is; the 5th return value keeps the reference's shape so that the
+            # trainer's `sim.reshape(...)` / `.cpu()` (T:645, T:701) works unchanged
+            topk_scores = torch.zeros((b, 10), device=g_unit.device, dtype=torch.float32)
         logits_ = ops.global_logits(g_unit, t_pos, g_add, logit_scale)
         return logits_, logits_local, neg_map, pos_map, topk_scores
 
@@ -311,10 +326,14 @@ class DenseCLIPB200(nn.Module):
 
     @torch.no_grad()
     def _momentum_update(self):
+        """T:554-559, one multi-tensor launch (lecb_ema_update) instead of three ATen kernels per parameter."""
         m = float(_cfg_get(self.cfg, "TRAIN.momentum", 0.995))
         for live, twin in self.model_pairs:
-            for p, pm in zip(live.parameters(), twin.parameters()):
-                pm.data = pm.data * m + p.data * (1.0 - m)
+            lp, tp = [p.data for p in live.parameters()], [p.data for p in twin.parameters()]
+            if all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() for t in lp + tp):
+                ops.ema_update(lp, tp, m)
+            else:
+                raise ops._lib.LecbError("lecb200: the EMA twin update needs fp32 CUDA prompt parameters (no CPU path)")
 
 
 DenseCLIP = DenseCLIPB200   # the reference's class name, for `cfg.TRAIN.MODEL == "DenseCLIP"` call sites

@@ -56,6 +56,10 @@ def allreduce_mean_grads(params, group=None):
     params = [p for p in params if p.requires_grad]
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
+    if all(p.is_cuda and p.dtype == torch.float32 for p in params):
+        GradBucket.for_params(params).allreduce_mean(group)
+        return
+    # CPU tensors: only the gloo protocol tests get here (the product runs on CUDA tensors, branch above)
     flat = flat_grads(params)
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     flat /= dist.get_world_size(group)
@@ -68,6 +72,73 @@ def allreduce_mean_grads(params, group=None):
         else:
             p.grad.copy_(g)
         off += n
+
+
+class GradBucket:
+    """One persistent flat fp32 buffer for the prompt-parameter gradients (the DDP bucket of T:786-787): a multi-tensor
+    pack kernel fills it (a parameter without gradient contributes zeros, like find_unused_parameters=True), ONE all-reduce
+    sums it over the ranks, and either `unpack` writes the averaged slices back into `.grad` or `PromptSGD.step` consumes
+    the flat buffer directly.  Three launches + one collective per step instead of cat / divide / one copy per parameter."""
+
+    _cache = {}
+
+    def __init__(self, params):
+        self.params = list(params)
+        self.flat = torch.zeros((sum(p.numel() for p in self.params),), device=self.params[0].device, dtype=torch.float32)
+
+    @classmethod
+    def for_params(cls, params):
+        key = tuple(id(p) for p in params)
+        b = cls._cache.get(key)
+        if b is None or b.flat.device != params[0].device:
+            b = cls._cache[key] = cls(params)
+        return b
+
+    def pack(self):
+        from . import ops
+        grads = [None if p.grad is None else p.grad.contiguous() for p in self.params]
+        ops.pack_f32(grads, [p.data for p in self.params], flat=self.flat)
+        return self.flat
+
+    def unpack(self, scale=1.0):
+        from . import ops
+        for p in self.params:
+            if p.grad is None:
+                p.grad = torch.empty_like(p.data)
+        ops.unpack_scale_f32(self.flat, [p.grad for p in self.params], scale)
+
+    def allreduce_sum(self, group=None):
+        """pack + all-reduce; returns the 1 / world factor that turns the flat sum into DDP's average."""
+        self.pack()
+        if multi_rank(group):
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            return 1.0 / dist.get_world_size(group)
+        return 1.0
+
+    def allreduce_mean(self, group=None):
+        self.unpack(self.allreduce_sum(group))
+
+
+class PromptSGD:
+    """torch.optim.SGD (momentum, weight decay, dampening 0, no nesterov — the optimiser the reference builds for the
+    prompt learner, T:773 / dassl/optim/optimizer.py) as ONE multi-tensor launch reading the flat gradient bucket."""
+
+    def __init__(self, params, lr, momentum=0.9, weight_decay=0.0):
+        self.params = [p for p in params]
+        self.lr, self.momentum, self.weight_decay = float(lr), float(momentum), float(weight_decay)
+        self.bufs = [torch.zeros_like(p.data) for p in self.params] if momentum else None
+        self.bucket = GradBucket.for_params(self.params)
+
+    @torch.no_grad()
+    def step(self, group=None):
+        from . import ops
+        scale = self.bucket.allreduce_sum(group)
+        ops.sgd_step(self.bucket.flat, [p.data for p in self.params], self.bufs, self.lr, self.momentum, self.weight_decay,
+                     grad_scale=scale)
+
+    def zero_grad(self):
+        for p in self.params:
+            p.grad = None
 
 
 def broadcast_params(params, src: int = 0, group=None):

@@ -85,9 +85,13 @@ class VisualRN:
                      for n in ("q_proj", "k_proj", "v_proj", "c_proj")}
 
     # ---- T:385-399 encode_image ----
-    def trunk(self, image):
-        """image fp32 NCHW [B,3,H,W] (cuda) -> layer4 features, NHWC bf16 [B,H/32,W/32,Cv]."""
-        x = ops.stem_conv1(image.contiguous(), *self.stem1)
+    def trunk(self, image, mean=None, std=None):
+        """image fp32 NCHW [B,3,H,W] (normalised, the reference's tensor) or uint8 NHWC [B,H,W,3] (raw pixels, normalised
+        with mean / std inside the stem kernel) -> layer4 features, NHWC bf16 [B,H/32,W/32,Cv]."""
+        if image.dtype == torch.uint8:
+            x = ops.stem_conv1_u8(image.contiguous(), *self.stem1, mean=mean or ops.CLIP_PIXEL_MEAN, std=std or ops.CLIP_PIXEL_STD)
+        else:
+            x = ops.stem_conv1(image.contiguous(), *self.stem1)
         b, h, w, c = x.shape
         if self.stem_pairs:
             x = x.view(b, h, w // 2, 2 * c)

@@ -4,6 +4,8 @@
 `ASL_loss(inputs, targets)`                             U:184-190
 `dualcoop_loss(inputs, inputs_g, targets)`              U:175-181
 `AsymmetricLoss_partial(...)`                           U:126-173
+`ranking_loss_with_cooccurrence(y_pred, y_true, cooccurrence, scale_=2.0, margin_=1)`   U:95-110 (T:842-850)
+`ema_consistency_loss(output, output_m, output_local, output_local_m)`                   the two KL terms of T:809-813
 Each launch produces the scalar loss and dloss/dlogits together; autograd just scales the stored gradient."""
 from __future__ import annotations
 
@@ -30,6 +32,31 @@ class _FusedLoss(torch.autograd.Function):
 def ranking_loss(y_pred, y_true, scale_=2.0, margin_=1):
     t = y_true.detach().float().contiguous()
     return _FusedLoss.apply(y_pred, lambda x: ops.ranking_fwd_bwd(x, t, scale_, margin_))
+
+
+def cooccurrence_pair_weights(cooccurrence):
+    """U:99-102: log(1 / (p + 1e-6)), zero diagonal, every row divided by its mean -> fp32 [K,K] (tiny; plain torch)."""
+    w = (1 / (cooccurrence.float() + 1e-6)).log()
+    w = w * (1 - torch.eye(w.shape[0], w.shape[1], device=w.device))
+    return (w / w.mean(-1)[:, None]).contiguous()
+
+
+def ranking_loss_with_cooccurrence(y_pred, y_true, cooccurrence, scale_=2.0, margin_=1):
+    t = y_true.detach().float().contiguous()
+    w = cooccurrence_pair_weights(cooccurrence.detach())
+    return _FusedLoss.apply(y_pred, lambda x: ops.ranking_cooc_fwd_bwd(x, t, w, scale_, margin_))
+
+
+def kl_softmax(output, output_m, weight=1.0):
+    """weight * nn.KLDivLoss(reduction="batchmean")(F.log_softmax(output, -1), F.softmax(output_m, -1)); gradient to
+    `output` only (the reference computes `output_m` under torch.no_grad(), T:517)."""
+    tgt = output_m.detach().float().contiguous()
+    return _FusedLoss.apply(output, lambda x: ops.kl_softmax_fwd_bwd(x, tgt, weight))
+
+
+def ema_consistency_loss(output, output_m, output_local, output_local_m, local_weight=10000.0):
+    """`ema_loss` of T:809-811: KL on the global logits + 10000 x KL on the local logits."""
+    return kl_softmax(output, output_m) + kl_softmax(output_local, output_local_m, local_weight)
 
 
 class AsymmetricLoss_partial(nn.Module):

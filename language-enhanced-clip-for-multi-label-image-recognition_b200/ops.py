@@ -342,3 +342,115 @@ def tn_gemm_small(a, b, j, out=None, alpha=1.0, accumulate=False):
     check(lib.lecb_tn_gemm_small(_ptr(a), lda, _ptr(b), int(b.dtype == torch.bfloat16), _ptr(out), r, j, d, float(alpha),
                                  int(accumulate), _stream()), "lecb_tn_gemm_small")
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: uint8 stem input, remaining losses, multi-tensor updates
+# ---------------------------------------------------------------------------------------------
+CLIP_PIXEL_MEAN = (0.48145466, 0.4578275, 0.40821073)      # cfg.INPUT.PIXEL_MEAN / PIXEL_STD of every shipped yaml
+CLIP_PIXEL_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def _f3(vals):
+    import ctypes
+    return (ctypes.c_float * 3)(*[float(v) for v in vals])
+
+
+def stem_conv1_u8(x, w27, bias, mean=CLIP_PIXEL_MEAN, std=CLIP_PIXEL_STD):
+    """x NHWC uint8 [B,H,W,3] raw pixels; ToTensor + Normalize(mean, std) applied inside the kernel;
+    -> NHWC bf16 [B,H/2,W/2,Cout] (conv + folded BN + ReLU), identical to stem_conv1 on the normalised float tensor."""
+    _need(x, torch.uint8, "x")
+    _need(w27, torch.float32, "w27")
+    _need(bias, torch.float32, "bias")
+    b, h, w, c = x.shape
+    assert c == 3
+    cout = w27.shape[1]
+    out = torch.empty((b, h // 2, w // 2, cout), device=x.device, dtype=torch.bfloat16)
+    m, s = _f3(mean), _f3(std)
+    check(lib.lecb_stem_conv1_u8(_ptr(x), _ptr(w27), _ptr(bias), m, s, _ptr(out), b, h, w, cout, _stream()),
+          "lecb_stem_conv1_u8")
+    return out
+
+
+def ranking_cooc_fwd_bwd(logits, targets, pair_weights, scale=2.0, margin=1.0, want_grad=True):
+    _need(logits, torch.float32, "logits")
+    _need(targets, torch.float32, "targets")
+    _need(pair_weights, torch.float32, "pair_weights")
+    b, k = logits.shape
+    assert tuple(pair_weights.shape) == (k, k)
+    grad = torch.empty_like(logits) if want_grad else None
+    loss = torch.empty((), device=logits.device, dtype=torch.float32)
+    check(lib.lecb_ranking_cooc_fwd_bwd(_ptr(logits), _ptr(targets), _ptr(pair_weights), _ptr(grad), _ptr(loss), b, k,
+                                        float(scale), float(margin), _stream()), "lecb_ranking_cooc_fwd_bwd")
+    return loss, grad
+
+
+def kl_softmax_fwd_bwd(logits, logits_target, weight=1.0, want_grad=True):
+    """weight * KLDivLoss(batchmean)(log_softmax(logits), softmax(logits_target)) and its gradient w.r.t. logits."""
+    _need(logits, torch.float32, "logits")
+    _need(logits_target, torch.float32, "logits_target")
+    assert logits.shape == logits_target.shape
+    b, k = logits.shape
+    grad = torch.empty_like(logits) if want_grad else None
+    loss = torch.empty((), device=logits.device, dtype=torch.float32)
+    check(lib.lecb_kl_softmax_fwd_bwd(_ptr(logits), _ptr(logits_target), _ptr(grad), _ptr(loss), b, k, float(weight),
+                                      _stream()), "lecb_kl_softmax_fwd_bwd")
+    return loss, grad
+
+
+class TensorList:
+    """HOST arrays of device pointers + element counts for the multi-tensor kernels (built once per parameter list)."""
+
+    def __init__(self, tensors, allow_none=False):
+        import ctypes
+        self.n = len(tensors)
+        self.tensors = list(tensors)
+        for t in tensors:
+            if t is None:
+                assert allow_none
+                continue
+            _need(t, torch.float32, "tensor")
+        self.ptrs = (ctypes.c_void_p * self.n)(*[None if t is None else t.data_ptr() for t in tensors])
+        self.sizes = None
+
+    def with_sizes(self, sizes):
+        import ctypes
+        self.sizes = (ctypes.c_longlong * self.n)(*[int(s) for s in sizes])
+        return self
+
+
+def _sizes(tensors):
+    import ctypes
+    return (ctypes.c_longlong * len(tensors))(*[int(t.numel()) for t in tensors])
+
+
+def ema_update(live, twin, momentum):
+    """twin_i <- momentum * twin_i + (1 - momentum) * live_i for every pair, one launch (T:554-559)."""
+    a, b = TensorList(live), TensorList(twin)
+    check(lib.lecb_ema_update(a.ptrs, b.ptrs, _sizes(live), a.n, float(momentum), _stream()), "lecb_ema_update")
+
+
+def pack_f32(tensors, like, flat=None):
+    """flat fp32 <- concat of `tensors` (None entries contribute zeros of the size of the matching `like` tensor)."""
+    total = sum(int(t.numel()) for t in like)
+    if flat is None:
+        flat = torch.empty((total,), device=like[0].device, dtype=torch.float32)
+    src = TensorList(tensors, allow_none=True)
+    check(lib.lecb_pack_f32(src.ptrs, _sizes(like), src.n, _ptr(flat), _stream()), "lecb_pack_f32")
+    return flat
+
+
+def unpack_scale_f32(flat, tensors, scale=1.0):
+    _need(flat, torch.float32, "flat")
+    dst = TensorList(tensors)
+    check(lib.lecb_unpack_scale_f32(_ptr(flat), dst.ptrs, _sizes(tensors), dst.n, float(scale), _stream()),
+          "lecb_unpack_scale_f32")
+
+
+def sgd_step(flat_grad, params, momentum_bufs, lr, momentum=0.0, weight_decay=0.0, grad_scale=1.0):
+    """torch.optim.SGD step (dampening 0, no nesterov, zero-initialised momentum buffers) from a flat gradient."""
+    _need(flat_grad, torch.float32, "flat_grad")
+    p = TensorList(params)
+    m = TensorList(momentum_bufs) if momentum_bufs is not None else None
+    check(lib.lecb_sgd_step(_ptr(flat_grad), p.ptrs, m.ptrs if m is not None else None, _sizes(params), p.n,
+                            float(grad_scale), float(lr), float(momentum), float(weight_decay), _stream()), "lecb_sgd_step")

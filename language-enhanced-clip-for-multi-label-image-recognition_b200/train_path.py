@@ -152,6 +152,15 @@ def forward_train(model, captions):
     shard = getattr(model, "shard_prompt_branch", False)
     if shard and not dist.multi_rank(None if shard is True else shard):
         shard = False                    # single process: nothing to shard over
+    if shard:
+        # feasibility is decided from values identical on every rank BEFORE any collective: with ceil(n / world)-row chunks
+        # the last ranks can end up with no rows (40 sequences on 16 ranks), and a rank that raised on its own would
+        # leave the others hanging in the all-gather; such a layout simply keeps the replicated branch everywhere
+        import torch.distributed as _d
+        world = _d.get_world_size(None if shard is True else shard)
+        n_rows = (3 if use_evidence else 2) * prompts.shape[0]
+        if -(-n_rows // world) * (world - 1) >= n_rows:
+            shard = False
     pack = (model.text_encoder.tower(), model._eot_dev, local, ssq, mask, g_unit, b, l, logit_scale, spatial,
             (True if shard is True else shard) if shard else None)
     plist = (prompts, prompts_double, prompts_evidence) if use_evidence else (prompts, prompts_double)

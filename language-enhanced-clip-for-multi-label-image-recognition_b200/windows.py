@@ -127,3 +127,43 @@ def resize_plan(in_size: int, out_size: int, filt: str = "bicubic"):
     _lib.check(_lib.lib.lecb_resize_plan(in_size, out_size, f, bounds.ctypes.data_as(ctypes.c_void_p),
                                          coeffs.ctypes.data_as(ctypes.c_void_p), ksize), "lecb_resize_plan")
     return bounds, coeffs
+
+
+def crop_resize(img, wins: Sequence[Window], size: int, filt: str = "bicubic", want_u8: bool = True, want_f32: bool = False,
+                mean=None, std=None):
+    """Crop + Pillow-compatible resize (+ ToTensor + Normalize) of `wins` of ONE decoded image on the GPU
+    (lecb_crop_resize_u8; reference: data_manager.py:348-492 + transforms.py:379-411, about a hundred PIL calls per image).
+
+    img uint8 CUDA tensor [H,W,3].  -> (u8 NHWC [n,size,size,3] | None, f32 NCHW [n,3,size,size] | None); the uint8 batch
+    is byte-identical to `PIL.Image.resize` of each crop and feeds `DenseCLIPB200(image_u8, if_test=True)` directly."""
+    import ctypes
+
+    import numpy as np
+    import torch
+
+    from . import _lib, ops
+    if not (img.is_cuda and img.dtype == torch.uint8 and img.dim() == 3 and img.shape[2] == 3 and img.is_contiguous()):
+        raise _lib.LecbError("crop_resize: img must be a contiguous uint8 CUDA tensor [H,W,3]")
+    h, w = int(img.shape[0]), int(img.shape[1])
+    n = len(wins)
+    f = {"bilinear": 0, "bicubic": 1}[filt]
+    rec = np.ascontiguousarray(np.asarray([[x.top, x.left, x.height, x.width, x.pad_top, x.pad_bottom] for x in wins], dtype=np.int32))
+    plan_ints, tmp_bytes = ctypes.c_longlong(0), ctypes.c_longlong(0)
+    wp = rec.ctypes.data_as(ctypes.c_void_p)
+    _lib.check(_lib.lib.lecb_window_plan_size(wp, n, h, w, size, f, ctypes.byref(plan_ints), ctypes.byref(tmp_bytes)),
+               "lecb_window_plan_size")
+    plan = torch.empty((plan_ints.value,), dtype=torch.int32).pin_memory()
+    _lib.check(_lib.lib.lecb_window_plan(wp, n, h, w, size, f, plan.data_ptr(), plan_ints.value), "lecb_window_plan")
+    plan_d = plan.to(img.device, non_blocking=True)
+    tmp = torch.empty((max(tmp_bytes.value, 1),), device=img.device, dtype=torch.uint8)
+    out_u8 = torch.empty((n, size, size, 3), device=img.device, dtype=torch.uint8) if want_u8 else None
+    out_f32 = torch.empty((n, 3, size, size), device=img.device, dtype=torch.float32) if want_f32 else None
+    m, s = ops._f3(mean or ops.CLIP_PIXEL_MEAN), ops._f3(std or ops.CLIP_PIXEL_STD)
+    _lib.check(_lib.lib.lecb_crop_resize_u8(img.data_ptr(), h, w, plan_d.data_ptr(), n, size, tmp.data_ptr(), ops._ptr(out_u8),
+                                            ops._ptr(out_f32), m, s, ops._stream()), "lecb_crop_resize_u8")
+    return out_u8, out_f32
+
+
+def whole_image(h: int, w: int) -> Window:
+    """The un-windowed test image as a Window (the first input of every sample: `Resize(INPUT.SIZE)` of the full image)."""
+    return Window(0, 0, h, w, 0, 0)

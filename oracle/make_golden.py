@@ -18,6 +18,9 @@ Fixtures written:
   losses.npz                 ranking_loss / ASL_loss / dualcoop_loss values + grads on [16,80]
   map.npz                    reference numpy mAP on synthetic scores/labels
   fusion.npz                 reference fuse / fuse6 (gen_final_ans.py) and adjust_predictions (T:611-615) on synthetic scores
+  train_ext_{tiny,rn50}.npz  the same step under TRAIN.ema / CSC / IF_LEARN_SCALE / co-occurrence ranking (round 2)
+  losses_ext.npz             ranking_loss_with_cooccurrence + the KL terms of T:809-813 on [16,80]
+  prompt_learner_tiny.npz    PromptLearner.forward(neg_prompt_wcls=True/False), CSC and generic, name_lens, state_dict
   vit_{tiny,b16_224,l14_224}.npz   reference VisionTransformer.forward (class-token feature) on synthetic weights
 """
 from __future__ import annotations
@@ -34,6 +37,7 @@ from . import synth
 
 GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
+CSC_ROWS = (0, 7, 33, 52, 79)          # classes whose CSC gradients are stored in full (train_ext_rn50.npz)
 TINY_CLASSES = ["person", "dog", "traffic light", "cup", "potted plant", "tv"]
 
 
@@ -51,16 +55,27 @@ def state_checksum(sd) -> np.ndarray:
     return acc
 
 
-def build_dense_clip(arch, sd, classnames, n_ctx, use_evidence, bank, seed, csc=False):
+def build_dense_clip(arch, sd, classnames, n_ctx, use_evidence, bank, seed, csc=False, ema=False, learn_scale=False,
+                     twin_offset=False):
     ns = RX.trainer_classes(bank, arch.embed_dim)
     clip_model = RX.build_reference_clip(arch, sd)
-    cfg = RX.make_cfg(arch.image_resolution, n_ctx=n_ctx, csc=csc, use_evidence=use_evidence)
+    cfg = RX.make_cfg(arch.image_resolution, n_ctx=n_ctx, csc=csc, use_evidence=use_evidence, ema=ema,
+                      learn_scale=learn_scale)
     model = ns["DenseCLIP"](cfg, classnames, clip_model)
     w = arch.transformer_width
+    n_cls = len(classnames) if csc else 0
     with torch.no_grad():
-        for name, tag in (("ctx", "pos"), ("ctx_double", "neg"), ("ctx_evidence", "evi")):
-            getattr(model.prompt_learner, name).copy_(synth.prompt_ctx(n_ctx, w, seed, tag))
+        for name, tag in (("ctx", "pos"), ("ctx_double", "neg")):
+            getattr(model.prompt_learner, name).copy_(synth.prompt_ctx(n_ctx, w, seed, tag, n_cls))
+        model.prompt_learner.ctx_evidence.copy_(synth.prompt_ctx(n_ctx, w, seed, "evi"))          # never CSC (T:147)
     model.copy_params()
+    if twin_offset:
+        # copy_params() makes the twin equal to the live learner, which would make the momentum update (T:554-559) a no-op:
+        # start the twin somewhere else so that `0.995 twin + 0.005 live` and the twin's logits are observable
+        with torch.no_grad():
+            for name, tag in (("ctx", "pos_m"), ("ctx_double", "neg_m")):
+                getattr(model.prompt_learner_m, name).add_(synth.prompt_ctx(n_ctx, w, seed, tag, n_cls))
+            model.prompt_learner_m.ctx_evidence.add_(synth.prompt_ctx(n_ctx, w, seed, "evi_m"))
     for name, p in model.named_parameters():
         if "prompt_learner" not in name:
             p.requires_grad_(False)          # T:763-765
@@ -136,6 +151,146 @@ def golden_train(tag, arch, batch, classnames, n_ctx, seed):
                 out["text_features" + s2] = r[3].detach().numpy()
             print(f"[train_{tag}] evidence={ev} loss={loss_name}: {loss.item():.6f}", flush=True)
     np.savez_compressed(os.path.join(GOLD, f"train_{tag}.npz"), **out)
+
+
+def _cooc_p():
+    """The co-occurrence prior the trainer builds from freq_stats.pkl (T:843-846): an INPUT of the loss, stored in the fixture."""
+    import pickle
+    with open(os.path.join(RX.MC, "freq_stats.pkl"), "rb") as f:
+        result = pickle.load(f)
+    p = torch.tensor(result["adj"] / result["nums"][:, np.newaxis], dtype=torch.float32)
+    return p / p.sum(-1)[:, None]
+
+
+def golden_train_ext(tag, arch, batch, classnames, n_ctx, seed):
+    """Config switches of the prompt-tuning step that train_<tag>.npz does not cover, each run through the reference's own
+    DenseCLIP.forward(None, captions) and the loss expression of forward_backward (T:804-815, T:842-850):
+      ema      TRAIN.ema=True: 6-tuple with logits_m_ / logits_local_m after _momentum_update (T:516-541, 554-559), loss =
+               ranking + KL(log_softmax(out) || softmax(out_m)) + 10000 x the local KL (T:809-813); twin parameters after the update
+      csc      TRAINER.Caption.CSC=True: class-specific ctx / ctx_double [K,n_ctx,W] (T:127-133)
+      scale    TRAIN.IF_LEARN_SCALE=True: logit scale exp(temperature) with its gradient (T:453-454, 493-494)
+      cooc     LOSSFUNC 'ranking_with_cooccurrence' (T:842-850, U:95-110) on the plain configuration"""
+    sd = synth.clip_state_dict(arch, seed=0)
+    caps = synth.captions(batch, seed, vocab=arch.vocab_size)
+    y = synth.labels(batch, len(classnames), seed)
+    L = RX.loss_functions()
+    kl = torch.nn.KLDivLoss(reduction="batchmean")
+    F = torch.nn.functional
+    out = {"caption_checksum": checksum(caps.float()), "state_checksum": state_checksum(sd),
+           "label_checksum": checksum(y), "batch": np.int64(batch), "seed": np.int64(seed), "n_ctx": np.int64(n_ctx)}
+    if len(classnames) == 80:
+        out["cooc_p"] = _cooc_p().numpy()
+
+    def record(sfx, model, r, loss):
+        loss.backward()
+        out["loss" + sfx] = np.float64(loss.item())
+        pl = model.prompt_learner
+        for pname in ("ctx", "ctx_double", "ctx_evidence", "temperature"):
+            g = getattr(pl, pname).grad
+            gt = torch.zeros_like(getattr(pl, pname)) if g is None else g
+            if gt.dim() == 3 and gt.shape[0] > len(CSC_ROWS):
+                # class-specific contexts [K,n_ctx,W]: keep a few classes in full and every class's norm (file size)
+                out[f"gradnorm_{pname}" + sfx] = gt.flatten(1).norm(dim=1).numpy()
+                gt = gt[list(CSC_ROWS)]
+            out[f"grad_{pname}" + sfx] = gt.numpy()
+            out[f"gradnone_{pname}" + sfx] = np.bool_(g is None)
+        out["logits" + sfx] = r[0].detach().numpy()
+        out["logits_local" + sfx] = r[1].detach().numpy()
+        out["text_features" + sfx] = r[3].detach().numpy()
+        print(f"[train_ext_{tag}] {sfx}: loss {loss.item():.6f}", flush=True)
+
+    def rank2(a, b):
+        return L["ranking_loss"](a, y, scale_=1.0, margin_=1) + L["ranking_loss"](b, y, scale_=1.0, margin_=1)
+
+    for ev in (False, True):
+        e = "_ev" if ev else ""
+        # --- ema ---
+        model = build_dense_clip(arch, sd, classnames, n_ctx, ev, None, seed, ema=True, twin_offset=True)
+        r = model(None, caps)
+        r_loss = rank2(r[0], r[1])
+        # ranking_loss scaled its arguments in place by 1.0 (U:86): values unchanged
+        ema_loss = kl(F.log_softmax(r[0], dim=-1), F.softmax(r[4], dim=-1)) + \
+            kl(F.log_softmax(r[1], dim=-1), F.softmax(r[5], dim=-1)) * 10000
+        out["r_loss_ema" + e] = np.float64(r_loss.item())
+        out["ema_loss_ema" + e] = np.float64(ema_loss.item())
+        out["logits_m_ema" + e] = r[4].detach().numpy()
+        out["logits_local_m_ema" + e] = r[5].detach().numpy()
+        for pname in ("ctx", "ctx_double", "ctx_evidence"):
+            out[f"twin_{pname}_ema" + e] = getattr(model.prompt_learner_m, pname).detach().numpy().copy()
+        record("_ema" + e, model, r, r_loss + ema_loss)
+        # --- learnable logit scale ---
+        model = build_dense_clip(arch, sd, classnames, n_ctx, ev, None, seed, learn_scale=True)
+        r = model(None, caps)
+        record("_scale" + e, model, r, rank2(r[0], r[1]))
+    # --- class-specific contexts (no evidence: T:147 keeps ctx_evidence generic either way) ---
+    model = build_dense_clip(arch, sd, classnames, n_ctx, True, None, seed, csc=True)
+    r = model(None, caps)
+    record("_csc_ev", model, r, rank2(r[0], r[1]))
+    # --- co-occurrence weighted ranking loss ---
+    if len(classnames) == 80:
+        p = _cooc_p()
+        model = build_dense_clip(arch, sd, classnames, n_ctx, False, None, seed)
+        r = model(None, caps)
+        loss = L["ranking_loss_with_cooccurrence"](r[0], y, p, scale_=1.0, margin_=1) + \
+            L["ranking_loss_with_cooccurrence"](r[1], y, p, scale_=1.0, margin_=1)
+        record("_cooc", model, r, loss)
+    np.savez_compressed(os.path.join(GOLD, f"train_ext_{tag}.npz"), **out)
+
+
+def golden_losses_ext():
+    """ranking_loss_with_cooccurrence (U:95-110) with the real freq_stats prior, and the two KL terms of T:809-813."""
+    L = RX.loss_functions()
+    F = torch.nn.functional
+    kl = torch.nn.KLDivLoss(reduction="batchmean")
+    g = torch.Generator().manual_seed(78)
+    x = torch.randn((16, 80), generator=g) * 2.0
+    xm = x + torch.randn((16, 80), generator=g) * 0.3
+    y = (torch.rand((16, 80), generator=g) < 0.06).float()
+    y[0, 3] = 1.0
+    y[5] = 0.0                                   # a row without positives contributes nothing
+    p = _cooc_p()
+    out = {"x": x.numpy(), "xm": xm.numpy(), "y": y.numpy(), "cooc_p": p.numpy()}
+    for name, fn in (("cooc_s1", lambda a: L["ranking_loss_with_cooccurrence"](a, y, p, scale_=1.0, margin_=1)),
+                     ("cooc_s2", lambda a: L["ranking_loss_with_cooccurrence"](a, y, p)),
+                     ("kl", lambda a: kl(F.log_softmax(a, dim=-1), F.softmax(xm, dim=-1))),
+                     ("kl_x10000", lambda a: kl(F.log_softmax(a, dim=-1), F.softmax(xm, dim=-1)) * 10000)):
+        a = x.clone().requires_grad_(True)
+        b = a * 1.0
+        loss = fn(b)
+        loss.backward()
+        out["loss_" + name] = np.float64(loss.item())
+        out["grad_" + name] = a.grad.numpy()
+        print(f"[losses_ext] {name}: {loss.item():.6f}", flush=True)
+    np.savez_compressed(os.path.join(GOLD, "losses_ext.npz"), **out)
+
+
+def golden_prompt_learner(classnames):
+    """PromptLearner.forward(neg_prompt_wcls=False) (T:199-242: the negative / evidence prompts built WITHOUT the class-name
+    tokens) and the CSC variant, on a small text width: outputs are pure concatenations, compared exactly."""
+    arch = synth.tiny_rn()
+    sd = synth.clip_state_dict(arch, seed=0)
+    ns = RX.trainer_classes(None, arch.embed_dim)
+    out = {}
+    for csc in (False, True):
+        clip_model = RX.build_reference_clip(arch, sd)
+        cfg = RX.make_cfg(arch.image_resolution, n_ctx=4, csc=csc)
+        pl = ns["PromptLearner"](cfg, TINY_CLASSES, clip_model)
+        n_cls = len(TINY_CLASSES) if csc else 0
+        with torch.no_grad():
+            pl.ctx.copy_(synth.prompt_ctx(4, arch.transformer_width, 7, "pos", n_cls))
+            pl.ctx_double.copy_(synth.prompt_ctx(4, arch.transformer_width, 7, "neg", n_cls))
+            pl.ctx_evidence.copy_(synth.prompt_ctx(4, arch.transformer_width, 7, "evi"))
+        sfx = "_csc" if csc else ""
+        for wcls in (True, False):
+            r = pl(neg_prompt_wcls=wcls)
+            for nm, t in zip(("prompts", "prompts_neg", "prompts_evidence"), r[:3]):
+                out[f"{nm}_wcls{int(wcls)}{sfx}"] = t.detach().numpy()
+        out["name_lens" + sfx] = np.asarray(pl.name_lens, dtype=np.int64)
+        out["tokenized_prompts" + sfx] = pl.tokenized_prompts.numpy()
+        for k, v in pl.state_dict().items():
+            out[f"state_{k}{sfx}"] = v.numpy()
+    np.savez_compressed(os.path.join(GOLD, "prompt_learner_tiny.npz"), **out)
+    print("[prompt_learner] written", flush=True)
 
 
 def golden_vit(tag, arch, batch, seed):
@@ -223,6 +378,10 @@ def main(which=None):
         "head_rn101": lambda: golden_head("rn101_448", synth.RN101(448), 2, classnames, 16, 2000, 1236, (True,)),
         "train_rn50": lambda: golden_train("rn50", synth.RN50(224), 4, classnames, 16, 1238),
         "fusion": golden_fusion,
+        "train_ext_tiny": lambda: golden_train_ext("tiny", synth.tiny_rn(), 6, TINY_CLASSES, 4, 1243),
+        "train_ext_rn50": lambda: golden_train_ext("rn50", synth.RN50(224), 4, classnames, 16, 1239),
+        "losses_ext": golden_losses_ext,
+        "prompt_learner": lambda: golden_prompt_learner(classnames),
         "vit_tiny": lambda: golden_vit("tiny", synth.tiny_vit(), 3, 1250),
         "vit_b16_224": lambda: golden_vit("b16_224", synth.VITB16(224), 2, 1251),
         "vit_l14_224": lambda: golden_vit("l14_224", synth.VITL14(224), 1, 1252),

@@ -340,6 +340,47 @@ def dualcoop_loss(x, y):
     return asymmetric_loss(x, y, 2, 1, 0.05, 1e-8, 0.9, -0.9, True)
 
 
+def ranking_loss_with_cooccurrence(y_pred, y_true, cooccurrence, scale=2.0, margin=1.0):
+    """U:95-110: the hinge of pair (i, j) weighted by log(1 / (p_ij + 1e-6)), zero diagonal, rows divided by their mean."""
+    y = y_pred * scale
+    t = y_true.float()
+    w = (1 / (cooccurrence + 1e-6)).log()
+    w = w * (1 - torch.eye(w.shape[0], w.shape[1]))
+    w = w / w.mean(-1)[:, None]
+    d = (margin - y[:, None, :] + y[:, :, None]).clamp_min(0) * w
+    return (d * t[:, None, :] * (1 - t[:, :, None])).sum((-1, -2)).mean()
+
+
+def kl_softmax(x, x_target):
+    """nn.KLDivLoss(reduction="batchmean")(log_softmax(x), softmax(x_target)) (T:796, T:809-811): sum_b,k q (log q - log p) / B."""
+    logp = torch.log_softmax(x, dim=-1)
+    q = torch.softmax(x_target, dim=-1)
+    return torch.xlogy(q, q).sum() / x.shape[0] - (q * logp).sum() / x.shape[0]
+
+
+def ema_loss(out, out_m, out_local, out_local_m):
+    """T:809-811."""
+    return kl_softmax(out, out_m) + kl_softmax(out_local, out_local_m) * 10000
+
+
+def momentum_update(live, twin, momentum=0.995):
+    """T:554-559 over dicts of tensors: twin <- twin * m + live * (1 - m)."""
+    return {k: twin[k] * momentum + live[k] * (1.0 - momentum) for k in twin}
+
+
+def dense_clip_train_ema(sd, arch, captions, pl_state, pl_state_m, token_ids, use_evidence=False, logit_scale=4.0,
+                         spatial_scale=50.0, momentum=0.995):
+    """DenseCLIP.forward(None, captions) with TRAIN.ema (T:516-541): the twin is updated FIRST (T:518), then encodes its own
+    prompts without gradient.  -> (logits_, logits_local, feats, t_pos, logits_m_, logits_local_m, updated twin state)."""
+    out = dense_clip_train(sd, arch, captions, pl_state, token_ids, use_evidence, logit_scale, spatial_scale)
+    with torch.no_grad():
+        keys = ("ctx", "ctx_double", "ctx_evidence")
+        new_m = dict(pl_state_m)
+        new_m.update(momentum_update({k: pl_state[k].detach() for k in keys}, {k: pl_state_m[k] for k in keys}, momentum))
+        out_m = dense_clip_train(sd, arch, captions, new_m, token_ids, use_evidence, logit_scale, spatial_scale)
+    return out + (out_m[0], out_m[1], new_m)
+
+
 # --------------------------------------------------------------------------------------------
 # metric (EV:137-175)
 # --------------------------------------------------------------------------------------------

@@ -11,8 +11,9 @@ from . import _cases as C
 LOGIT_TOL = 1e-2        # north_star: max abs logit error <= 1e-2 (bf16 operands, fp32 accumulation)
 
 
-def build_model(case, use_evidence, bank=None, tag="coco"):
-    """lecb200 DenseCLIPB200 on cuda:0 holding the case's synthetic weights and prompt contexts."""
+def build_model(case, use_evidence, bank=None, tag="coco", **cfg_kw):
+    """lecb200 DenseCLIPB200 on cuda:0 holding the case's synthetic weights and prompt contexts.
+    cfg_kw: make_cfg switches (csc=, ema=, learn_scale=, ...)."""
     from lecb200.clip_model import CLIPParams
     from lecb200.dense_clip import DenseCLIPB200
     arch = case["arch"]
@@ -21,7 +22,7 @@ def build_model(case, use_evidence, bank=None, tag="coco"):
     assert not missing and not unexpected, (missing, unexpected)
     clip = clip.float().cuda().eval()
     toks, n_ctx, names = C.tokens_for(tag)
-    cfg = make_cfg(arch.image_resolution, n_ctx=n_ctx, use_evidence=use_evidence)
+    cfg = make_cfg(arch.image_resolution, n_ctx=n_ctx, use_evidence=use_evidence, **cfg_kw)
     model = DenseCLIPB200(cfg, names, clip, caption_bank=bank, tokenized_prompts=toks).cuda()
     with torch.no_grad():
         model.prompt_learner.ctx.copy_(case["pl_state"]["ctx"])
