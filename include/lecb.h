@@ -65,6 +65,11 @@ int lecb_gemm_bf16(const void* A, const void* W, const float* bias, const void* 
  * conv2/conv3).  Requirements: Cin % 32 == 0, Cout % 8 == 0. */
 int lecb_conv3x3_bf16(const void* x, const void* w, const float* bias, void* out, int B, int H, int Wd,
                       int Cin, int Cout, unsigned flags, void* stream);
+/* Wide layers (N >= 256, K >= 256 and a multiple of 64, bf16 output, at least one 256 x 256 tile per SM) run on the CTA-pair
+ * variant of the kernel: two CTAs of a cluster own a 256 x 256 tile, each stages its 128 rows of A and half of the W tile,
+ * one tcgen05.mma.cta_group::2 (M = 256) reads both halves (gemm_pair.cu).  lecb_set_pair_gemm(0 / 1) switches that path off /
+ * on at run time (default on; environment LECB_NO_PAIR=1 starts with it off) and returns the previous setting. */
+int lecb_set_pair_gemm(int enable);
 /* 1 if lecb_conv3x3_bf16 accepts LECB_EPI_AVGPOOL2 for this problem (halo-tile mode: Cin 32 / 64, Cout <= 128,
  * even H and W, at least two 128-pixel patches per SM), else 0 — the caller then runs lecb_avgpool2x2 itself. */
 int lecb_conv3x3_pool_fusable(int B, int H, int Wd, int Cin, int Cout);
@@ -162,14 +167,15 @@ int lecb_kl_softmax_fwd_bwd(const float* logits, const float* logits_target, flo
 
 /* ---- multi-tensor updates over the prompt-learner parameter list: HOST arrays of `count` (<= 16) device pointers and
  * element counts, one launch each ----
- * lecb_ema_update: twin_i <- momentum * twin_i + (1 - momentum) * live_i                     (_momentum_update, T:554-559)
+ * lecb_ema_update: twin_i <- twin_i * momentum + live_i * one_minus_momentum (_momentum_update, T:554-559; the caller
+ *   passes `1. - momentum` evaluated in double and rounded once, as Python / ATen do: the update is bit-identical)
  * lecb_pack_f32: flat <- concat_i src_i (a NULL source contributes zeros: a parameter without gradient, what DDP's
  *   find_unused_parameters=True covers at T:787); lecb_unpack_scale_f32: dst_i <- scale * its slice of flat — the flat
  *   gradient bucket that is all-reduced once per step (T:786-787)
  * lecb_sgd_step: p_i <- p_i - lr * (buf_i <- momentum * buf_i + grad_scale * flat_i + weight_decay * p_i), torch.optim.SGD
  *   with zero-initialised momentum buffers (the optimiser built at T:773) */
 int lecb_ema_update(const float* const* live, float* const* twin, const long long* n, int count, float momentum,
-                    void* stream);
+                    float one_minus_momentum, void* stream);
 int lecb_pack_f32(const float* const* src, const long long* n, int count, float* flat, void* stream);
 int lecb_unpack_scale_f32(const float* flat, float* const* dst, const long long* n, int count, float scale, void* stream);
 int lecb_sgd_step(const float* flat_grad, float* const* params, float* const* momentum_buf, const long long* n, int count,

@@ -21,6 +21,7 @@ SIGNATURES = {
                                c_uint, c_void_p]),
     "lecb_conv3x3_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_uint, c_void_p]),
+    "lecb_set_pair_gemm": (c_int, [c_int]),
     "lecb_conv3x3_pool_fusable": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "lecb_stem_conv1": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "lecb_stem_conv1_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
@@ -46,7 +47,7 @@ SIGNATURES = {
     "lecb_ranking_cooc_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float,
                                           c_void_p]),
     "lecb_kl_softmax_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_float, c_void_p]),
-    "lecb_ema_update": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p]),
+    "lecb_ema_update": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p]),
     "lecb_pack_f32": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "lecb_unpack_scale_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p]),
     "lecb_sgd_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_float, c_void_p]),

@@ -29,6 +29,14 @@
 
 namespace lecb {
 
+// CTA-pair (cta_group::2) path for the wide layers: gemm_pair.cu
+bool pair_gemm_eligible(int64_t M, int N, int K, unsigned flags, bool has_sumsq_f32_out);
+bool pair_conv_eligible(int B, int H, int Wd, int Cin, int Cout, unsigned flags);
+int launch_pair_gemm(const void* A, const void* Wt, const float* bias, const void* residual, void* out, float* row_sumsq,
+                     int64_t M, int N, int K, unsigned flags, cudaStream_t stream);
+int launch_pair_conv3x3(const void* x, const void* w, const float* bias, void* out, int B, int H, int Wd, int Cin, int Cout,
+                        unsigned flags, cudaStream_t stream);
+
 constexpr int kTileM = 128;
 constexpr int kEpiWarps = 8;                       // groups of four (a warp reads TMEM lane quarter warp % 4).  Measured with
                                                    // 12: no faster on the short-K residual GEMMs and 3-20 % slower on the convs
@@ -139,14 +147,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int num_tiles = (p.num_m_tiles / MT) * p.num_n_tiles;
   // Tile schedule.  Default: tile t = blockIdx.x + i * gridDim.x, n fastest.  b_resident: the CTA keeps n tile
   // blockIdx.x % num_n_tiles and walks m tiles blockIdx.x / num_n_tiles + i * (gridDim.x / num_n_tiles).
+  // Fused top-10 epilogue: the CTA owns ONE m block (blockIdx.x % num_m_tiles: its running lists are flushed once) and walks
+  // n tiles blockIdx.x / num_m_tiles + i * (gridDim.x / num_m_tiles); the CTAs of different m blocks read the same bank
+  // tile at about the same time, so the bank crosses HBM -> L2 once however many query blocks there are.
+  const bool topk_sched = p.topk_val != nullptr;
+  const int tk_stride = topk_sched ? static_cast<int>(gridDim.x) / p.num_m_tiles : 1;
+  const int tk_n0 = topk_sched ? static_cast<int>(blockIdx.x) / p.num_m_tiles : 0;
   const int res_n = p.b_resident ? static_cast<int>(blockIdx.x) % p.num_n_tiles : 0;
   const int res_m0 = p.b_resident ? static_cast<int>(blockIdx.x) / p.num_n_tiles : 0;
   const int res_ms = p.b_resident ? static_cast<int>(gridDim.x) / p.num_n_tiles : 1;
-  const int my_tiles = MT * (p.b_resident
+  const int my_tiles = topk_sched ? (tk_n0 < p.num_n_tiles ? (p.num_n_tiles - tk_n0 + tk_stride - 1) / tk_stride : 0) :
+                       MT * (p.b_resident
                            ? (res_m0 < p.num_m_tiles ? (p.num_m_tiles - res_m0 + res_ms - 1) / res_ms : 0)
                            : (static_cast<int>(blockIdx.x) < num_tiles ? (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0));
   auto tile_coords = [&](int i, int& m_blk, int& n_blk) {
-    if (p.b_resident) {
+    if (topk_sched) {
+      m_blk = static_cast<int>(blockIdx.x) % p.num_m_tiles;
+      n_blk = tk_n0 + i * tk_stride;
+    } else if (p.b_resident) {
       m_blk = res_m0 + i * res_ms;
       n_blk = res_n;
     } else if (MT == 2) {
@@ -680,17 +698,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int j = 0; j < 32; ++j) {
             const float v = __uint_as_float(r[j]);
             if (v > tk_val[9] && n0 + j < p.N) {           // strict: of equal values the lower index (seen first) stays
-              int pos = 9;
+              // branch-free sorted insertion with STATIC indices only: the list must stay in registers (a runtime-indexed
+              // array lives in local memory, and with the whole carve-out given to shared memory there is no L1: every
+              // access would be an L2 round trip on the epilogue's critical path)
+              const int col = n0 + j;
 #pragma unroll
-              for (int q = 8; q >= 0; --q) {
-                if (v > tk_val[q]) {
-                  tk_val[q + 1] = tk_val[q];
-                  tk_idx[q + 1] = tk_idx[q];
-                  pos = q;
-                }
+              for (int q = 9; q >= 1; --q) {
+                const bool above = v > tk_val[q - 1];        // the element above moves down into slot q
+                const bool here = v > tk_val[q];             // ... else v lands here if it beats the current occupant
+                tk_idx[q] = above ? tk_idx[q - 1] : (here ? col : tk_idx[q]);
+                tk_val[q] = above ? tk_val[q - 1] : (here ? v : tk_val[q]);
               }
-              tk_val[pos] = v;
-              tk_idx[pos] = n0 + j;
+              if (v > tk_val[0]) {
+                tk_val[0] = v;
+                tk_idx[0] = col;
+              }
             }
           }
         }
@@ -838,6 +860,12 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
     smem_bytes = p.operand_bytes + NB * Cfg::kCBytes + kBarBytes + kBiasBytes;
     grid = (sms / p.num_n_tiles) * p.num_n_tiles;
   }
+  if (p.topk_val != nullptr) {             // one m block per CTA (see the kernel's tile schedule)
+    int per_m = sms / p.num_m_tiles;
+    if (per_m > p.num_n_tiles) per_m = p.num_n_tiles;
+    if (per_m < 1) return fail(LECB_ERR_ARG, "top-10 epilogue: too many row blocks (%d) for %d SMs", p.num_m_tiles, sms);
+    grid = per_m * p.num_m_tiles;
+  }
   if (p.mt == 2) gemm_kernel<BN, BK, NB, kConv, kPairable ? 2 : 1><<<grid, kNumThreads, smem_bytes, stream>>>(tmA, tmB, tmC, tmR, p);
   else kern<<<grid, kNumThreads, smem_bytes, stream>>>(tmA, tmB, tmC, tmR, p);
   count_launch();
@@ -944,6 +972,8 @@ extern "C" int lecb_gemm_bf16(const void* A, const void* W, const float* bias, c
   LECB_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
                  "lecb_gemm_bf16: operands must be 16-byte aligned");
+  if (pair_gemm_eligible(M, N, K, flags, false))
+    return launch_pair_gemm(A, W, bias, residual, out, row_sumsq, M, N, K, flags, static_cast<cudaStream_t>(stream));
   const int BK = (K % 64 == 0) ? 64 : 32;
   int BN = pick_bn(N);
   if (BK == 32 && BN > 64) BN = 64;
@@ -1016,8 +1046,10 @@ extern "C" int lecb_gemm_topk10(const void* A_hilo, const void* bank, int64_t M,
   p.topk_val = part_val;
   p.topk_idx = part_idx;
   p.topk_slots = slots;
-  const int64_t tiles = static_cast<int64_t>(p.num_m_tiles) * p.num_n_tiles;
-  const int grid = static_cast<int>(tiles < sms ? tiles : sms);
+  LECB_CHECK_ARG(p.num_m_tiles <= sms, "lecb_gemm_topk10: at most %d query rows per call (M=%lld)", sms * kTileM, (long long)M);
+  int per_m = sms / p.num_m_tiles;                 // CTAs per m block
+  if (per_m > p.num_n_tiles) per_m = p.num_n_tiles;
+  const int grid = per_m * p.num_m_tiles;
   if (slots_used) *slots_used = grid;
   LECB_CHECK_ARG(slots >= grid, "lecb_gemm_topk10: %d partial slots, the launch needs %d", slots, grid);
   CUtensorMap tmA, tmB;
@@ -1075,6 +1107,8 @@ extern "C" int lecb_conv3x3_bf16(const void* x, const void* w, const float* bias
                  "lecb_conv3x3_bf16: only LECB_EPI_RELU / LECB_EPI_QUICKGELU / LECB_EPI_AVGPOOL2 are supported");
   const bool want_pool = (flags & LECB_EPI_AVGPOOL2) != 0;
   LECB_CHECK_ARG(!want_pool || (H % 2 == 0 && Wd % 2 == 0), "lecb_conv3x3_bf16: LECB_EPI_AVGPOOL2 needs even H and W (H=%d W=%d)", H, Wd);
+  if (pair_conv_eligible(B, H, Wd, Cin, Cout, flags))
+    return launch_pair_conv3x3(x, w, bias, out, B, H, Wd, Cin, Cout, flags, static_cast<cudaStream_t>(stream));
   int BN, BK;
   conv_tile_shape(Cin, Cout, BN, BK);
   const int64_t M = static_cast<int64_t>(B) * H * Wd;

@@ -25,14 +25,15 @@ struct TensorList {
 };
 
 // blockIdx.y = tensor, blockIdx.x strides over its elements
-__global__ void __launch_bounds__(256) ema_update_kernel(const TensorList tl, float momentum) {
+__global__ void __launch_bounds__(256) ema_update_kernel(const TensorList tl, float momentum, float one_minus) {
   const int t = blockIdx.y;
   const float* __restrict__ live = tl.src[t];
   float* __restrict__ twin = tl.dst[t];
   const long long n = tl.n[t];
-  const float one_minus = 1.0f - momentum;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
-    twin[i] = twin[i] * momentum + live[i] * one_minus;            // same operation order as T:559
+    // T:559 `param_m.data * momentum + param.data * (1. - momentum)`: two rounded products and a rounded sum (no FMA
+    // contraction), `1. - momentum` evaluated in double by Python and rounded to fp32 once — bit-identical to ATen
+    twin[i] = __fadd_rn(__fmul_rn(twin[i], momentum), __fmul_rn(live[i], one_minus));
 }
 
 __global__ void __launch_bounds__(256) pack_kernel(const TensorList tl, float* __restrict__ flat) {
@@ -104,14 +105,14 @@ static dim3 list_grid(long long max_n, int count) {
 using namespace lecb;
 
 extern "C" int lecb_ema_update(const float* const* live, float* const* twin, const long long* n, int count, float momentum,
-                               void* stream) {
+                               float one_minus_momentum, void* stream) {
   LECB_CHECK_ARG(live && twin, "lecb_ema_update: null pointer list");
   TensorList tl{};
   long long mx = 0;
   int st = fill_list(tl, live, twin, nullptr, n, count, "lecb_ema_update", &mx);
   if (st) return st;
   for (int i = 0; i < count; ++i) LECB_CHECK_ARG(tl.src[i] && tl.dst[i], "lecb_ema_update: tensor %d is null", i);
-  ema_update_kernel<<<list_grid(mx, count), 256, 0, static_cast<cudaStream_t>(stream)>>>(tl, momentum);
+  ema_update_kernel<<<list_grid(mx, count), 256, 0, static_cast<cudaStream_t>(stream)>>>(tl, momentum, one_minus_momentum);
   count_launch();
   return check_launch("ema_update_kernel");
 }

@@ -300,6 +300,7 @@ extern "C" int lecb_stem_conv1_u8(const uint8_t* x, const float* w, const float*
   LECB_CHECK_ARG(x && w && bias && out && mean && stdv, "lecb_stem_conv1_u8: null pointer");
   LECB_CHECK_ARG(B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "lecb_stem_conv1_u8: H, W must be even and positive");
   LECB_CHECK_ARG(stdv[0] != 0.f && stdv[1] != 0.f && stdv[2] != 0.f, "lecb_stem_conv1_u8: zero std");
+  LECB_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 3) == 0, "lecb_stem_conv1_u8: the image batch must be 4-byte aligned");
   if (Cout != 32) return fail(LECB_ERR_UNSUPPORTED, "lecb_stem_conv1_u8: Cout=%d (only the CLIP ResNet stem width 32)", Cout);
   return launch_stem_conv1_tc(x, 1, w, bias, mean, stdv, out, B, H, W, static_cast<cudaStream_t>(stream));
 }

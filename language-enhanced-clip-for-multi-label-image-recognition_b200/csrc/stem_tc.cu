@@ -89,25 +89,79 @@ stem_conv1_tc_kernel(const void* __restrict__ xin, const float* __restrict__ w27
     const int ho0 = ty * kTileH, wo0 = tx * kTileW;
     const int hi0 = 2 * ho0 - 1, wi0 = 2 * wo0 - 1;
     // ---- stage the input patch: [17][33][3] bf16, zeros outside the image (conv padding, ragged tiles) ----
+    // One warp per patch row segment, lanes along the contiguous axis (coalesced), no per-element divisions.
+    const int lane = t & 31;
     if (kU8) {
-      const uint8_t* x = static_cast<const uint8_t*>(xin) + static_cast<int64_t>(b) * H * W * 3;
-      for (int i = t; i < kPatchH * kPatchW * 3; i += 128) {
-        const int r = i / (kPatchW * 3), cc = i - r * (kPatchW * 3);        // cc = col * 3 + ci: contiguous bytes of one row
-        const int c = cc / 3, ci = cc - c * 3;
-        const int hi = hi0 + r, wi = wi0 + c;
-        __nv_bfloat16 v = __float2bfloat16(0.f);
-        if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = lut[ci * 256 + __ldg(x + (static_cast<int64_t>(hi) * W + wi) * 3 + ci)];
-        patch[r * kPatchPitch + cc] = v;
+      // a patch row is 99 contiguous bytes of the NHWC image: lanes 0..25 fetch the aligned 32-bit words covering it
+      const uint8_t* xb = static_cast<const uint8_t*>(xin);
+      const int64_t total = static_cast<int64_t>(B) * H * W * 3;
+      constexpr int kRowsPerWarp = (kPatchH + 3) / 4;                    // 5: every word load is issued before the first use
+      uint32_t words[kRowsPerWarp];
+#pragma unroll
+      for (int it = 0; it < kRowsPerWarp; ++it) {
+        const int r = warp + 4 * it;
+        const int hi = hi0 + r;
+        const bool row_ok = r < kPatchH && hi >= 0 && hi < H;
+        const int64_t g0 = ((static_cast<int64_t>(b) * H + (row_ok ? hi : 0)) * W + wi0) * 3;      // first byte of the row (may be < 0)
+        const int64_t o = (g0 >= 0 ? g0 : g0 - 3) / 4 * 4 + 4 * lane;                             // aligned down (floor)
+        uint32_t word = 0;
+        if (row_ok && lane < 26) {
+          if (o >= 0 && o + 4 <= total) {
+            word = __ldg(reinterpret_cast<const uint32_t*>(xb + o));
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (o + k >= 0 && o + k < total) word |= static_cast<uint32_t>(__ldg(xb + o + k)) << (8 * k);
+          }
+        }
+        words[it] = word;
+      }
+#pragma unroll
+      for (int it = 0; it < kRowsPerWarp; ++it) {
+        const int r = warp + 4 * it;
+        const int hi = hi0 + r;
+        const bool row_ok = hi >= 0 && hi < H;
+        if (r < kPatchH && lane < 26) {
+          const int64_t g0 = ((static_cast<int64_t>(b) * H + (row_ok ? hi : 0)) * W + wi0) * 3;
+          const int shift = static_cast<int>(g0 - (g0 >= 0 ? g0 : g0 - 3) / 4 * 4);                // 0..3
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int cc = 4 * lane + k - shift;                         // byte position inside the row: col * 3 + ci
+            if (cc >= 0 && cc < kPatchW * 3) {
+              const int c = (cc * 171) >> 9;                             // cc / 3 for cc < 512
+              const int ci = cc - 3 * c;
+              const int wi = wi0 + c;
+              const bool ok = row_ok && wi >= 0 && wi < W;
+              patch[r * kPatchPitch + cc] = ok ? lut[ci * 256 + ((words[it] >> (8 * k)) & 0xffu)] : __float2bfloat16(0.f);
+            }
+          }
+        }
       }
     } else {
+      // 3 planes x 17 rows = 51 segments of 33 floats; all of a warp's loads are issued before the first store
       const float* x = static_cast<const float*>(xin) + static_cast<int64_t>(b) * 3 * H * W;
-      for (int i = t; i < 3 * kPatchH * kPatchW; i += 128) {
-        const int ci = i / (kPatchH * kPatchW), rc = i - ci * (kPatchH * kPatchW);
-        const int r = rc / kPatchW, c = rc - r * kPatchW;                  // c fastest: coalesced row segments per plane
-        const int hi = hi0 + r, wi = wi0 + c;
-        float v = 0.f;
-        if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = __ldg(x + (static_cast<int64_t>(ci) * H + hi) * W + wi);
-        patch[r * kPatchPitch + c * 3 + ci] = __float2bfloat16(v);
+      constexpr int kSeg = 3 * kPatchH;                                  // 51
+      constexpr int kPerWarp = (kSeg + 3) / 4;                           // 13
+      float v0[kPerWarp], v1[kPerWarp];
+#pragma unroll
+      for (int it = 0; it < kPerWarp; ++it) {
+        const int sgm = warp + 4 * it;
+        const int ci = sgm / kPatchH, r = sgm - ci * kPatchH;
+        const int hi = hi0 + r;
+        const bool row_ok = sgm < kSeg && hi >= 0 && hi < H;
+        const float* rp = x + (static_cast<int64_t>(ci) * H + (row_ok ? hi : 0)) * W;
+        const int wa = wi0 + lane, wb = wi0 + 32;
+        v0[it] = (row_ok && wa >= 0 && wa < W) ? __ldg(rp + wa) : 0.f;
+        v1[it] = (row_ok && lane == 0 && wb < W) ? __ldg(rp + wb) : 0.f;       // wb >= 31 > 0 always
+      }
+#pragma unroll
+      for (int it = 0; it < kPerWarp; ++it) {
+        const int sgm = warp + 4 * it;
+        if (sgm < kSeg) {
+          const int ci = sgm / kPatchH, r = sgm - ci * kPatchH;
+          patch[r * kPatchPitch + lane * 3 + ci] = __float2bfloat16(v0[it]);
+          if (lane == 0) patch[r * kPatchPitch + 32 * 3 + ci] = __float2bfloat16(v1[it]);
+        }
       }
     }
     __syncthreads();

@@ -427,7 +427,8 @@ def _sizes(tensors):
 def ema_update(live, twin, momentum):
     """twin_i <- momentum * twin_i + (1 - momentum) * live_i for every pair, one launch (T:554-559)."""
     a, b = TensorList(live), TensorList(twin)
-    check(lib.lecb_ema_update(a.ptrs, b.ptrs, _sizes(live), a.n, float(momentum), _stream()), "lecb_ema_update")
+    check(lib.lecb_ema_update(a.ptrs, b.ptrs, _sizes(live), a.n, float(momentum), float(1.0 - float(momentum)), _stream()),
+          "lecb_ema_update")
 
 
 def pack_f32(tensors, like, flat=None):

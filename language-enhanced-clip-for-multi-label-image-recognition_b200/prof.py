@@ -42,6 +42,9 @@ def _work(name, a):
     if name == "lecb_stem_conv1":
         b, h, w, co = a[4], a[5], a[6], a[7]
         return 2.0 * b * (h // 2) * (w // 2) * co * 27, 4.0 * b * 3 * h * w + 2.0 * b * (h // 2) * (w // 2) * co
+    if name == "lecb_stem_conv1_u8":
+        b, h, w, co = a[6], a[7], a[8], a[9]
+        return 2.0 * b * (h // 2) * (w // 2) * co * 27, 1.0 * b * 3 * h * w + 2.0 * b * (h // 2) * (w // 2) * co
     if name == "lecb_head_aggregate":
         ldn, b, p, k, n_txt = a[1], a[7], a[8], a[9], a[10]
         maps = 2 if a[5] else 0
@@ -63,7 +66,8 @@ class KernelTimer:
     def __enter__(self):
         lib = _lib.lib
         for name in _lib.SIGNATURES:
-            if name in ("lecb_abi_version", "lecb_last_error", "lecb_launch_count", "lecb_conv3x3_pool_fusable", "lecb_resize_ksize", "lecb_resize_plan"):      # host-only
+            if name in ("lecb_abi_version", "lecb_last_error", "lecb_launch_count", "lecb_conv3x3_pool_fusable", "lecb_resize_ksize",
+                        "lecb_resize_plan", "lecb_window_plan_size", "lecb_window_plan", "lecb_set_pair_gemm"):      # host-only
                 continue
             fn = getattr(lib, name)
             self._saved[name] = fn

@@ -129,6 +129,9 @@ def resize_plan(in_size: int, out_size: int, filt: str = "bicubic"):
     return bounds, coeffs
 
 
+_PLAN_CACHE = {}
+
+
 def crop_resize(img, wins: Sequence[Window], size: int, filt: str = "bicubic", want_u8: bool = True, want_f32: bool = False,
                 mean=None, std=None):
     """Crop + Pillow-compatible resize (+ ToTensor + Normalize) of `wins` of ONE decoded image on the GPU
@@ -147,15 +150,22 @@ def crop_resize(img, wins: Sequence[Window], size: int, filt: str = "bicubic", w
     h, w = int(img.shape[0]), int(img.shape[1])
     n = len(wins)
     f = {"bilinear": 0, "bicubic": 1}[filt]
-    rec = np.ascontiguousarray(np.asarray([[x.top, x.left, x.height, x.width, x.pad_top, x.pad_bottom] for x in wins], dtype=np.int32))
-    plan_ints, tmp_bytes = ctypes.c_longlong(0), ctypes.c_longlong(0)
-    wp = rec.ctypes.data_as(ctypes.c_void_p)
-    _lib.check(_lib.lib.lecb_window_plan_size(wp, n, h, w, size, f, ctypes.byref(plan_ints), ctypes.byref(tmp_bytes)),
-               "lecb_window_plan_size")
-    plan = torch.empty((plan_ints.value,), dtype=torch.int32).pin_memory()
-    _lib.check(_lib.lib.lecb_window_plan(wp, n, h, w, size, f, plan.data_ptr(), plan_ints.value), "lecb_window_plan")
-    plan_d = plan.to(img.device, non_blocking=True)
-    tmp = torch.empty((max(tmp_bytes.value, 1),), device=img.device, dtype=torch.uint8)
+    # the plan depends on the image SIZE and the window list only: datasets have a handful of image sizes, so the uploaded
+    # blob and the scratch buffer are kept per (size, windows) and an image costs just the two kernel launches
+    key = (h, w, size, f, str(img.device), tuple(wins))
+    hit = _PLAN_CACHE.get(key)
+    if hit is None:
+        rec = np.ascontiguousarray(np.asarray([[x.top, x.left, x.height, x.width, x.pad_top, x.pad_bottom] for x in wins], dtype=np.int32))
+        plan_ints, tmp_bytes = ctypes.c_longlong(0), ctypes.c_longlong(0)
+        wp = rec.ctypes.data_as(ctypes.c_void_p)
+        _lib.check(_lib.lib.lecb_window_plan_size(wp, n, h, w, size, f, ctypes.byref(plan_ints), ctypes.byref(tmp_bytes)),
+                   "lecb_window_plan_size")
+        plan = torch.empty((plan_ints.value,), dtype=torch.int32)
+        _lib.check(_lib.lib.lecb_window_plan(wp, n, h, w, size, f, plan.data_ptr(), plan_ints.value), "lecb_window_plan")
+        if len(_PLAN_CACHE) >= 64:
+            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+        hit = _PLAN_CACHE[key] = (plan.to(img.device), torch.empty((max(tmp_bytes.value, 1),), device=img.device, dtype=torch.uint8))
+    plan_d, tmp = hit
     out_u8 = torch.empty((n, size, size, 3), device=img.device, dtype=torch.uint8) if want_u8 else None
     out_f32 = torch.empty((n, 3, size, size), device=img.device, dtype=torch.float32) if want_f32 else None
     m, s = ops._f3(mean or ops.CLIP_PIXEL_MEAN), ops._f3(std or ops.CLIP_PIXEL_STD)

@@ -1,0 +1,90 @@
+"""CTA-pair (cta_group::2) GEMM / 3x3 conv kernel (gemm_pair.cu) through the public entry points, on shapes large enough
+to be routed to it, against fp32 torch on the same bf16-rounded operands AND against the single-CTA kernel (switch
+lecb_set_pair_gemm)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).cuda()
+
+
+def _check(got, want, what):
+    got = got.float()
+    scale = want.abs().max().item() + 1e-6
+    err = (got - want).abs().max().item()
+    assert err <= scale * (2.0 ** -7), f"{what}: max err {err:.4g} vs scale {scale:.4g}"
+
+
+@pytest.fixture
+def pair_switch():
+    from lecb200 import _lib
+    prev = _lib.lib.lecb_set_pair_gemm(1)
+    yield _lib.lib.lecb_set_pair_gemm
+    _lib.lib.lecb_set_pair_gemm(prev)
+
+
+# (M, N, K): one tile per SM exactly, several waves, ragged M (odd number of 128-row halves), N tail, deep K, 4 and 8 n tiles
+PAIR_SHAPES = [(37888, 256, 256), (200704, 256, 1024), (50000, 256, 512), (38000 + 77, 512, 256), (40000, 320, 256),
+               (25088, 1024, 256), (12544, 2048, 2048), (100480, 768, 768)]
+
+
+@pytest.mark.parametrize("m,n,k", PAIR_SHAPES)
+def test_pair_gemm_matches_torch_and_single_cta(m, n, k, pair_switch):
+    from lecb200 import ops
+    a = _rand((m, k), 21).bfloat16()
+    w = _rand((n, k), 22, k ** -0.5).bfloat16()
+    bias = _rand((n,), 23)
+    res = _rand((m, n), 24).bfloat16()
+    base = a.float() @ w.float().t() + bias
+    for name, kw, want in (("bias+relu", dict(relu=True), base.relu()),
+                           ("bias+res+relu", dict(residual=res, relu=True), (base + res.float()).relu()),
+                           ("quickgelu", dict(quick_gelu=True), base * torch.sigmoid(1.702 * base))):
+        pair_switch(1)
+        got = ops.gemm(a, w, bias, **kw)
+        torch.cuda.synchronize()
+        _check(got, want, f"pair {m}x{n}x{k} {name}")
+        pair_switch(0)
+        single = ops.gemm(a, w, bias, **kw)
+        torch.cuda.synchronize()
+        # same operands, same fp32 accumulation order along K (k blocks in order, four MMAs each): identical bits
+        assert torch.equal(got, single), f"{name}: pair and single-CTA kernels differ by {(got.float() - single.float()).abs().max().item()}"
+    pair_switch(1)
+    ssq = torch.zeros((m,), device="cuda")
+    out = ops.gemm(a, w, bias, row_sumsq=ssq)
+    torch.cuda.synchronize()
+    want = out.float().pow(2).sum(-1)
+    assert ((ssq - want).abs() / (want + 1e-6)).max().item() < 1e-4
+
+
+@pytest.mark.parametrize("b,h,w,cin,cout", [(64, 28, 28, 256, 256), (256, 14, 14, 512, 512), (16, 56, 56, 256, 256), (48, 28, 28, 128, 512)])
+def test_pair_conv3x3_matches_torch_and_single_cta(b, h, w, cin, cout, pair_switch):
+    from lecb200 import ops
+    x = _rand((b, h, w, cin), 27).bfloat16()
+    wt = _rand((cout, 3, 3, cin), 28, (9 * cin) ** -0.5).bfloat16()
+    bias = _rand((cout,), 29, 0.1)
+    pair_switch(1)
+    got = ops.conv3x3(x, wt, bias, relu=True)
+    torch.cuda.synchronize()
+    want = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wt.float().permute(0, 3, 1, 2), bias, padding=1)
+    _check(got, want.relu().permute(0, 2, 3, 1), f"pair conv {b}x{h}x{w}x{cin}->{cout}")
+    pair_switch(0)
+    single = ops.conv3x3(x, wt, bias, relu=True)
+    torch.cuda.synchronize()
+    assert torch.equal(got, single)
+
+
+def test_pair_path_is_taken(pair_switch):
+    """The routing itself: a wide layer launches gemm_pair_kernel (2 x 74 CTAs) — visible as a different launch shape is not
+    observable from Python, so check the eligibility rule through its effect: with the pair path on and off the results are
+    bit-identical (tests above) and both runs count one launch."""
+    import lecb200
+    from lecb200 import ops
+    a = _rand((37888, 256), 1).bfloat16()
+    w = _rand((256, 256), 2, 0.06).bfloat16()
+    n0 = lecb200.launch_count()
+    ops.gemm(a, w)
+    assert lecb200.launch_count() - n0 == 1

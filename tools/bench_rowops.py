@@ -84,3 +84,26 @@ w27 = torch.randn((27, 32), device=dev)
 bias = torch.randn((32,), device=dev)
 ms = timeit(lambda: ops.stem_conv1(img, w27, bias))
 report("stem_conv1", img.numel() * 4 + 256 * 224 * 224 * 32 * 2, ms, "B=256 448x448")
+u8 = torch.randint(0, 256, (256, 448, 448, 3), device=dev, dtype=torch.uint8)
+ms = timeit(lambda: ops.stem_conv1_u8(u8, w27, bias))
+report("stem_conv1_u8", u8.numel() + 256 * 224 * 224 * 32 * 2, ms, "B=256 448x448 uint8 NHWC")
+del img, u8
+# KL consistency term and the co-occurrence ranking loss at scaled inputs
+n = 1 << 19
+x = torch.randn((n, 80), device=dev) * 2
+xm = x + torch.randn_like(x) * 0.3
+y = (torch.rand((n, 80), device=dev) < 0.04).float()
+wt = torch.rand((80, 80), device=dev) + 0.5
+ms = timeit(lambda: ops.kl_softmax_fwd_bwd(x, xm, 1.0))
+report("kl_softmax_fwd_bwd", n * 80 * 12, ms, f"[{n},80]")
+ms = timeit(lambda: ops.ranking_cooc_fwd_bwd(x, y, wt, 1.0, 1.0))
+report("ranking_cooc_fwd_bwd", n * 80 * 12, ms, f"[{n},80]")
+del x, xm, y
+# test-time windows: 116 windows (scales 2, 3 + the whole image) of a 375 x 500 image -> 448 x 448 uint8
+import numpy as np  # noqa: E402
+from lecb200 import windows as WN  # noqa: E402
+h, w = 375, 500
+wins = [WN.whole_image(h, w)] + [q for s in (2, 3) for q in WN.sliding_windows(h, w, s)]
+img8 = torch.from_numpy(np.random.default_rng(0).integers(0, 256, size=(h, w, 3), dtype=np.uint8)).cuda()
+ms = timeit(lambda: WN.crop_resize(img8, wins, 448), iters=10)
+report("crop_resize_u8 (plan on host + 2 kernels)", len(wins) * 448 * 448 * 3, ms, f"{len(wins)} windows of {h}x{w} -> 448x448")
