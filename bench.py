@@ -592,7 +592,10 @@ def bench_train(cx, per_gpu_batch, steps, warmup, use_graph=True):
     broadcast_params(params)                 # DDP's construction-time broadcast (T:786-787)
     opt = PromptSGD(params, lr=0.002, momentum=0.9)
     b = per_gpu_batch
-    caps = synth.captions(b, 100 + rank, vocab=arch.vocab_size).to(dev)
+    caps = synth.captions(b, 100 + rank, vocab=arch.vocab_size)
+    # the captured step cannot read the batch's longest caption back from the device: promise it up front
+    model.caption_len_hint = int(caps.argmax(-1).max()) + 1
+    caps = caps.to(dev)
     y = synth.labels(b, len(names), 100 + rank).to(dev)
 
     def eager_step():
@@ -641,6 +644,7 @@ def bench_train(cx, per_gpu_batch, steps, warmup, use_graph=True):
                                   "distribution), 160 prompt sequences, ASL loss, prompt-gradient all-reduce, SGD",
                       "per_gpu_batch": b, "global_batch": world * b, "parallelism": f"dp{world}"},
            "cuda_graph": graphed, "gpu_launches": int(launches if not graphed else launches_eager),
+           "caption_positions_run": int(model.caption_len_hint), "caption_positions_total": int(caps.shape[1]),
            "final_loss": float(loss), "finite": bool(torch.isfinite(loss))}
     del model
     torch.cuda.empty_cache()

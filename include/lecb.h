@@ -117,6 +117,11 @@ int lecb_causal_attn_fwd(const void* qkv, void* out, int N, int L, int W, int he
  * Only the first `q_rows` query rows of every sequence are computed and stored (q_rows == T: all of them;
  * q_rows == 1: the class token only, used by the dense last block); other rows of `out` are left untouched. */
 int lecb_attn_fwd(const void* qkv, void* out, int B, int T, int W, int heads, int q_rows, int causal, void* stream);
+/* The kernel is bound by the MUFU (one ex2 per score, 16 per clock and SM): every n-th score's exponential (n in {2, 3, 4};
+ * 0 = none; default 4; sequences shorter than 256 tokens always use 0) is evaluated instead as 2^round(x) * cubic(x - round(x))
+ * on the FMA pipe (relative error 7.7e-5, 4 % of half a bf16 ulp of the probability): +5-7 % at the ViT shapes.
+ * lecb_set_attn_poly returns the previous setting. */
+int lecb_set_attn_poly(int n);
 
 /* ---- ViT visual tower row kernels (VisionTransformer.forward, M:259-276) ----
  * lecb_patchify: x NCHW fp32 [B,3,H,W] -> bf16 [B*(H/p)*(W/p), Kpad], column k = c*p*p + py*p + px (the flattening

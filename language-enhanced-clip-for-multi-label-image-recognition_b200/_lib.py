@@ -22,6 +22,7 @@ SIGNATURES = {
     "lecb_conv3x3_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_uint, c_void_p]),
     "lecb_set_pair_gemm": (c_int, [c_int]),
+    "lecb_set_attn_poly": (c_int, [c_int]),
     "lecb_conv3x3_pool_fusable": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "lecb_stem_conv1": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "lecb_stem_conv1_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -59,11 +59,27 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// 2^x on the FMA pipe: round-to-nearest split x = n + f (magic-number add: no F2I / FRND, which share the MUFU's quarter-rate
+// datapath), cubic in f on [-0.5, 0.5] (relative error 7.7e-5 = 4 % of half a bf16 ulp, below the rounding the probabilities
+// get anyway; tools/micro/exp2_poly.py), n added into the exponent field.  The kernel is bound by the 16 ex2 per clock and SM of
+// the MUFU (one per score); evaluating every kPoly-th score here moves that share of the work to the 128-lane FMA pipe.
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -125.0f);                              // keeps 2^n normal; such probabilities are zero after the bf16 rounding
+  const float t = x + 12582912.0f;                    // 1.5 * 2^23: the low mantissa bits now hold round(x)
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(0.0550886838f, f, 0.242604051f);
+  p = fmaf(p, f, 0.693276242f);
+  p = fmaf(p, f, 0.99992894f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 // kind::f16 instruction descriptor with selectable B major-ness (bit 16: 1 = MN-major)
 __host__ __device__ constexpr uint32_t attn_idesc(uint32_t n, bool b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// kPoly: 0 = every exponential on the MUFU; n > 0 = scores whose column index is n-1 mod n use poly_exp2 (FMA pipe)
+template <int kPoly>
 __global__ void __launch_bounds__(kAtThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -245,8 +261,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         uint32_t(&r)[32] = c2 ? rb : ra;
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float e0 = fast_exp2(fmaf(__uint_as_float(r[i]), p.sc, -msc));
-          float e1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), p.sc, -msc));
+          const float x0 = fmaf(__uint_as_float(r[i]), p.sc, -msc), x1 = fmaf(__uint_as_float(r[i + 1]), p.sc, -msc);
+          float e0 = (kPoly > 0 && i % kPoly == kPoly - 1) ? poly_exp2(x0) : fast_exp2(x0);
+          float e1 = (kPoly > 0 && (i + 1) % kPoly == kPoly - 1) ? poly_exp2(x1) : fast_exp2(x1);
           if (kMask && c2 * 32 + i > lim) e0 = 0.f;
           if (kMask && c2 * 32 + i + 1 > lim) e1 = 0.f;
           sum += e0 + e1;
@@ -372,6 +389,39 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 
 using namespace lecb;
 
+namespace lecb {
+static int g_attn_poly = -1;        // -1: not initialised (LECB_ATTN_POLY or the default), else 0 / 2 / 3 / 4
+constexpr int kAttnPolyDefault = 4;
+
+template <int kPoly>
+static int launch_attn(const CUtensorMap& tm, const AttnParams& p, int grid, cudaStream_t stream) {
+  static DeviceOnce once;                    // the attribute is per device: one flag per device ordinal
+  bool& configured = once.flag();
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<kPoly>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes);
+    if (e != cudaSuccess) return fail(LECB_ERR_CUDA, "cudaFuncSetAttribute(attn smem=%d): %s", kAtSmemBytes, cudaGetErrorString(e));
+    // two CTAs per SM need the full 228 KB shared-memory carve-out
+    cudaFuncSetAttribute(attn_fwd_kernel<kPoly>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
+  attn_fwd_kernel<kPoly><<<grid, kAtThreads, kAtSmemBytes, stream>>>(tm, p);
+  count_launch();
+  return check_launch("attn_fwd_kernel");
+}
+}  // namespace lecb
+
+// Share of the attention softmax's exponentials evaluated by the polynomial on the FMA pipe: 0 = none, n in {2, 3, 4} = every
+// n-th score.  Returns the previous setting (A/B measurements; environment LECB_ATTN_POLY sets the initial value).
+extern "C" int lecb_set_attn_poly(int n) {
+  if (lecb::g_attn_poly < 0) {
+    const char* e = getenv("LECB_ATTN_POLY");
+    lecb::g_attn_poly = e ? atoi(e) : lecb::kAttnPolyDefault;
+  }
+  const int prev = lecb::g_attn_poly;
+  if (n == 0 || n == 2 || n == 3 || n == 4) lecb::g_attn_poly = n;
+  return prev;
+}
+
 extern "C" int lecb_attn_fwd(const void* qkv, void* out, int B, int T, int W, int heads, int q_rows, int causal,
                              void* stream) {
   LECB_CHECK_ARG(qkv && out, "lecb_attn_fwd: null pointer");
@@ -380,20 +430,6 @@ extern "C" int lecb_attn_fwd(const void* qkv, void* out, int B, int T, int W, in
   LECB_CHECK_ARG(B <= 65535 && heads <= 65535, "lecb_attn_fwd: grid too large");
   LECB_CHECK_ARG((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                  "lecb_attn_fwd: operands must be 16-byte aligned");
-  static DeviceOnce once;                    // the attribute is per device: one flag per device ordinal
-  bool& configured = once.flag();
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes);
-    if (e != cudaSuccess) return fail(LECB_ERR_CUDA, "cudaFuncSetAttribute(attn smem=%d): %s", kAtSmemBytes, cudaGetErrorString(e));
-    // two CTAs per SM need the full 228 KB shared-memory carve-out
-    cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (getenv("LECB_DEBUG")) {
-      int occ = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, attn_fwd_kernel, kAtThreads, kAtSmemBytes);
-      fprintf(stderr, "[lecb] attn_fwd_kernel: %d CTAs/SM, %d B dynamic smem\n", occ, kAtSmemBytes);
-    }
-    configured = true;
-  }
   CUtensorMap tm;
   int st = encode_tiled_3d(&tm, qkv, static_cast<uint64_t>(3) * W, static_cast<uint64_t>(T), static_cast<uint64_t>(B),
                            kAtDh, kAtTile);
@@ -413,7 +449,14 @@ extern "C" int lecb_attn_fwd(const void* qkv, void* out, int B, int T, int W, in
   const int sms = sm_count();
   if (sms <= 0) return fail(LECB_ERR_CUDA, "no CUDA device");
   const int grid = p.total_items < 2 * sms ? p.total_items : 2 * sms;        // persistent: two CTAs per SM
-  attn_fwd_kernel<<<grid, kAtThreads, kAtSmemBytes, static_cast<cudaStream_t>(stream)>>>(tm, p);
-  count_launch();
-  return check_launch("attn_fwd_kernel");
+  if (g_attn_poly < 0) lecb_set_attn_poly(-1);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // short sequences (the text tower's 77 tokens: a single key block per row) are latency-bound, not MUFU-bound: measured
+  // 27.7 us with every exponential on the MUFU against 28.3 with a quarter on the FMA pipe — they keep the plain kernel
+  switch (T >= 256 ? g_attn_poly : 0) {
+    case 2: return launch_attn<2>(tm, p, grid, s);
+    case 3: return launch_attn<3>(tm, p, grid, s);
+    case 4: return launch_attn<4>(tm, p, grid, s);
+    default: return launch_attn<0>(tm, p, grid, s);
+  }
 }

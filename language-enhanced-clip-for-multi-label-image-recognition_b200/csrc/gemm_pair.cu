@@ -119,12 +119,16 @@ __host__ __device__ constexpr uint32_t make_idesc_pair(uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((256u >> 4) << 24);
 }
 
-template <int NB, bool kConv>
+// kF32: fp32 output (+ optional fp32 residual: the transformers' residual stream, M:226-227) in 32-column staged blocks
+// (128-byte rows) instead of bf16 output (+ bf16 residual) in 64-column blocks
+template <int NB, bool kConv, bool kF32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const PairParams p) {
   using Cfg = PairCfg<NB>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int kCCols = kF32 ? 32 : 64;                // columns per staged block (128-byte rows either way)
+  constexpr int kCBlocks = kPN / kCCols;                // 4 or 8 blocks per CTA tile: even, so block cb belongs to group cb % 2
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;                                   // [kStages][16 KB]
   uint8_t* sB = smem + kStages * kPABytes;              // [kStages][16 KB]
@@ -164,7 +168,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 2 * 4 * kPCBlocks);        // every (block, epilogue warp) of both CTAs
+      mbar_init(&tempty[i], 2 * 4 * kCBlocks);         // every (block, epilogue warp) of both CTAs
     }
     for (int i = 0; i < kNBar; ++i) {
       mbar_init(&cfree[i], 1);
@@ -252,14 +256,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == kPWarpDma) {
     // ------------------------------- epilogue DMA (per CTA, own rows) -----------------------
     if (elect_one()) {
-      const uint32_t total = static_cast<uint32_t>(my_tiles) * kPCBlocks;
+      const uint32_t total = static_cast<uint32_t>(my_tiles) * kCBlocks;
       const bool has_res = p.residual != nullptr;
       auto coords = [&](uint32_t g, int& m0, int& n0) {
-        const int i = static_cast<int>(g / kPCBlocks), cb = static_cast<int>(g % kPCBlocks);
+        const int i = static_cast<int>(g / kCBlocks), cb = static_cast<int>(g % kCBlocks);
         int m_pair, n_blk;
         tile_coords(i, m_pair, n_blk);
         m0 = (m_pair * 2 + static_cast<int>(rank)) * kPM;
-        n0 = n_blk * kPN + cb * 64;
+        n0 = n_blk * kPN + cb * kCCols;
       };
       auto make_free = [&](uint32_t g) {
         const int buf = g % NB, bi = g % kNBar;
@@ -315,14 +319,61 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         sbias[par * 256 + tid] = col < p.N ? __ldg(p.bias + col) : 0.f;
         asm volatile("bar.sync 1, %0;" ::"n"(kPEpiWarps * 32) : "memory");
       }
-      const uint32_t g0 = static_cast<uint32_t>(tile_seq) * kPCBlocks;       // kPCBlocks is even: block cb belongs to group cb % 2
+      const uint32_t g0 = static_cast<uint32_t>(tile_seq) * kCBlocks;
       mbar_wait(&tfull[acc], (static_cast<uint32_t>(tile_seq) >> 1) & 1u);
       tc_fence_after();
 #pragma unroll 1
-      for (int cb = group; cb < kPCBlocks; cb += kPGroups) {
+      for (int cb = group; cb < kCBlocks; cb += kPGroups) {
         const uint32_t gblk = g0 + cb;
         const int buf = gblk % NB;
         uint8_t* cbuf = sC + buf * kPCBytes;
+        if constexpr (kF32) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + lane_base + static_cast<uint32_t>(acc * kPN + cb * 32), r);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&tempty[acc]);
+          mbar_wait(&cfree[gblk % kNBar], (gblk / kNBar) & 1);
+          const int n0 = n_blk * kPN + cb * 32;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias != nullptr) {
+            const float4* bp = reinterpret_cast<const float4*>(sb + (n0 - n_blk * kPN));
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = bp[j / 4];
+              const float2 lo = fadd2(make_float2(v[j], v[j + 1]), make_float2(b.x, b.y));
+              const float2 hi = fadd2(make_float2(v[j + 2], v[j + 3]), make_float2(b.z, b.w));
+              v[j] = lo.x; v[j + 1] = lo.y; v[j + 2] = hi.x; v[j + 3] = hi.y;
+            }
+          }
+          if (p.residual != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 f = *reinterpret_cast<const float4*>(cbuf + swizzled_chunk_offset(erow, q, 128));
+              const float2 lo = fadd2(make_float2(v[q * 4], v[q * 4 + 1]), make_float2(f.x, f.y));
+              const float2 hi = fadd2(make_float2(v[q * 4 + 2], v[q * 4 + 3]), make_float2(f.z, f.w));
+              v[q * 4] = lo.x; v[q * 4 + 1] = lo.y; v[q * 4 + 2] = hi.x; v[q * 4 + 3] = hi.y;
+            }
+          }
+          if (relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (gelu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            *reinterpret_cast<float4*>(cbuf + swizzled_chunk_offset(erow, q, 128)) =
+                make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            if (p.row_sumsq != nullptr && n0 + q * 4 < p.N)
+              ssq += v[q * 4] * v[q * 4] + v[q * 4 + 1] * v[q * 4 + 1] + v[q * 4 + 2] * v[q * 4 + 2] + v[q * 4 + 3] * v[q * 4 + 3];
+          }
+        } else {
         uint32_t r[2][32];
 #pragma unroll
         for (int half = 0; half < 2; ++half)
@@ -384,6 +435,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&cfull[gblk % kNBar]);
@@ -401,11 +453,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int NB, bool kConv>
+template <int NB, bool kConv, bool kF32>
 static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                        const PairParams& p, cudaStream_t stream) {
   using Cfg = PairCfg<NB>;
-  auto kern = gemm_pair_kernel<NB, kConv>;
+  auto kern = gemm_pair_kernel<NB, kConv, kF32>;
   static DeviceOnce once;
   bool& configured = once.flag();
   if (!configured) {
@@ -423,13 +475,13 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return check_launch("gemm_pair_kernel");
 }
 
-template <bool kConv>
+template <bool kConv, bool kF32>
 static int dispatch_pair(int nb, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
                          const PairParams& p, cudaStream_t s) {
   switch (nb) {
-    case 5: return launch_pair<5, kConv>(tmA, tmB, tmC, tmR, p, s);
-    case 4: return launch_pair<4, kConv>(tmA, tmB, tmC, tmR, p, s);
-    default: return launch_pair<2, kConv>(tmA, tmB, tmC, tmR, p, s);
+    case 5: return launch_pair<5, kConv, kF32>(tmA, tmB, tmC, tmR, p, s);
+    case 4: return launch_pair<4, kConv, kF32>(tmA, tmB, tmC, tmR, p, s);
+    default: return launch_pair<2, kConv, kF32>(tmA, tmB, tmC, tmR, p, s);
   }
 }
 
@@ -440,7 +492,8 @@ static int g_pair_mode = -1;           // -1: not initialised (LECB_NO_PAIR deci
 bool pair_gemm_eligible(int64_t M, int N, int K, unsigned flags, bool has_sumsq_f32_out) {
   if (g_pair_mode < 0) g_pair_mode = getenv("LECB_NO_PAIR") != nullptr ? 0 : 1;
   if (g_pair_mode == 0 || has_sumsq_f32_out) return false;
-  if (flags & (LECB_EPI_OUT_F32 | LECB_EPI_RES_F32 | LECB_GEMM_F16_OPERANDS | LECB_EPI_AVGPOOL2)) return false;
+  if (flags & (LECB_GEMM_F16_OPERANDS | LECB_EPI_AVGPOOL2)) return false;
+  if ((flags & LECB_EPI_RES_F32) && !(flags & LECB_EPI_OUT_F32)) return false;
   if (N < kPN || N % 8 != 0 || K % kPK != 0 || K < 4 * kPK) return false;      // K <= 128 layers already run at their HBM bound
   const int sms = sm_count();
   if (sms <= 1) return false;
@@ -471,14 +524,19 @@ int launch_pair_gemm(const void* A, const void* Wt, const float* bias, const voi
   if (st) return st;
   st = encode_tiled_2d(&tmB, Wt, static_cast<uint64_t>(N), static_cast<uint64_t>(K), kPN / 2, kPK);
   if (st) return st;
-  st = encode_tiled_2d(&tmC, out, static_cast<uint64_t>(M), static_cast<uint64_t>(N), kPM, 64);
+  const bool f32 = (flags & LECB_EPI_OUT_F32) != 0;
+  const uint32_t ccols = f32 ? 32 : 64, esz = f32 ? 4 : 2;
+  st = encode_tiled_2d_ex(&tmC, out, static_cast<uint64_t>(M), static_cast<uint64_t>(N), kPM, ccols, esz);
   if (st) return st;
   tmR = tmC;
   if (residual != nullptr) {
-    st = encode_tiled_2d(&tmR, residual, static_cast<uint64_t>(M), static_cast<uint64_t>(N), kPM, 64);
+    st = encode_tiled_2d_ex(&tmR, residual, static_cast<uint64_t>(M), static_cast<uint64_t>(N), kPM, ccols, esz);
     if (st) return st;
   }
-  return dispatch_pair<false>(staging_buffers(p.num_kb, residual != nullptr), tmA, tmB, tmC, tmR, p, stream);
+  // fp32 blocks carry half the columns: twice the blocks in flight for the same bytes
+  const int nb = f32 ? (p.num_kb <= 16 ? 4 : 2) : staging_buffers(p.num_kb, residual != nullptr);
+  if (f32) return dispatch_pair<false, true>(nb, tmA, tmB, tmC, tmR, p, stream);
+  return dispatch_pair<false, false>(nb, tmA, tmB, tmC, tmR, p, stream);
 }
 
 bool pair_conv_eligible(int B, int H, int Wd, int Cin, int Cout, unsigned flags) {
@@ -508,7 +566,7 @@ int launch_pair_conv3x3(const void* x, const void* w, const float* bias, void* o
   if (st) return st;
   st = encode_tiled_2d(&tmC, out, static_cast<uint64_t>(p.M), static_cast<uint64_t>(Cout), kPM, 64);
   if (st) return st;
-  return dispatch_pair<true>(2, tmA, tmB, tmC, tmC, p, stream);
+  return dispatch_pair<true, false>(2, tmA, tmB, tmC, tmC, p, stream);
 }
 
 }  // namespace lecb

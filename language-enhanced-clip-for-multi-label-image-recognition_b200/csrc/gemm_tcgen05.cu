@@ -972,7 +972,8 @@ extern "C" int lecb_gemm_bf16(const void* A, const void* W, const float* bias, c
   LECB_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
                  "lecb_gemm_bf16: operands must be 16-byte aligned");
-  if (pair_gemm_eligible(M, N, K, flags, false))
+  // (a bf16 residual with an fp32 output stays on the single-CTA kernel's direct path)
+  if (pair_gemm_eligible(M, N, K, flags, (flags & LECB_EPI_OUT_F32) && residual != nullptr && !(flags & LECB_EPI_RES_F32)))
     return launch_pair_gemm(A, W, bias, residual, out, row_sumsq, M, N, K, flags, static_cast<cudaStream_t>(stream));
   const int BK = (K % 64 == 0) ? 64 : 32;
   int BN = pick_bn(N);

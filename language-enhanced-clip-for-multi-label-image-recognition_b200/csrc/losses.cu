@@ -128,15 +128,42 @@ ranking_fwd_bwd_kernel(const float* __restrict__ ypred, const float* __restrict_
   float* l_t = l_y + K;
   int* l_j = reinterpret_cast<int*>(l_t + K);
   float acc = 0.f;
-  for (int64_t b = static_cast<int64_t>(blockIdx.x) * kRankWarps + warp; b < B; b += static_cast<int64_t>(gridDim.x) * kRankWarps) {
+  // The row loop is software-pipelined: the next row's scores and targets are requested before this row is processed, so a
+  // warp always has two rows of loads in flight (one row per warp left the kernel latency-bound at 0.27 of HBM peak).
+  const int64_t row_step = static_cast<int64_t>(gridDim.x) * kRankWarps;
+  float yn[CH], tn[CH];
+  {
+    const int64_t b0 = static_cast<int64_t>(blockIdx.x) * kRankWarps + warp;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int k = c * 32 + lane;
+      const bool in = k < K && b0 < B;
+      yn[c] = in ? __ldcs(ypred + b0 * K + k) : 0.f;
+      tn[c] = in ? __ldcs(ytrue + b0 * K + k) : 0.f;
+    }
+  }
+  for (int64_t b = static_cast<int64_t>(blockIdx.x) * kRankWarps + warp; b < B; b += row_step) {
     float y[CH], t[CH], g[CH];
     int n_pos = 0;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
+      y[c] = yn[c] * scale;
+      t[c] = tn[c];
+    }
+    {
+      const int64_t bn = b + row_step;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int k = c * 32 + lane;
+        const bool in = k < K && bn < B;
+        yn[c] = in ? __ldcs(ypred + bn * K + k) : 0.f;
+        tn[c] = in ? __ldcs(ytrue + bn * K + k) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
       const int k = c * 32 + lane;
       const bool in = k < K;
-      y[c] = in ? __ldcs(ypred + b * K + k) * scale : 0.f;
-      t[c] = in ? __ldcs(ytrue + b * K + k) : 0.f;
       g[c] = 0.f;
       const unsigned m = __ballot_sync(0xffffffffu, in && t[c] != 0.f);
       if (in && t[c] != 0.f) {
@@ -233,16 +260,37 @@ kl_softmax_fwd_bwd_kernel(const float* __restrict__ x, const float* __restrict__
                           float* __restrict__ loss_out, int64_t B, int K, float weight, float inv_batch) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float acc = 0.f;
-  for (int64_t b = static_cast<int64_t>(blockIdx.x) * kRankWarps + warp; b < B; b += static_cast<int64_t>(gridDim.x) * kRankWarps) {
+  const int64_t row_step = static_cast<int64_t>(gridDim.x) * kRankWarps;
+  float an[CH], mn[CH];                         // next row, requested one iteration ahead (two rows of loads in flight)
+  {
+    const int64_t b0 = static_cast<int64_t>(blockIdx.x) * kRankWarps + warp;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int k = c * 32 + lane;
+      const bool in = k < K && b0 < B;
+      an[c] = in ? __ldcs(x + b0 * K + k) : -INFINITY;
+      mn[c] = in ? __ldcs(xm + b0 * K + k) : -INFINITY;
+    }
+  }
+  for (int64_t b = static_cast<int64_t>(blockIdx.x) * kRankWarps + warp; b < B; b += row_step) {
     float a[CH], m[CH];
     float amax = -INFINITY, mmax = -INFINITY;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
-      const int k = c * 32 + lane;
-      a[c] = k < K ? __ldcs(x + b * K + k) : -INFINITY;
-      m[c] = k < K ? __ldcs(xm + b * K + k) : -INFINITY;
+      a[c] = an[c];
+      m[c] = mn[c];
       amax = fmaxf(amax, a[c]);
       mmax = fmaxf(mmax, m[c]);
+    }
+    {
+      const int64_t bn = b + row_step;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int k = c * 32 + lane;
+        const bool in = k < K && bn < B;
+        an[c] = in ? __ldcs(x + bn * K + k) : -INFINITY;
+        mn[c] = in ? __ldcs(xm + bn * K + k) : -INFINITY;
+      }
     }
     amax = warp_max(amax);
     mmax = warp_max(mmax);

@@ -31,7 +31,7 @@ struct StemNorm {
 };
 
 template <bool kU8>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 stem_conv1_tc_kernel(const void* __restrict__ xin, const float* __restrict__ w27, const float* __restrict__ bias,
                      __nv_bfloat16* __restrict__ out, int B, int H, int W, int tiles_x, int tiles_y, int num_tiles, StemNorm nrm) {
   __shared__ __align__(1024) uint8_t sA[128 * kStemK * 2];        // 8 KB, rows of 64 bytes
@@ -82,89 +82,136 @@ stem_conv1_tc_kernel(const void* __restrict__ xin, const float* __restrict__ w27
   uint32_t phase = 0;
   const int py = t / kTileW, px = t % kTileW;
 
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int tx = tile % tiles_x;
-    const int ty = (tile / tiles_x) % tiles_y;
-    const int b = tile / (tiles_x * tiles_y);
-    const int ho0 = ty * kTileH, wo0 = tx * kTileW;
-    const int hi0 = 2 * ho0 - 1, wi0 = 2 * wo0 - 1;
-    // ---- stage the input patch: [17][33][3] bf16, zeros outside the image (conv padding, ragged tiles) ----
-    // One warp per patch row segment, lanes along the contiguous axis (coalesced), no per-element divisions.
-    const int lane = t & 31;
+  // ---- input staging, split in two so that the NEXT tile's global loads are in flight while this tile is multiplied and
+  // stored: fetch() issues the loads into registers, stash() converts them into the [17][33][3] bf16 patch (zeros outside
+  // the image: conv padding, ragged tiles).  ncu on the first version of this kernel: 62 % issue-slot utilisation with 40 % of
+  // all instructions in per-segment 64-bit address arithmetic and 16 % in the tile -> (image, row, column) divisions — so
+  // the loops below run over compile-time (plane, row group) indices with 32-bit offsets from one per-tile base pointer, the
+  // tile origin is computed once per tile, and the 33rd column of the 51 segments is fetched by 51 threads in one step.
+  const int lane = t & 31;
+  constexpr int kRowsPerWarp = (kPatchH + 3) / 4;                      // 5 patch rows per warp (row = warp + 4 j)
+  uint32_t words[kU8 ? kRowsPerWarp : 1];                              // u8: one aligned word of each of the warp's rows
+  float v0[kU8 ? 1 : 3 * kRowsPerWarp], v1 = 0.f;                      // fp32: columns 0..31 of (plane, row); column 32 of segment t
+  const int64_t total_u8 = static_cast<int64_t>(B) * H * W * 3;
+  const int tiles_per_image = tiles_x * tiles_y;
+  struct Origin {
+    int b, hi0, wi0;
+  };
+  auto tile_origin = [&](int tile) {
+    Origin o;
+    o.b = tile / tiles_per_image;
+    const int rem = tile - o.b * tiles_per_image;
+    const int ty = rem / tiles_x;
+    o.hi0 = 2 * (ty * kTileH) - 1;
+    o.wi0 = 2 * ((rem - ty * tiles_x) * kTileW) - 1;
+    return o;
+  };
+  auto fetch = [&](const Origin& o) {
     if (kU8) {
       // a patch row is 99 contiguous bytes of the NHWC image: lanes 0..25 fetch the aligned 32-bit words covering it
       const uint8_t* xb = static_cast<const uint8_t*>(xin);
-      const int64_t total = static_cast<int64_t>(B) * H * W * 3;
-      constexpr int kRowsPerWarp = (kPatchH + 3) / 4;                    // 5: every word load is issued before the first use
-      uint32_t words[kRowsPerWarp];
+      const int64_t img0 = static_cast<int64_t>(o.b) * H * W * 3;
 #pragma unroll
       for (int it = 0; it < kRowsPerWarp; ++it) {
         const int r = warp + 4 * it;
-        const int hi = hi0 + r;
+        const int hi = o.hi0 + r;
         const bool row_ok = r < kPatchH && hi >= 0 && hi < H;
-        const int64_t g0 = ((static_cast<int64_t>(b) * H + (row_ok ? hi : 0)) * W + wi0) * 3;      // first byte of the row (may be < 0)
-        const int64_t o = (g0 >= 0 ? g0 : g0 - 3) / 4 * 4 + 4 * lane;                             // aligned down (floor)
+        const int64_t g0 = img0 + ((row_ok ? hi : 0) * W + o.wi0) * 3;                            // first byte of the row (may be < 0)
+        const int64_t off = (g0 & ~static_cast<int64_t>(3)) + 4 * lane;                           // aligned down (floor, two's complement)
         uint32_t word = 0;
         if (row_ok && lane < 26) {
-          if (o >= 0 && o + 4 <= total) {
-            word = __ldg(reinterpret_cast<const uint32_t*>(xb + o));
+          if (off >= 0 && off + 4 <= total_u8) {
+            word = __ldg(reinterpret_cast<const uint32_t*>(xb + off));
           } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              if (o + k >= 0 && o + k < total) word |= static_cast<uint32_t>(__ldg(xb + o + k)) << (8 * k);
+              if (off + k >= 0 && off + k < total_u8) word |= static_cast<uint32_t>(__ldg(xb + off + k)) << (8 * k);
           }
         }
-        words[it] = word;
+        words[kU8 ? it : 0] = word;
       }
+    } else {
+      const float* xi = static_cast<const float*>(xin) + static_cast<int64_t>(o.b) * 3 * H * W;       // this image
+      const int plane = H * W;
+      const int wa = o.wi0 + lane;
+      const bool col_ok = wa >= 0 && wa < W;
+#pragma unroll
+      for (int j = 0; j < kRowsPerWarp; ++j) {
+        const int r = warp + 4 * j;
+        const int hi = o.hi0 + r;
+        const bool ok = r < kPatchH && hi >= 0 && hi < H && col_ok;
+        const int off = hi * W + wa;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) v0[kU8 ? 0 : ci * kRowsPerWarp + j] = ok ? __ldg(xi + ci * plane + off) : 0.f;
+      }
+      // column 32 of segment t = (plane t / 17, row t % 17): 51 threads, one load each
+      {
+        const int ci = t / kPatchH, r = t - ci * kPatchH;
+        const int hi = o.hi0 + r, wb = o.wi0 + 32;
+        v1 = (t < 3 * kPatchH && hi >= 0 && hi < H && wb < W) ? __ldg(xi + ci * plane + hi * W + wb) : 0.f;      // wb >= 31 > 0
+      }
+    }
+  };
+  auto stash = [&](const Origin& o) {
+    if (kU8) {
+      // lane l holds bytes [4l, 4l+4) of the aligned window; byte cc = 4l + k - shift of the row is (column cc / 3, channel cc % 3).
+      // Only tiles on the left / right image border have invalid columns: the common tiles skip the per-byte column test.
+      const int img_lo2 = static_cast<int>((static_cast<int64_t>(o.b) * H * W * 3) & 3);
+      const bool edge_cols = o.wi0 < 0 || o.wi0 + kPatchW > W;
 #pragma unroll
       for (int it = 0; it < kRowsPerWarp; ++it) {
         const int r = warp + 4 * it;
-        const int hi = hi0 + r;
+        const int hi = o.hi0 + r;
         const bool row_ok = hi >= 0 && hi < H;
         if (r < kPatchH && lane < 26) {
-          const int64_t g0 = ((static_cast<int64_t>(b) * H + (row_ok ? hi : 0)) * W + wi0) * 3;
-          const int shift = static_cast<int>(g0 - (g0 >= 0 ? g0 : g0 - 3) / 4 * 4);                // 0..3
+          // low two bits of the row's first byte address (floor-mod also for the negative offset of the first image row)
+          const int shift = (img_lo2 + (((row_ok ? hi : 0) * W + o.wi0) * 3)) & 3;
+          const int cc0 = 4 * lane - shift;                              // row byte of this lane's first byte (may be < 0)
+          const uint32_t w4 = words[kU8 ? it : 0];
+          __nv_bfloat16* prow = patch + r * kPatchPitch;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int cc = 4 * lane + k - shift;                         // byte position inside the row: col * 3 + ci
+            const int cc = cc0 + k;
             if (cc >= 0 && cc < kPatchW * 3) {
-              const int c = (cc * 171) >> 9;                             // cc / 3 for cc < 512
+              const int c = (cc * 171) >> 9;                             // cc / 3 for 0 <= cc < 512
               const int ci = cc - 3 * c;
-              const int wi = wi0 + c;
-              const bool ok = row_ok && wi >= 0 && wi < W;
-              patch[r * kPatchPitch + cc] = ok ? lut[ci * 256 + ((words[it] >> (8 * k)) & 0xffu)] : __float2bfloat16(0.f);
+              bool ok = row_ok;
+              if (edge_cols) {
+                const int wi = o.wi0 + c;
+                ok = ok && wi >= 0 && wi < W;
+              }
+              prow[cc] = ok ? lut[ci * 256 + ((w4 >> (8 * k)) & 0xffu)] : __float2bfloat16(0.f);
             }
           }
         }
       }
     } else {
-      // 3 planes x 17 rows = 51 segments of 33 floats; all of a warp's loads are issued before the first store
-      const float* x = static_cast<const float*>(xin) + static_cast<int64_t>(b) * 3 * H * W;
-      constexpr int kSeg = 3 * kPatchH;                                  // 51
-      constexpr int kPerWarp = (kSeg + 3) / 4;                           // 13
-      float v0[kPerWarp], v1[kPerWarp];
 #pragma unroll
-      for (int it = 0; it < kPerWarp; ++it) {
-        const int sgm = warp + 4 * it;
-        const int ci = sgm / kPatchH, r = sgm - ci * kPatchH;
-        const int hi = hi0 + r;
-        const bool row_ok = sgm < kSeg && hi >= 0 && hi < H;
-        const float* rp = x + (static_cast<int64_t>(ci) * H + (row_ok ? hi : 0)) * W;
-        const int wa = wi0 + lane, wb = wi0 + 32;
-        v0[it] = (row_ok && wa >= 0 && wa < W) ? __ldg(rp + wa) : 0.f;
-        v1[it] = (row_ok && lane == 0 && wb < W) ? __ldg(rp + wb) : 0.f;       // wb >= 31 > 0 always
-      }
+      for (int j = 0; j < kRowsPerWarp; ++j) {
+        const int r = warp + 4 * j;
+        if (r < kPatchH) {
 #pragma unroll
-      for (int it = 0; it < kPerWarp; ++it) {
-        const int sgm = warp + 4 * it;
-        if (sgm < kSeg) {
-          const int ci = sgm / kPatchH, r = sgm - ci * kPatchH;
-          patch[r * kPatchPitch + lane * 3 + ci] = __float2bfloat16(v0[it]);
-          if (lane == 0) patch[r * kPatchPitch + 32 * 3 + ci] = __float2bfloat16(v1[it]);
+          for (int ci = 0; ci < 3; ++ci) patch[r * kPatchPitch + lane * 3 + ci] = __float2bfloat16(v0[kU8 ? 0 : ci * kRowsPerWarp + j]);
         }
       }
+      if (t < 3 * kPatchH) {
+        const int ci = t / kPatchH, r = t - ci * kPatchH;
+        patch[r * kPatchPitch + 32 * 3 + ci] = __float2bfloat16(v1);
+      }
     }
+  };
+
+  Origin cur = tile_origin(blockIdx.x < static_cast<unsigned>(num_tiles) ? blockIdx.x : 0);
+  if (static_cast<int>(blockIdx.x) < num_tiles) fetch(cur);
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int b = cur.b, ho0 = (cur.hi0 + 1) / 2, wo0 = (cur.wi0 + 1) / 2;
+    // the previous iteration's readers of `patch` finished before its second __syncthreads
+    stash(cur);
     __syncthreads();
+    if (tile + static_cast<int>(gridDim.x) < num_tiles) {      // the next tile's loads are in flight during the MMA and the stores
+      cur = tile_origin(tile + gridDim.x);
+      fetch(cur);
+    }
     // ---- this thread's im2col row: three runs of 9 consecutive patch elements (ky = 0, 1, 2) ----
     {
       uint16_t v[kStemK];

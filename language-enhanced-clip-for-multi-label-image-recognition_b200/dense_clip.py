@@ -196,6 +196,17 @@ class DenseCLIPB200(nn.Module):
         self.return_interm_layers = return_interm_layers
         ap = getattr(clip_model.visual, "attnpool", None)
         if ap is not None:                     # ModifiedResNet tower (the reference's only dense path)
+            # T:364-368: `visual_encoder = IntermediateLayerGetter(self.model.visual, return_layers)` re-registers the trunk's
+            # children (up to the last returned layer) under a second name, and a slice of the attnpool positional embedding is
+            # kept as a plain attribute: no compute here, but the same state_dict keys / attribute surface as the reference
+            last = "layer4"
+            alias = nn.ModuleDict()
+            for name, child in clip_model.visual.named_children():
+                alias[name] = child
+                if name == last:
+                    break
+            self.visual_encoder = alias
+            self.positional_embedding = ap.positional_embedding[1::]
             self.v_linear_weight, self.v_linear_bias = ap.v_proj.weight, ap.v_proj.bias      # aliases, T:370-373
             self.c_linear_weight, self.c_linear_bias = ap.c_proj.weight, ap.c_proj.bias
         self.logit_scale = clip_model.logit_scale

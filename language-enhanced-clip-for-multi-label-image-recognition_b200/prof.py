@@ -67,7 +67,7 @@ class KernelTimer:
         lib = _lib.lib
         for name in _lib.SIGNATURES:
             if name in ("lecb_abi_version", "lecb_last_error", "lecb_launch_count", "lecb_conv3x3_pool_fusable", "lecb_resize_ksize",
-                        "lecb_resize_plan", "lecb_window_plan_size", "lecb_window_plan", "lecb_set_pair_gemm"):      # host-only
+                        "lecb_resize_plan", "lecb_window_plan_size", "lecb_window_plan", "lecb_set_pair_gemm", "lecb_set_attn_poly"):      # host-only
                 continue
             fn = getattr(lib, name)
             self._saved[name] = fn

@@ -89,12 +89,30 @@ class _DualPromptHead(torch.autograd.Function):
         return (None, d_scale) + grads
 
 
+def caption_run_length(model, captions):
+    """Positions of the caption tower that can matter: everything up to the last EOT of the batch.  The mask is causal
+    (M:364-370), so later positions cannot influence earlier ones, and they are padding (token id 0) whose logits get -10000
+    before the token softmax (T:491-498): their weight is exactly zero in fp32.  Real captions end near position 20 of 77
+    (74 % of the caption FLOPs are padding), so the tower runs on [B, l_run] instead of [B, 77].
+    Needs one host read of the batch's longest caption; under CUDA-graph capture (no host reads) the caller's promise
+    `model.caption_len_hint` is used, else the full length."""
+    l = captions.shape[1]
+    if not bool(getattr(model, "trim_caption_padding", True)):
+        return l
+    if captions.is_cuda and torch.cuda.is_current_stream_capturing():
+        hint = getattr(model, "caption_len_hint", None)
+        return l if hint is None else max(1, min(l, int(hint)))
+    return max(1, min(l, int(captions.argmax(dim=-1).max()) + 1))
+
+
 @torch.no_grad()
-def _caption_branch(model, captions):
-    """T:474-477,485-486,491: per-token caption features (frozen path)."""
+def _caption_branch(model, captions, l_run=None):
+    """T:474-477,485-486,491: per-token caption features (frozen path) for the first l_run positions."""
     tw = model.text_encoder.tower()
+    if l_run is not None and l_run < captions.shape[1]:
+        captions = captions[:, :l_run].contiguous()
     b, l = captions.shape
-    x = (tw.tok[captions] + tw.pos).contiguous()
+    x = (tw.tok[captions] + tw.pos[:l]).contiguous()
     n, _, w = x.shape
     xs = x.reshape(n * l, w)
     for blk in tw.blocks:
@@ -138,9 +156,12 @@ def forward_train(model, captions):
     if bool(_cfg(model, "TRAIN.IF_LEARN_spatial_SCALE", False)):
         raise NotImplementedError("lecb200: a learnable spatial scale is not supported on the prompt-tuning path "
                                   "(every shipped config fixes TRAIN.spatial_SCALE_text)")
+    l_full = captions.shape[1]
+    l_run = caption_run_length(model, captions)           # before the upload when the batch still lives on the host
     captions = captions.to(model.text_encoder.positional_embedding.device)
-    b, l = captions.shape
-    local, ssq, mask, g_unit = _caption_branch(model, captions)
+    b = captions.shape[0]
+    l = l_run
+    local, ssq, mask, g_unit = _caption_branch(model, captions, l_run)
     prompts, prompts_double, prompts_evidence, temperature, spatial_T, _ = model.prompt_learner()
     learn = bool(_cfg(model, "TRAIN.IF_LEARN_SCALE", False))
     logit_scale = float(temperature.exp()) if learn else 4.0
@@ -166,7 +187,12 @@ def forward_train(model, captions):
     plist = (prompts, prompts_double, prompts_evidence) if use_evidence else (prompts, prompts_double)
     logits, logits_local, text_features = _DualPromptHead.apply(pack, temperature if learn else None, *plist)
     with torch.no_grad():
-        image_features = ops.l2norm_rows(local, out_dtype=torch.float32).view(b, l, -1).permute(1, 0, 2)
+        feats = ops.l2norm_rows(local, out_dtype=torch.float32).view(b, l, -1)
+        if l < l_full:
+            # positions past the batch's last EOT were not run: zeros there (the reference holds the normalised features of
+            # pad tokens, which its own -10000 mask keeps from reaching any logit)
+            feats = torch.nn.functional.pad(feats, (0, 0, 0, l_full - l))
+        image_features = feats.permute(1, 0, 2)
     logits_m, logits_local_m = None, None
     if bool(_cfg(model, "TRAIN.ema", False)):
         with torch.no_grad():

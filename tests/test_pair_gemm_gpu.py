@@ -88,3 +88,34 @@ def test_pair_path_is_taken(pair_switch):
     n0 = lecb200.launch_count()
     ops.gemm(a, w)
     assert lecb200.launch_count() - n0 == 1
+
+
+@pytest.mark.parametrize("m,n,k", [(100480, 768, 768), (40000, 768, 3072), (38000 + 13, 1024, 1024), (37888, 320, 256)])
+def test_pair_gemm_f32_out_and_residual(m, n, k, pair_switch):
+    """fp32 output (+ fp32 residual stream) through the pair kernel's 32-column staged blocks: the ViT / text-tower
+    out-proj and MLP-proj GEMMs (M:226-227)."""
+    from lecb200 import ops
+    a = _rand((m, k), 31).bfloat16()
+    w = _rand((n, k), 32, k ** -0.5).bfloat16()
+    bias = _rand((n,), 33)
+    res = _rand((m, n), 34)
+    base = a.float() @ w.float().t() + bias
+    tol = 2e-3 * (base.abs().max().item() + 1)
+    for name, fn, want in (("f32", lambda: ops.gemm(a, w, bias, out_f32=True), base),
+                           ("f32+res", lambda: ops.gemm_f32res(a, w, bias, res), base + res),
+                           ("f32+gelu", lambda: ops.gemm(a, w, bias, quick_gelu=True, out_f32=True), base * torch.sigmoid(1.702 * base))):
+        pair_switch(1)
+        got = fn()
+        torch.cuda.synchronize()
+        assert got.dtype == torch.float32
+        assert (got - want).abs().max().item() <= tol, name
+        pair_switch(0)
+        single = fn()
+        torch.cuda.synchronize()
+        assert torch.equal(got, single), f"{name}: pair and single-CTA kernels differ by {(got - single).abs().max().item()}"
+    pair_switch(1)
+    ssq = torch.zeros((m,), device="cuda")
+    out = ops.gemm(a, w, bias, out_f32=True, row_sumsq=ssq)
+    torch.cuda.synchronize()
+    want = out.pow(2).sum(-1)
+    assert ((ssq - want).abs() / (want + 1e-6)).max().item() < 1e-4
