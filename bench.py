@@ -598,12 +598,17 @@ def bench_train(cx, per_gpu_batch, steps, warmup, use_graph=True):
     caps = caps.to(dev)
     y = synth.labels(b, len(names), 100 + rank).to(dev)
 
-    def eager_step():
+    def compute():                           # forward + loss + backward + gradients packed into the flat bucket
         out = model(None, caps)
         loss = losses.ASL_loss(out[0], y) + losses.ASL_loss(out[1], y)
         opt.zero_grad()
         loss.backward()
-        opt.step()                           # pack -> all-reduce (N > 1) -> fused SGD from the flat bucket
+        opt.pack()
+        return loss
+
+    def eager_step():
+        loss = compute()
+        opt.reduce_and_update()              # all-reduce (N > 1) -> fused SGD from the flat bucket
         return loss
 
     step, graphed = eager_step, False
@@ -620,11 +625,15 @@ def bench_train(cx, per_gpu_batch, steps, warmup, use_graph=True):
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             opt.zero_grad()
+            # one rank: the whole step is one graph.  Several ranks: the collective and the update stay outside the capture
+            # (two launches + one all-reduce per step), so a capture never wraps an NCCL call
             with torch.cuda.graph(graph):
-                static_loss = eager_step()
+                static_loss = eager_step() if world == 1 else compute()
 
             def step():
                 graph.replay()
+                if world > 1:
+                    opt.reduce_and_update()
                 return static_loss
             step()
             graphed = True

@@ -170,6 +170,16 @@ int lecb_ranking_cooc_fwd_bwd(const float* logits, const float* targets, const f
 int lecb_kl_softmax_fwd_bwd(const float* logits, const float* logits_target, float* grad, float* loss, int64_t B, int K,
                             float weight, void* stream);
 
+/* ---- distribution-balanced loss: `ResampleLoss` (trainers/dbl.py:263-445; LOSSFUNC 'dbl', T:818-841) with use_sigmoid=True,
+ * partial=False: re-balanced weights sigmoid(beta (freq_inv_k / sum_k y_k freq_inv_k - gamma)) + alpha (dbl.py:411-416;
+ * freq_inv NULL = no re-weighting), logit regularisation (init_bias fp32 [K] or NULL, neg_scale or 0; dbl.py:401-409),
+ * weighted BCE-with-logits averaged over B*K, and the optional focal factor balance_param (1 - e^-L0)^gamma on the two
+ * scalar means (dbl.py:373-383).  Writes loss (device scalar) and dloss/dlogits; scratch2 = two floats (focal only). ---- */
+int lecb_resample_bce_fwd_bwd(const float* logits, const float* labels, const float* freq_inv, const float* init_bias,
+                              float* grad, float* loss, float* scratch2, int64_t B, int K, float map_alpha, float map_beta,
+                              float map_gamma, float neg_scale, int focal, float focal_gamma, float balance_param,
+                              float loss_weight, void* stream);
+
 /* ---- multi-tensor updates over the prompt-learner parameter list: HOST arrays of `count` (<= 16) device pointers and
  * element counts, one launch each ----
  * lecb_ema_update: twin_i <- twin_i * momentum + live_i * one_minus_momentum (_momentum_update, T:554-559; the caller

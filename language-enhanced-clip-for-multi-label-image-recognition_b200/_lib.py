@@ -48,6 +48,8 @@ SIGNATURES = {
     "lecb_ranking_cooc_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float,
                                           c_void_p]),
     "lecb_kl_softmax_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_float, c_void_p]),
+    "lecb_resample_bce_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int,
+                                          c_float, c_float, c_float, c_float, c_int, c_float, c_float, c_float, c_void_p]),
     "lecb_ema_update": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p]),
     "lecb_pack_f32": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "lecb_unpack_scale_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p]),

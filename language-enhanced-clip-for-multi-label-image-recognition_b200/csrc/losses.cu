@@ -331,6 +331,117 @@ kl_softmax_fwd_bwd_kernel(const float* __restrict__ x, const float* __restrict__
   }
 }
 
+
+// Distribution-balanced loss (`ResampleLoss`, trainers/dbl.py:263-445, built at T:818-830 for LOSSFUNC 'dbl') with
+// use_sigmoid=True, partial=False: re-balanced weights (dbl.py:411-416), logit regularisation (dbl.py:401-409), weighted
+// binary cross-entropy with logits averaged over all B*K elements (dbl.py:49-65) and the optional focal factor — which in
+// the reference multiplies two SCALARS, because its `binary_cross_entropy` always reduces with 'mean' (dbl.py:61-63, 373-383).
+// One warp per row (the repeat rate sum_k y_k / freq_k is a row reduction).
+//   kMode 0: no focal term: loss and dloss/dlogits in one pass.
+//   kMode 1: focal, pass 1: sums[0] += unweighted BCE, sums[1] += weighted BCE (no gradient).
+//   kMode 2: focal, pass 2: loss = bp (1 - e^-L0)^g Lw with L0 = sums[0] / n, Lw = sums[1] / n;
+//            grad = dLw * bp (1 - e^-L0)^g + dL0 * bp g (1 - e^-L0)^(g-1) e^-L0 Lw.
+struct ResampleParams {
+  float map_alpha, map_beta, map_gamma, neg_scale, focal_gamma, balance_param, loss_weight, inv_n;
+  int reweight, has_neg_scale;
+};
+
+template <int CH, int kMode>
+__global__ void __launch_bounds__(kRankWarps * 32)
+resample_bce_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ freq_inv,
+                    const float* __restrict__ init_bias, float* __restrict__ grad, float* __restrict__ loss_out,
+                    float* __restrict__ sums, int64_t B, int K, ResampleParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc0 = 0.f, accw = 0.f;
+  float c_w = p.loss_weight, c_0 = 0.f;          // gradient coefficients of the weighted / unweighted mean
+  if (kMode == 2) {
+    const float l0 = sums[0] * p.inv_n, lw = sums[1] * p.inv_n;
+    const float q = 1.0f - expf(-l0);
+    const float f = p.balance_param * powf(q, p.focal_gamma);
+    const float df = p.balance_param * p.focal_gamma * powf(q, p.focal_gamma - 1.0f) * expf(-l0);
+    c_w = p.loss_weight * f;
+    c_0 = p.loss_weight * df * lw;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *loss_out = p.loss_weight * f * lw;
+  }
+  for (int64_t b = static_cast<int64_t>(blockIdx.x) * kRankWarps + warp; b < B; b += static_cast<int64_t>(gridDim.x) * kRankWarps) {
+    float xv[CH], yv[CH], fi[CH];
+    float rr = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int k = c * 32 + lane;
+      const bool in = k < K;
+      xv[c] = in ? __ldcs(x + b * K + k) : 0.f;
+      yv[c] = in ? __ldcs(y + b * K + k) : 0.f;
+      fi[c] = (in && p.reweight) ? __ldg(freq_inv + k) : 0.f;
+      rr += yv[c] * fi[c];
+    }
+    if (p.reweight) rr = warp_sum(rr);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int k = c * 32 + lane;
+      if (k < K) {
+        float w = 1.0f;
+        if (p.reweight) {      // sigmoid(beta * (freq_inv / repeat_rate - gamma)) + alpha; a row without positives divides by zero -> 1 + alpha
+          const float pw = fi[c] / rr;
+          w = 1.0f / (1.0f + expf(-p.map_beta * (pw - p.map_gamma))) + p.map_alpha;
+        }
+        float z = xv[c] + (init_bias ? __ldg(init_bias + k) : 0.f);
+        float dz = 1.0f;
+        if (p.has_neg_scale) {
+          dz = (1.0f - yv[c]) * p.neg_scale + yv[c];
+          z = z * (1.0f - yv[c]) * p.neg_scale + z * yv[c];
+          w = w / p.neg_scale * (1.0f - yv[c]) + w * yv[c];
+        }
+        // binary_cross_entropy_with_logits: max(z, 0) - z y + log(1 + exp(-|z|));  d/dz = sigmoid(z) - y
+        const float e = expf(-fabsf(z));
+        const float bce = fmaxf(z, 0.f) - z * yv[c] + log1pf(e);
+        const float sg = z >= 0.f ? 1.0f / (1.0f + e) : e / (1.0f + e);
+        acc0 += bce;
+        accw += w * bce;
+        if (kMode != 1 && grad) __stcs(grad + b * K + k, (c_w * w + c_0) * (sg - yv[c]) * dz * p.inv_n);
+      }
+    }
+  }
+  if (kMode == 2) return;
+  __shared__ float s0[kRankWarps], sw[kRankWarps];
+  acc0 = warp_sum(acc0);
+  accw = warp_sum(accw);
+  if (lane == 0) {
+    s0[warp] = acc0;
+    sw[warp] = accw;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, bsum = 0.f;
+#pragma unroll
+    for (int w = 0; w < kRankWarps; ++w) {
+      a += s0[w];
+      bsum += sw[w];
+    }
+    if (kMode == 0) {
+      atomicAdd(loss_out, p.loss_weight * bsum * p.inv_n);
+    } else {
+      atomicAdd(sums, a);
+      atomicAdd(sums + 1, bsum);
+    }
+  }
+}
+
+template <int kMode>
+static int launch_resample(const float* x, const float* y, const float* freq_inv, const float* init_bias, float* grad, float* loss,
+                           float* sums, int64_t B, int K, const ResampleParams& p, cudaStream_t s) {
+  int64_t blocks = (B + kRankWarps - 1) / kRankWarps;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  const int chunks = (K + 31) / 32;
+  if (chunks <= 3)
+    resample_bce_kernel<3, kMode><<<static_cast<unsigned>(blocks), kRankWarps * 32, 0, s>>>(x, y, freq_inv, init_bias, grad, loss, sums, B, K, p);
+  else
+    resample_bce_kernel<8, kMode><<<static_cast<unsigned>(blocks), kRankWarps * 32, 0, s>>>(x, y, freq_inv, init_bias, grad, loss, sums, B, K, p);
+  count_launch();
+  return check_launch("resample_bce_kernel");
+}
+
 template <bool kCooc>
 static int launch_ranking(const float* logits, const float* targets, const float* wt, float* grad, float* loss, int64_t B,
                           int K, float scale, float margin, cudaStream_t s) {
@@ -419,4 +530,24 @@ extern "C" int lecb_kl_softmax_fwd_bwd(const float* logits, const float* logits_
     kl_softmax_fwd_bwd_kernel<8><<<static_cast<unsigned>(blocks), kRankWarps * 32, 0, s>>>(logits, logits_target, grad, loss, B, K, weight, inv_b);
   count_launch();
   return check_launch("kl_softmax_fwd_bwd_kernel");
+}
+
+extern "C" int lecb_resample_bce_fwd_bwd(const float* logits, const float* labels, const float* freq_inv, const float* init_bias,
+                                         float* grad, float* loss, float* scratch2, int64_t B, int K, float map_alpha,
+                                         float map_beta, float map_gamma, float neg_scale, int focal, float focal_gamma,
+                                         float balance_param, float loss_weight, void* stream) {
+  LECB_CHECK_ARG(logits && labels && loss, "lecb_resample_bce_fwd_bwd: null pointer");
+  LECB_CHECK_ARG(B > 0 && K > 0 && K <= 256, "lecb_resample_bce_fwd_bwd: need 0 < K <= 256");
+  LECB_CHECK_ARG(!focal || scratch2, "lecb_resample_bce_fwd_bwd: the focal variant needs two floats of scratch");
+  LECB_CHECK_ARG(neg_scale == 0.f || freq_inv, "lecb_resample_bce_fwd_bwd: neg_scale rescales the weights: it needs reweighting (freq_inv)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ResampleParams p{map_alpha, map_beta, map_gamma, neg_scale, focal_gamma, balance_param, loss_weight,
+                   1.0f / static_cast<float>(B * K), freq_inv ? 1 : 0, neg_scale != 0.f ? 1 : 0};
+  cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), s);
+  if (e == cudaSuccess && focal) e = cudaMemsetAsync(scratch2, 0, 2 * sizeof(float), s);
+  if (e != cudaSuccess) return fail(LECB_ERR_CUDA, "lecb_resample_bce_fwd_bwd: memset: %s", cudaGetErrorString(e));
+  if (!focal) return launch_resample<0>(logits, labels, freq_inv, init_bias, grad, loss, nullptr, B, K, p, s);
+  int st = launch_resample<1>(logits, labels, freq_inv, init_bias, nullptr, loss, scratch2, B, K, p, s);
+  if (st) return st;
+  return launch_resample<2>(logits, labels, freq_inv, init_bias, grad, loss, scratch2, B, K, p, s);
 }

@@ -131,8 +131,22 @@ class PromptSGD:
 
     @torch.no_grad()
     def step(self, group=None):
+        self.pack()
+        self.reduce_and_update(group)
+
+    @torch.no_grad()
+    def pack(self):
+        """First half of step(): gradients -> flat bucket (one launch; safe inside a CUDA-graph capture of the step)."""
+        self.bucket.pack()
+
+    @torch.no_grad()
+    def reduce_and_update(self, group=None):
+        """Second half: all-reduce the bucket over the ranks (if any) and apply the fused SGD update from it."""
         from . import ops
-        scale = self.bucket.allreduce_sum(group)
+        scale = 1.0
+        if multi_rank(group):
+            dist.all_reduce(self.bucket.flat, op=dist.ReduceOp.SUM, group=group)
+            scale = 1.0 / dist.get_world_size(group)
         ops.sgd_step(self.bucket.flat, [p.data for p in self.params], self.bufs, self.lr, self.momentum, self.weight_decay,
                      grad_scale=scale)
 

@@ -81,3 +81,52 @@ def dualcoop_loss(inputs, inputs_g, targets):
 def ASL_loss(inputs, targets):
     return AsymmetricLoss_partial(gamma_neg=2, gamma_pos=1, clip=0.05)(inputs, targets, thresh_pos=0.9, thresh_neg=0.9,
                                                                          if_partial=False)
+
+
+class ResampleLoss(nn.Module):
+    """`ResampleLoss` of trainers/dbl.py:263-445 (LOSSFUNC 'dbl', built at T:818-830) on one fused kernel.
+
+    Same constructor keywords as the reference; the class frequencies come from `freq_file` (a pickle with `class_freq` /
+    `neg_class_freq`, what `mmcv.load` reads there) or directly from the additive `class_freq=` / `neg_class_freq=` arguments.
+    Supported: use_sigmoid=True, partial=False, reweight_func None | 'rebalance', weight_norm=None, any focal / map_param /
+    logit_reg setting — the combinations T:823-839 construct.  The in-place `logits += init_bias` side effect of dbl.py:405
+    is not reproduced (the argument is left untouched, like `ranking_loss`)."""
+
+    def __init__(self, use_sigmoid=False, reduction='mean', loss_weight=1.0, partial=False,
+                 focal=dict(focal=True, balance_param=2.0, gamma=2), CB_loss=dict(CB_beta=0.9, CB_mode='average_w'),
+                 map_param=dict(alpha=10.0, beta=0.2, gamma=0.1), logit_reg=dict(neg_scale=5.0, init_bias=0.1),
+                 reweight_func=None, weight_norm=None, freq_file='./class_freq.pkl', class_freq=None, neg_class_freq=None,
+                 device="cuda"):
+        super().__init__()
+        if not use_sigmoid or partial:
+            raise NotImplementedError("lecb200 ResampleLoss: use_sigmoid=True, partial=False (the configuration built at T:823-830)")
+        if reweight_func not in (None, "rebalance") or weight_norm is not None:
+            raise NotImplementedError(f"lecb200 ResampleLoss: reweight_func={reweight_func!r} / weight_norm={weight_norm!r} is not built")
+        if reduction != "mean":
+            raise NotImplementedError("lecb200 ResampleLoss: reduction='mean' (dbl.py:61-63 averages whatever is asked)")
+        if class_freq is None:
+            import pickle
+            with open(freq_file, "rb") as f:
+                stats = pickle.load(f)
+            class_freq, neg_class_freq = stats["class_freq"], stats["neg_class_freq"]
+        cf = torch.as_tensor(class_freq, dtype=torch.float32, device=device)
+        ncf = torch.as_tensor(neg_class_freq, dtype=torch.float32, device=device)
+        self.loss_weight, self.reweight_func = float(loss_weight), reweight_func
+        self.focal, self.gamma, self.balance_param = bool(focal["focal"]), float(focal["gamma"]), float(focal["balance_param"])
+        self.map_alpha, self.map_beta, self.map_gamma = float(map_param["alpha"]), float(map_param["beta"]), float(map_param["gamma"])
+        self.logit_reg = dict(logit_reg)
+        self.neg_scale = float(logit_reg["neg_scale"]) if "neg_scale" in logit_reg else 1.0
+        init_bias = float(logit_reg["init_bias"]) if "init_bias" in logit_reg else 0.0
+        train_num = cf[0] + ncf[0]
+        self.register_buffer("class_freq", cf)
+        self.register_buffer("freq_inv", (torch.ones_like(cf) / cf).contiguous())                        # dbl.py:341
+        self.register_buffer("init_bias", (-torch.log(train_num / cf - 1) * init_bias / self.neg_scale).contiguous())      # dbl.py:338-339
+
+    def forward(self, cls_score, label, weight=None, avg_factor=None, reduction_override=None, **kwargs):
+        y = label.detach().float().contiguous()
+        fi = self.freq_inv if self.reweight_func == "rebalance" else None
+        ib = self.init_bias if "init_bias" in self.logit_reg else None
+        ns = self.neg_scale if "neg_scale" in self.logit_reg else 0.0
+        return _FusedLoss.apply(cls_score, lambda x: ops.resample_bce_fwd_bwd(
+            x, y, fi, ib, self.map_alpha, self.map_beta, self.map_gamma, ns, self.focal, self.gamma, self.balance_param,
+            self.loss_weight))

@@ -455,3 +455,23 @@ def sgd_step(flat_grad, params, momentum_bufs, lr, momentum=0.0, weight_decay=0.
     m = TensorList(momentum_bufs) if momentum_bufs is not None else None
     check(lib.lecb_sgd_step(_ptr(flat_grad), p.ptrs, m.ptrs if m is not None else None, _sizes(params), p.n,
                             float(grad_scale), float(lr), float(momentum), float(weight_decay), _stream()), "lecb_sgd_step")
+
+
+def resample_bce_fwd_bwd(logits, labels, freq_inv=None, init_bias=None, map_alpha=10.0, map_beta=0.2, map_gamma=0.1,
+                         neg_scale=0.0, focal=False, focal_gamma=2.0, balance_param=2.0, loss_weight=1.0, want_grad=True):
+    """ResampleLoss (dbl.py:263-445, use_sigmoid) forward + backward; freq_inv / init_bias fp32 [K] or None."""
+    _need(logits, torch.float32, "logits")
+    _need(labels, torch.float32, "labels")
+    b, k = logits.shape
+    for t, nm in ((freq_inv, "freq_inv"), (init_bias, "init_bias")):
+        if t is not None:
+            _need(t, torch.float32, nm)
+            assert t.numel() == k
+    grad = torch.empty_like(logits) if want_grad else None
+    loss = torch.empty((), device=logits.device, dtype=torch.float32)
+    scratch = torch.empty((2,), device=logits.device, dtype=torch.float32) if focal else None
+    check(lib.lecb_resample_bce_fwd_bwd(_ptr(logits), _ptr(labels), _ptr(freq_inv), _ptr(init_bias), _ptr(grad), _ptr(loss),
+                                        _ptr(scratch), b, k, float(map_alpha), float(map_beta), float(map_gamma), float(neg_scale),
+                                        int(bool(focal)), float(focal_gamma), float(balance_param), float(loss_weight), _stream()),
+          "lecb_resample_bce_fwd_bwd")
+    return loss, grad

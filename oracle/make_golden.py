@@ -20,6 +20,7 @@ Fixtures written:
   fusion.npz                 reference fuse / fuse6 (gen_final_ans.py) and adjust_predictions (T:611-615) on synthetic scores
   train_ext_{tiny,rn50}.npz  the same step under TRAIN.ema / CSC / IF_LEARN_SCALE / co-occurrence ranking (round 2)
   losses_ext.npz             ranking_loss_with_cooccurrence + the KL terms of T:809-813 on [16,80]
+  resample_loss.npz          ResampleLoss (trainers/dbl.py, LOSSFUNC 'dbl'): shipped, focal + logit_reg and unweighted settings
   prompt_learner_tiny.npz    PromptLearner.forward(neg_prompt_wcls=True/False), CSC and generic, name_lens, state_dict
   vit_{tiny,b16_224,l14_224}.npz   reference VisionTransformer.forward (class-token feature) on synthetic weights
 """
@@ -264,6 +265,50 @@ def golden_losses_ext():
     np.savez_compressed(os.path.join(GOLD, "losses_ext.npz"), **out)
 
 
+RESAMPLE_CONFIGS = {
+    # the loss the trainer builds for LOSSFUNC 'dbl' (T:823-830) and the commented alternative next to it (T:831-838)
+    "shipped": dict(use_sigmoid=True, reweight_func="rebalance", focal=dict(focal=False, balance_param=2.0, gamma=2), logit_reg=dict(),
+                    map_param=dict(alpha=0.1, beta=10.0, gamma=0.2), loss_weight=1.0),
+    "focal_reg": dict(use_sigmoid=True, reweight_func="rebalance", focal=dict(focal=True, balance_param=2.0, gamma=2),
+                      logit_reg=dict(neg_scale=2.0, init_bias=0.05), map_param=dict(alpha=0.1, beta=10.0, gamma=0.2), loss_weight=1.0),
+    "plain": dict(use_sigmoid=True, reweight_func=None, focal=dict(focal=False, balance_param=2.0, gamma=2), logit_reg=dict(),
+                  map_param=dict(alpha=0.1, beta=10.0, gamma=0.2), loss_weight=0.5),
+}
+
+
+def golden_resample():
+    """`ResampleLoss` (trainers/dbl.py:263-445) run on synthetic logits / labels / class frequencies."""
+    import pickle
+    import tempfile
+    cls = RX.resample_loss_class()
+    g = torch.Generator().manual_seed(79)
+    x = torch.randn((16, 80), generator=g) * 2.0
+    y = (torch.rand((16, 80), generator=g) < 0.06).float()
+    y[0, 3] = 1.0
+    y[5] = 0.0                                    # a row without positives: repeat rate 0 -> weight 1 + alpha
+    class_freq = torch.randint(40, 4000, (80,), generator=g).float().numpy()
+    neg_class_freq = (20000.0 - class_freq).astype(np.float32)
+    out = {"x": x.numpy(), "y": y.numpy(), "class_freq": class_freq, "neg_class_freq": neg_class_freq}
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "class_freq.pkl")
+        with open(path, "wb") as f:
+            pickle.dump({"class_freq": class_freq, "neg_class_freq": neg_class_freq}, f)
+        real_cuda = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda self, *a, **k: self          # dbl.py:326-341 moves its tables to the GPU; there is none here
+        try:
+            for name, kw in RESAMPLE_CONFIGS.items():
+                fn = cls(freq_file=path, **kw)
+                a = x.clone().requires_grad_(True)
+                loss = fn(a * 1.0, y)                           # non-leaf copy: dbl.py:405 adds init_bias in place
+                loss.backward()
+                out["loss_" + name] = np.float64(loss.item())
+                out["grad_" + name] = a.grad.numpy()
+                print(f"[resample] {name}: {loss.item():.6f}", flush=True)
+        finally:
+            torch.Tensor.cuda = real_cuda
+    np.savez_compressed(os.path.join(GOLD, "resample_loss.npz"), **out)
+
+
 def golden_prompt_learner(classnames):
     """PromptLearner.forward(neg_prompt_wcls=False) (T:199-242: the negative / evidence prompts built WITHOUT the class-name
     tokens) and the CSC variant, on a small text width: outputs are pure concatenations, compared exactly."""
@@ -381,6 +426,7 @@ def main(which=None):
         "train_ext_tiny": lambda: golden_train_ext("tiny", synth.tiny_rn(), 6, TINY_CLASSES, 4, 1243),
         "train_ext_rn50": lambda: golden_train_ext("rn50", synth.RN50(224), 4, classnames, 16, 1239),
         "losses_ext": golden_losses_ext,
+        "resample": golden_resample,
         "prompt_learner": lambda: golden_prompt_learner(classnames),
         "vit_tiny": lambda: golden_vit("tiny", synth.tiny_vit(), 3, 1250),
         "vit_b16_224": lambda: golden_vit("b16_224", synth.VITB16(224), 2, 1251),

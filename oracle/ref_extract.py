@@ -133,6 +133,32 @@ def loss_functions():
     return ns
 
 
+def resample_loss_class():
+    """-> the reference `ResampleLoss` (trainers/dbl.py:263-445) with the helpers it calls (dbl.py:20-65, 179-222).
+    The module itself cannot be imported (mmcv, matplotlib, sklearn at dbl.py:4-9), and the class moves its frequency
+    tables to the GPU in __init__ (`.cuda()`, dbl.py:326-341): the namespace gets an `mmcv.load` that unpickles and, for the
+    duration of a construction, callers patch `torch.Tensor.cuda` to the identity (see oracle/make_golden.golden_resample)."""
+    import functools
+    import pickle
+    import types
+    import numpy as np
+    import torch
+    import torch.nn as nn
+    from torch.nn import functional as F
+
+    def _load(path):
+        with open(path, "rb") as f:
+            return pickle.load(f)
+
+    code = _extract(os.path.join(MC, "trainers", "dbl.py"),
+                    ["cross_entropy", "_expand_binary_labels", "binary_cross_entropy", "partial_cross_entropy", "reduce_loss",
+                     "weight_reduce_loss", "ResampleLoss"])
+    ns = {"torch": torch, "nn": nn, "F": F, "np": np, "functools": functools, "mmcv": types.SimpleNamespace(load=_load),
+          "__name__": "_lecb_ref_dbl"}
+    exec(code, ns)
+    return ns["ResampleLoss"]
+
+
 def checkpoint_functions():
     """-> namespace with the reference `save_checkpoint`, `load_checkpoint`, `load_pretrained_weights`
     (Dassl.pytorch-master/dassl/utils/torchtools.py:27-120, 266-320).  torch >= 2.6 made weights_only=True the default

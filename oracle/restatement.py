@@ -351,6 +351,31 @@ def ranking_loss_with_cooccurrence(y_pred, y_true, cooccurrence, scale=2.0, marg
     return (d * t[:, None, :] * (1 - t[:, :, None])).sum((-1, -2)).mean()
 
 
+def resample_loss(x, y, class_freq, neg_class_freq, reweight=True, map_alpha=10.0, map_beta=0.2, map_gamma=0.1, logit_reg=None,
+                  focal=False, focal_gamma=2.0, balance_param=2.0, loss_weight=1.0):
+    """`ResampleLoss.forward` (dbl.py:351-383) for use_sigmoid=True, partial=False, reweight_func None | 'rebalance':
+    every `binary_cross_entropy` call reduces with 'mean' (dbl.py:61-63), so the focal factor multiplies two scalars."""
+    logit_reg = logit_reg or {}
+    y = y.float()
+    freq_inv = 1.0 / class_freq
+    w = None
+    if reweight:
+        repeat_rate = (y * freq_inv).sum(1, keepdim=True)
+        w = torch.sigmoid(map_beta * (freq_inv[None] / repeat_rate - map_gamma)) + map_alpha
+    neg_scale = logit_reg.get("neg_scale", 1.0)
+    if "init_bias" in logit_reg:
+        train_num = class_freq[0] + neg_class_freq[0]
+        x = x + (-torch.log(train_num / class_freq - 1) * logit_reg["init_bias"] / neg_scale)
+    if "neg_scale" in logit_reg:
+        x = x * (1 - y) * neg_scale + x * y
+        w = w / neg_scale * (1 - y) + w * y
+    bce = torch.nn.functional.binary_cross_entropy_with_logits
+    if focal:
+        pt = torch.exp(-bce(x, y, None, reduction="mean"))
+        return loss_weight * balance_param * (1 - pt) ** focal_gamma * bce(x, y, w, reduction="mean")
+    return loss_weight * bce(x, y, w, reduction="mean")
+
+
 def kl_softmax(x, x_target):
     """nn.KLDivLoss(reduction="batchmean")(log_softmax(x), softmax(x_target)) (T:796, T:809-811): sum_b,k q (log q - log p) / B."""
     logp = torch.log_softmax(x, dim=-1)

@@ -179,3 +179,22 @@ def test_prompt_learner_mirror_matches_reference(csc):
     assert set(sd) == want, set(sd) ^ want
     for k, v in sd.items():
         np.testing.assert_array_equal(v.numpy(), g[f"state_{k}{sfx}"], err_msg=k)
+
+
+def test_resample_loss_matches_reference():
+    """`ResampleLoss` (trainers/dbl.py, LOSSFUNC 'dbl'): restatement vs the reference class on the three fixture settings."""
+    from oracle.make_golden import RESAMPLE_CONFIGS
+    g = C.load("resample_loss.npz")
+    x0, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    cf, ncf = torch.from_numpy(g["class_freq"]), torch.from_numpy(g["neg_class_freq"])
+    for name, kw in RESAMPLE_CONFIGS.items():
+        a = x0.clone().requires_grad_(True)
+        loss = R.resample_loss(a, y, cf, ncf, reweight=kw["reweight_func"] == "rebalance", map_alpha=kw["map_param"]["alpha"],
+                               map_beta=kw["map_param"]["beta"], map_gamma=kw["map_param"]["gamma"], logit_reg=kw["logit_reg"],
+                               focal=kw["focal"]["focal"], focal_gamma=kw["focal"]["gamma"], balance_param=kw["focal"]["balance_param"],
+                               loss_weight=kw["loss_weight"])
+        loss.backward()
+        ref = float(g["loss_" + name])
+        assert abs(loss.item() - ref) < 1e-5 * max(1.0, abs(ref)), name
+        np.testing.assert_allclose(a.grad.numpy(), g["grad_" + name], atol=1e-7, rtol=1e-4, err_msg=name)
+        np.testing.assert_array_equal(a.detach().numpy(), g["x"])

@@ -66,6 +66,34 @@ def test_losses_ext_match_reference():
         np.testing.assert_array_equal(a.detach().cpu().numpy(), g["x"])
 
 
+def test_resample_loss_matches_reference():
+    """`ResampleLoss` (trainers/dbl.py:263-445, LOSSFUNC 'dbl' at T:818-841) through the fused kernel, same constructor keywords."""
+    L = _losses()
+    from oracle.make_golden import RESAMPLE_CONFIGS
+    g = C.load("resample_loss.npz")
+    x0, y = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["y"]).cuda()
+    for name, kw in RESAMPLE_CONFIGS.items():
+        fn = L.ResampleLoss(class_freq=g["class_freq"], neg_class_freq=g["neg_class_freq"], **kw)
+        a = x0.clone().requires_grad_(True)
+        loss = fn(a, y)
+        loss.backward()
+        ref = float(g["loss_" + name])
+        assert abs(loss.item() - ref) < 1e-5 * max(1.0, abs(ref)), (name, loss.item(), ref)
+        np.testing.assert_allclose(a.grad.cpu().numpy(), g["grad_" + name], atol=2e-7, rtol=2e-4, err_msg=name)
+        np.testing.assert_array_equal(a.detach().cpu().numpy(), g["x"])
+    # size-independent property at a roofline-sized input: the mean over a batch is the mean of the means of its equal parts
+    from lecb200 import ops
+    torch.manual_seed(4)
+    xb = torch.randn((1 << 16, 80), device="cuda") * 2
+    yb = (torch.rand_like(xb) < 0.05).float()
+    fi = (1.0 / torch.from_numpy(g["class_freq"])).cuda().contiguous()
+    whole, gw = ops.resample_bce_fwd_bwd(xb, yb, fi, None, 0.1, 10.0, 0.2)
+    parts = [ops.resample_bce_fwd_bwd(xb[i::4].contiguous(), yb[i::4].contiguous(), fi, None, 0.1, 10.0, 0.2)[0] for i in range(4)]
+    assert abs(whole.item() - torch.stack(parts).mean().item()) < 1e-5 * abs(whole.item())
+    _, g2 = ops.resample_bce_fwd_bwd(xb[:1024].contiguous(), yb[:1024].contiguous(), fi, None, 0.1, 10.0, 0.2)
+    torch.testing.assert_close(gw[:1024] * (xb.shape[0] / 1024), g2, rtol=1e-5, atol=1e-9)
+
+
 @pytest.mark.parametrize("k", [80, 33, 200, 6])
 @pytest.mark.parametrize("soft", [False, True])
 def test_ranking_kernel_matches_dense_formula(k, soft):
@@ -473,3 +501,38 @@ def test_ddp_wrapped_step_equals_unwrapped(tmp_path):
         assert e_ddp <= max(2e-2, 3 * e_rep) and c_ddp > 0.9995
     for a, b, ga in zip(p1, p2, g1):             # one SGD step: lr x the gradient difference allowed above
         assert float((a - b).abs().max()) <= 0.002 * 5e-2 * float(ga.abs().max()) + 1e-7
+
+
+def test_window_pipeline_matches_host_pipeline():
+    """pipeline.score_image_with_windows (crop + resize + score + fuse on the GPU) == the reference's flow re-enacted with the
+    oracle's Pillow-exact resize on the host, the same model for the scoring and the oracle's aggregation rule (T:641-673)."""
+    from lecb200 import pipeline
+    from lecb200 import windows as WN
+    from oracle import pil_resize as PR
+    from lecb200 import ops
+    c = C.head_case("small")
+    model = build_model(c, use_evidence=True)
+    size = c["arch"].image_resolution
+    rng = np.random.default_rng(11)
+    h, w = 150, 200
+    img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    got = pipeline.score_image_with_windows(model, torch.from_numpy(img).cuda(), size, multi_scale=(2, 3), chunk=64)
+    wins = [WN.whole_image(h, w)] + [x for s in (2, 3) for x in WN.sliding_windows(h, w, s)]
+    assert got["n_windows"] == len(wins) - 1
+    host = []
+    for win in wins:
+        rows, cols = WN.source_rows_cols(win, h, w)
+        host.append(PR.test_transform(np.ascontiguousarray(img[rows][:, cols]), (size, size), ops.CLIP_PIXEL_MEAN, ops.CLIP_PIXEL_STD))
+    x = torch.from_numpy(np.stack(host)).cuda()
+    o, o_pos = [], []
+    for i in range(0, x.shape[0], 64):
+        r = model(x[i:i + 64], if_test=True)
+        o.append(r[0])
+        o_pos.append(r[1])
+    o, o_pos = torch.cat(o).cpu(), torch.cat(o_pos).cpu()
+    want = R.aggregate_blocks(o[:1], o[1:].unsqueeze(0), 0.3, 1.4)
+    want_pos = R.aggregate_blocks(o_pos[:1], o_pos[1:].unsqueeze(0), 0.3, 1.4)
+    # identical uint8 network inputs (bit-exact resize) -> the scores agree to the run-to-run noise of the fp32 atomics
+    assert (got["output_blocks"][0].cpu() - o[1:]).abs().max().item() <= 1e-5
+    assert (got["output_final"].cpu() - want).abs().max().item() <= 1e-4
+    assert (got["output_pos_final"].cpu() - want_pos).abs().max().item() <= 1e-4
