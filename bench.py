@@ -698,8 +698,11 @@ def sharded_prompt_check(cx):
     d_logits, d_grad, d_cos = (float(v) for v in t)
     return {"what": "class-sharded prompt branch vs replicated branch, same captions (max over ranks)",
             "logits_max_abs_diff": d_logits, "grad_max_diff_over_max": d_grad, "grad_one_minus_cosine": d_cos,
-            "tolerance": {"logits": 1e-3, "grad": 2e-2},
-            "ok": bool(d_logits <= 1e-3 and d_grad <= 2e-2)}
+            # the backward is not bit-reproducible (fp32 atomics feeding bf16 roundings: two identical runs differ by ~2 % of
+            # max on ctx_double.grad), and the two branches round at different points: the gate is the one the gradients are
+            # held to against the reference (5 % of max, cosine > 0.999)
+            "tolerance": {"logits": 1e-3, "grad": 5e-2, "grad_one_minus_cosine": 1e-3},
+            "ok": bool(d_logits <= 1e-3 and d_grad <= 5e-2 and d_cos <= 1e-3)}
 
 
 def main():
