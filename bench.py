@@ -504,9 +504,12 @@ def bench_headline(cx, args):
             tpath = os.path.join(ROOT, "profiles", tname)
             if os.path.exists(tpath) and B == 256:
                 with open(tpath) as f:
-                    fam_t = json.load(f)["by_kernel_family"].get("gemm_kernel")
-                if fam_t:
-                    traffic, traffic_src = fam_t["dram_bytes_per_launch"], f"profiles/{tname} (ncu dram__bytes_read+write, mean over the step's launches)"
+                    fams = json.load(f)["by_kernel_family"]
+                parts = [fams[k] for k in ("gemm_kernel", "gemm_pair_kernel") if k in fams]      # single-CTA and CTA-pair kernels
+                if parts:
+                    n_l = sum(x["launches"] for x in parts)
+                    traffic = sum(x["dram_bytes_total"] for x in parts) / max(n_l, 1)
+                    traffic_src = f"profiles/{tname} (ncu dram__bytes_read+write, mean over the step's {n_l} GEMM / conv launches)"
                     break
         gemm_by = sum(table[n]["bytes"] for n in fam if n in table)
         # The kernel serves layers on both sides of the ridge: per (entry point, shape) the bound is

@@ -42,7 +42,8 @@ constexpr int kEpiWarps = 8;                       // groups of four (a warp rea
                                                    // 12: no faster on the short-K residual GEMMs and 3-20 % slower on the convs
                                                    // (the 128-register cap of 480 threads costs more than the third group hides)
 constexpr int kGroups = kEpiWarps / 4;
-constexpr int kTFull = (kGroups % 2 == 0) ? kGroups : 2 * kGroups;
+constexpr int kTFull = (kGroups % 2 == 0) ? kGroups : 2 * kGroups;   // single-tile kernels: lcm(2 accumulators, kGroups)
+constexpr int kTFullMax = 4;                       // barrier slots reserved in the layout (paired-tile kernels use four)
 constexpr int kNumThreads = 32 * (kEpiWarps + 3);
 constexpr int kWarpTma = kEpiWarps, kWarpMma = kEpiWarps + 1, kWarpDma = kEpiWarps + 2;
 constexpr int kBiasBytes = 2048;                   // [2][256] floats: a tile's bias slice, double-buffered by tile parity
@@ -124,11 +125,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* bars = reinterpret_cast<uint64_t*>(sC + NB * Cfg::kCBytes);
   uint64_t* full = bars;                       // [kMaxStages] (the resident-W mode may run a deeper A ring)
   uint64_t* empty = bars + kMaxStages;
-  // tfull: one barrier per (tile mod kTFull), kTFull = lcm(2 accumulators, kGroups): successive phases of one barrier
+  // tfull: one barrier per (tile mod kTF), kTF = lcm(accumulators in flight, kGroups) — 2 for the single-tile kernels, FOUR
+  // for the paired-tile kernels (four accumulators).  The barrier count must equal the accumulator count: the next completion
+  // of tfull[i] then needs the accumulator it guards to be drained first, so a waiter can never be lapped.  Round 1 indexed
+  // the paired-tile kernels' four accumulators with two barriers: the MMA thread, allowed to run four tiles ahead, could
+  // complete tfull[1] twice more (tiles t+2, t+4... of the other accumulator pair) before a delayed epilogue warp had looked
+  // at tile t — the waiter then aliased on the phase parity and the CTA deadlocked (seen once in ~10 long bench runs, caught by
+  // the mbarrier time-out: MMA on tempty[3], epilogue on tfull[1], both parity 1).  Successive phases of one barrier
   // then belong to the same accumulator AND the same owner groups, so every waiter sees every phase of the barriers it
   // waits on (a group that skipped phases, or lagged two behind, would alias on the phase parity)
   uint64_t* tfull = bars + 2 * kMaxStages;
-  uint64_t* tempty = tfull + kTFull;
+  constexpr int kTF = MT == 2 ? 4 : kTFull;
+  static_assert(kTF <= kTFullMax, "tfull slots");
+  uint64_t* tempty = tfull + kTFullMax;
   // staging barriers: one (free, full) pair per buffer — but never fewer than two pairs: with a single buffer the two
   // epilogue groups would share one barrier and a group could be two phases ahead of it (parity aliasing), so the
   // barrier index (block % kNBar) is decoupled from the buffer index (block % NB)
@@ -187,7 +196,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
-    for (int i = 0; i < kTFull; ++i) mbar_init(&tfull[i], 1);
+    for (int i = 0; i < kTFullMax; ++i) mbar_init(&tfull[i], 1);
     for (int i = 0; i < 4; ++i) {
       // staged path: both epilogue groups read every accumulator (8 warps) unless a tile is a single block,
       // in which case the groups alternate tiles (4 warps); direct fp32 path: group 0 only
@@ -345,7 +354,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             stage = 0;
             phase ^= 1;
           }
-          umma_commit(&tfull[ti % kTFull]);
+          umma_commit(&tfull[ti % kTF]);
           continue;
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -372,8 +381,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[ti % kTFull]);
-        if (MT == 2) umma_commit(&tfull[(ti + 1) % kTFull]);
+        umma_commit(&tfull[ti % kTF]);
+        if (MT == 2) umma_commit(&tfull[(ti + 1) % kTF]);
       }
     }
   } else if (warp == kWarpDma) {
@@ -466,7 +475,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tile_coords(tile_seq, m_blk, n_blk);
       const int acc = tile_seq & (2 * MT - 1);        // accumulator of this (sub-)tile
       const int par = tile_seq & 1;                     // bias slice parity
-      const uint32_t tf_phase = static_cast<uint32_t>(tile_seq / kTFull) & 1u;
+      const uint32_t tf_phase = static_cast<uint32_t>(tile_seq / kTF) & 1u;
       const int64_t row = static_cast<int64_t>(m_blk) * kTileM + erow;
       const bool row_ok = row < p.M;
       float ssq = 0.f;
@@ -502,7 +511,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t g0 = static_cast<uint32_t>(tile_seq) * cblocks;
         const int cb_first = (group + kGroups - static_cast<int>(g0 % kGroups)) % kGroups;
         if (cb_first >= cblocks) continue;
-        mbar_wait(&tfull[tile_seq % kTFull], tf_phase);
+        mbar_wait(&tfull[tile_seq % kTF], tf_phase);
         tc_fence_after();
 #pragma unroll 1
         for (int cb = cb_first; cb < cblocks; cb += kGroups) {
@@ -563,7 +572,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t g0 = static_cast<uint32_t>(tile_seq) * kCBlocks;
         const int cb_first = (group + kGroups - static_cast<int>(g0 % kGroups)) % kGroups;
         if (cb_first >= kCBlocks) continue;       // no block of this tile belongs to this group
-        mbar_wait(&tfull[tile_seq % kTFull], tf_phase);
+        mbar_wait(&tfull[tile_seq % kTF], tf_phase);
         tc_fence_after();
 #pragma unroll 1
         for (int cb = cb_first; cb < kCBlocks; cb += kGroups) {
@@ -686,7 +695,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tk_idx[j] = -1;
           }
         }
-        mbar_wait(&tfull[tile_seq % kTFull], tf_phase);
+        mbar_wait(&tfull[tile_seq % kTF], tf_phase);
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
@@ -721,7 +730,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (lane == 0) mbar_arrive(&tempty[acc]);
       } else {
         if (group != 0) continue;                 // direct fp32 stores: one group is plenty (small GEMMs)
-        mbar_wait(&tfull[tile_seq % kTFull], tf_phase);
+        mbar_wait(&tfull[tile_seq % kTF], tf_phase);
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {

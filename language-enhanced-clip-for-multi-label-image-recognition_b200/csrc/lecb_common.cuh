@@ -6,6 +6,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace lecb {
 
@@ -45,11 +46,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Spin on the phase; a wait that lasts > ~4 s of SM clocks is a protocol bug: trap instead of hanging the GPU.
+static __device__ __noinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity) {
+  printf("[lecb] mbarrier wait timed out: block %d thread %d barrier smem 0x%x parity %u\n", static_cast<int>(blockIdx.x),
+         static_cast<int>(threadIdx.x), bar_addr, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) __trap();
+    if (clock64() - t0 > 8000000000LL) mbar_timeout(smem_u32(bar), parity);
   }
 }
 
