@@ -37,6 +37,12 @@ int launch_pair_gemm(const void* A, const void* Wt, const float* bias, const voi
 int launch_pair_conv3x3(const void* x, const void* w, const float* bias, void* out, int B, int H, int Wd, int Cin, int Cout,
                         unsigned flags, cudaStream_t stream);
 
+// experiment / kill switches, read from the environment ONCE at first use (round 1 called getenv on every launch)
+static bool env_flag_no_resident() { static const bool v = getenv("LECB_NO_RESIDENT") != nullptr; return v; }
+static bool env_flag_no_halo() { static const bool v = getenv("LECB_NO_HALO") != nullptr; return v; }
+static bool env_flag_halo_single() { static const bool v = getenv("LECB_HALO_SINGLE") != nullptr; return v; }
+static bool env_flag_no_mt2() { static const bool v = getenv("LECB_NO_MT2") != nullptr; return v; }
+
 constexpr int kTileM = 128;
 constexpr int kEpiWarps = 8;                       // groups of four (a warp reads TMEM lane quarter warp % 4).  Measured with
                                                    // 12: no faster on the short-K residual GEMMs and 3-20 % slower on the convs
@@ -951,7 +957,7 @@ static int dispatch(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& t
     if (stages < 1) return fail(LECB_ERR_UNSUPPORTED, "halo conv does not fit shared memory (BN=%d copy=%d)", BN, p.copy_bytes);
     p.b_resident = 1;
     p.res_stages = stages;
-  } else if (p.mt == 1 && p.num_kb >= 2 && p.num_n_tiles <= 8 && sms > 0 && p.num_m_tiles >= 4 * sms && !getenv("LECB_NO_RESIDENT")) {
+  } else if (p.mt == 1 && p.num_kb >= 2 && p.num_n_tiles <= 8 && sms > 0 && p.num_m_tiles >= 4 * sms && !env_flag_no_resident()) {
     const int ring = resident_ring(BN, BK, p.num_kb, nb);
     if (ring >= 3) {                          // a two-stage A ring next to a resident 128 KB W tile measured slower than streaming
       p.b_resident = 1;
@@ -1080,7 +1086,7 @@ extern "C" int lecb_gemm_topk10(const void* A_hilo, const void* bank, int64_t M,
 // tile, at least two patches per SM, and a patch shape (16x8 or 8x16) that tiles the image with <= 15 % waste.
 static bool halo_plan(int B, int H, int Wd, int Cin, int BN, int& th, int& tw) {
   const int sms = sm_count();
-  if (!((Cin == 64 || Cin == 32) && BN <= 128 && sms > 0) || getenv("LECB_NO_HALO")) return false;
+  if (!((Cin == 64 || Cin == 32) && BN <= 128 && sms > 0) || env_flag_no_halo()) return false;
   auto waste = [&](int a, int b) {       // padded / real pixels for an a x b patch
     return static_cast<double>(((H + a - 1) / a) * a) * (((Wd + b - 1) / b) * b) / (static_cast<double>(H) * Wd);
   };
@@ -1158,7 +1164,7 @@ extern "C" int lecb_conv3x3_bf16(const void* x, const void* w, const float* bias
       // Measured (RN101, layer1 conv2): the single-copy layout moves 2.4x fewer bytes and fits five stages, yet runs
       // 18 % SLOWER than three aligned copies — operand groups that straddle 1024-byte swizzle atoms cost the tensor
       // pipe more than the L2 traffic saved.  Kept behind a switch as the record of that experiment.
-      if (tw == 8 && Cin == 64 && getenv("LECB_HALO_SINGLE")) {
+      if (tw == 8 && Cin == 64 && env_flag_halo_single()) {
         p.halo_single = 1;
         p.copy_bytes = ((th + 2) * (tw + 2) * 128 + 1023) / 1024 * 1024;
         st = encode_tiled_4d_nhwc(&tmA, x, B, H, Wd, Cin, 64, tw + 2, th + 2);
@@ -1179,7 +1185,7 @@ extern "C" int lecb_conv3x3_bf16(const void* x, const void* w, const float* bias
   {
     const int sms = sm_count();
     if (BN == 128 && BK == 64 && p.num_n_tiles == 1 && p.num_m_tiles % 2 == 0 && sms > 0 && p.num_m_tiles >= 4 * sms &&
-        !getenv("LECB_NO_MT2"))
+        !env_flag_no_mt2())
       p.mt = 2;
   }
   st = encode_im2col_3x3(&tmA, x, B, H, Wd, Cin, BK, kTileM);

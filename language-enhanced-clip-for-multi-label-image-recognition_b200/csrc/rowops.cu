@@ -281,7 +281,8 @@ extern "C" int lecb_stem_conv1(const float* x, const float* w, const float* bias
   const int64_t total = static_cast<int64_t>(B) * (H / 2) * ((W / 2 + 1) / 2);     // two output pixels per thread
   const unsigned grid = static_cast<unsigned>((total + 127) / 128);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (Cout == 32 && !getenv("LECB_STEM_CUDA_CORES"))      // the real CLIP ResNets (width 64): tensor-core implicit GEMM
+  static const bool cuda_core_stem = getenv("LECB_STEM_CUDA_CORES") != nullptr;     // read once, not per launch
+  if (Cout == 32 && !cuda_core_stem)      // the real CLIP ResNets (width 64): tensor-core implicit GEMM
     return launch_stem_conv1_tc(x, 0, w, bias, nullptr, nullptr, out, B, H, W, s);
   if (Cout == 32)
     stem_conv1_kernel<32><<<grid, 128, 0, s>>>(x, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W);
