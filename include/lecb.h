@@ -140,6 +140,7 @@ int lecb_copy_cols(const void* src, int64_t ld_src, int col0, void* dst, int64_t
  * features, columns [0,K) = positive, [K,2K) = negative, [2K,3K) = evidence (n_txt == 3);
  * row_sumsq fp32 [B*P] (or NULL if rows are already unit) supplies 1/||feature||;
  * row_mask u8 [B*P] (or NULL): 1 = padded caption token (T:491), skipped.
+ * K <= 128 classes.  Map rows of masked tokens are left untouched (the host wrapper zero-fills the maps when a mask is given).
  * -> logits_local fp32 [B,K]; optional neg_map / pos_map fp32 [P,B,K] (3rd/4th return values, T:472;
  * neg_map is post winner-take-all when evidence is used, as in the reference). */
 int lecb_head_aggregate(const float* dots, int ldn, const float* row_sumsq, const uint8_t* row_mask,

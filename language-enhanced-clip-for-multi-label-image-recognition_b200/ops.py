@@ -20,6 +20,11 @@ def _stream():
 def _need(t, dtype, name):
     if not t.is_cuda:
         raise _lib.LecbError(f"{name} must be a CUDA tensor (lecb200 has no CPU path)")
+    if t.device.index != torch.cuda.current_device():
+        # every launch goes to the current device's current stream (one process per GPU): a tensor of another device would
+        # be dereferenced on the wrong GPU
+        raise _lib.LecbError(f"{name} lives on cuda:{t.device.index} but the current device is cuda:{torch.cuda.current_device()} "
+                             "(lecb200 runs one process per GPU; wrap the call in torch.cuda.device(...))")
     if t.dtype != dtype:
         raise _lib.LecbError(f"{name} must be {dtype}, got {t.dtype}")
     if not t.is_contiguous():
@@ -214,8 +219,10 @@ def head_aggregate(dots, b, p, k, n_txt, row_sumsq=None, row_mask=None, logit_sc
     _need(dots, torch.float32, "dots")
     ldn = dots.shape[-1]
     out = torch.empty((b, k), device=dots.device, dtype=torch.float32)
-    neg = torch.empty((p, b, k), device=dots.device, dtype=torch.float32) if want_maps else None
-    pos = torch.empty((p, b, k), device=dots.device, dtype=torch.float32) if want_maps else None
+    # rows of masked tokens are not written by the kernel: with a mask the maps start from zeros
+    alloc = torch.zeros if row_mask is not None else torch.empty
+    neg = alloc((p, b, k), device=dots.device, dtype=torch.float32) if want_maps else None
+    pos = alloc((p, b, k), device=dots.device, dtype=torch.float32) if want_maps else None
     if row_mask is not None:
         _need(row_mask, torch.uint8, "row_mask")
     check(lib.lecb_head_aggregate(_ptr(dots), ldn, _ptr(row_sumsq), _ptr(row_mask), _ptr(out), _ptr(neg), _ptr(pos),
