@@ -227,6 +227,10 @@ int lecb_causal_attn_bwd(const void* qkv, const void* dout, void* dqkv, int N, i
 /* the same on tcgen05 tensor cores (five M=128 MMAs per (sequence, head), transposed operands read in place through
  * MN-major descriptors); L <= 128.  Probabilities and dS are rounded to bf16 for the MMAs, like lecb_attn_fwd. */
 int lecb_attn_causal_bwd(const void* qkv, const void* dout, void* dqkv, int N, int L, int W, int heads, void* stream);
+/* the frozen residual ReLU adapter of the adapter trainer (`x + Adapter(x)`, trainers/Caption_distill_double_adapter.py:304-317,
+ * :109; its two bias-free linears are lecb_gemm_bf16): out = x + max(z, 0) on fp32; dz = dy * 1[z > 0] rounded to bf16 */
+int lecb_residual_relu_fwd(const float* x, const float* z, float* out, int64_t n, void* stream);
+int lecb_relu_bwd(const float* dy, const void* z, int z_is_bf16, void* dz_bf16, int64_t n, void* stream);
 /* backward of y = x/||x|| on fp32 rows (T:487-488,503) */
 int lecb_l2norm_bwd(const float* x, const float* dy, float* dx, int64_t rows, int D, void* stream);
 /* gradient of logits_local w.r.t. the raw dot products (same operands as lecb_head_aggregate; T:496-514) */

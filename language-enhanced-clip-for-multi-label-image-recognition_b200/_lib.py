@@ -70,6 +70,8 @@ SIGNATURES = {
                                    c_i64, c_int, c_void_p]),
     "lecb_causal_attn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "lecb_attn_causal_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "lecb_residual_relu_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
+    "lecb_relu_bwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_i64, c_void_p]),
     "lecb_l2norm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
     "lecb_head_aggregate_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                         c_int, c_float, c_float, c_void_p]),

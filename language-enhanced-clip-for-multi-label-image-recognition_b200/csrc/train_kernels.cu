@@ -513,6 +513,46 @@ static int ew_grid(int64_t nvec) {
 
 using namespace lecb;
 
+// ---- residual ReLU adapter (`x + Adapter(x)`, trainers/Caption_distill_double_adapter.py:304-317, :109): elementwise pieces ----
+// out = x + max(z, 0) (fp32) and its bf16 copy for the next GEMM; z = a1 @ W2^T raw.
+namespace lecb {
+__global__ void __launch_bounds__(256)
+residual_relu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ z, float* __restrict__ out, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[i] = x[i] + fmaxf(z[i], 0.f);
+}
+// dz = dy * 1[z > 0], rounded to bf16 (the A operand of the data-gradient GEMM); z fp32 or bf16 (post-activation works too)
+template <typename TZ>
+__global__ void __launch_bounds__(256)
+relu_bwd_kernel(const float* __restrict__ dy, const TZ* __restrict__ z, __nv_bfloat16* __restrict__ dz, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float zi;
+    if constexpr (sizeof(TZ) == 2) zi = __bfloat162float(z[i]);
+    else zi = z[i];
+    dz[i] = __float2bfloat16(zi > 0.f ? dy[i] : 0.f);
+  }
+}
+}  // namespace lecb
+
+extern "C" int lecb_residual_relu_fwd(const float* x, const float* z, float* out, int64_t n, void* stream) {
+  LECB_CHECK_ARG(x && z && out && n > 0, "lecb_residual_relu_fwd: bad argument");
+  lecb::residual_relu_fwd_kernel<<<ew_grid((n + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, z, out, n);
+  count_launch();
+  return check_launch("residual_relu_fwd_kernel");
+}
+
+extern "C" int lecb_relu_bwd(const float* dy, const void* z, int z_is_bf16, void* dz_bf16, int64_t n, void* stream) {
+  LECB_CHECK_ARG(dy && z && dz_bf16 && n > 0, "lecb_relu_bwd: bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (z_is_bf16)
+    lecb::relu_bwd_kernel<__nv_bfloat16><<<ew_grid((n + 7) / 8), 256, 0, s>>>(dy, static_cast<const __nv_bfloat16*>(z),
+                                                                             static_cast<__nv_bfloat16*>(dz_bf16), n);
+  else
+    lecb::relu_bwd_kernel<float><<<ew_grid((n + 7) / 8), 256, 0, s>>>(dy, static_cast<const float*>(z), static_cast<__nv_bfloat16*>(dz_bf16), n);
+  count_launch();
+  return check_launch("relu_bwd_kernel");
+}
+
 extern "C" int lecb_quick_gelu_fwd(const void* v, void* u, int64_t n, void* stream) {
   LECB_CHECK_ARG(v && u && n > 0 && n % 8 == 0, "lecb_quick_gelu_fwd: need n %% 8 == 0");
   quick_gelu_fwd_kernel<<<ew_grid(n / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(

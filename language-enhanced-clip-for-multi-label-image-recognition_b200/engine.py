@@ -224,6 +224,28 @@ class TextTower:
             })
         self.ln_final = (g("ln_final.weight").float().contiguous(), g("ln_final.bias").float().contiguous())
         self.text_proj_t = g("text_projection").t().to(torch.bfloat16).contiguous()      # [D, W] K-major
+        self.adapter = None
+
+    def set_adapter(self, w_down, w_up):
+        """Frozen residual adapter between the transformer and ln_final (Caption_distill_double_adapter.py:304-317, :109):
+        x <- x + relu(relu(x W_down^T) W_up^T).  Only the EOT row of a prompt reaches the output (ln_final and the projection
+        are per-row), so the adapter runs on those N rows.  w_down [W/4, W], w_up [W, W/4] (nn.Linear weights, no bias)."""
+        wd, wu = w_down.detach().to(self.device), w_up.detach().to(self.device)
+        self.adapter = {"down": wd.to(torch.bfloat16).contiguous(), "up": wu.to(torch.bfloat16).contiguous(),
+                        "down_t": wd.t().to(torch.bfloat16).contiguous(), "up_t": wu.t().to(torch.bfloat16).contiguous()}
+
+    def _adapter_fwd(self, xr):
+        """xr fp32 [N,W] -> (xr + adapter(xr), a1 bf16 [N,W/4] post-ReLU, z2 fp32 [N,W] pre-ReLU)."""
+        a1 = ops.gemm(xr.to(torch.bfloat16), self.adapter["down"], relu=True)
+        z2 = ops.gemm(a1, self.adapter["up"], out_f32=True)
+        return ops.residual_relu_fwd(xr, z2), a1, z2
+
+    def _adapter_bwd(self, d_out, a1, z2):
+        """d_out fp32 [N,W] = dL/d(xr + adapter(xr)) -> dL/dxr (identity path + data gradient through the frozen adapter)."""
+        dz2 = ops.relu_bwd(d_out, z2)                                        # [N,W] bf16
+        da1 = ops.gemm(dz2, self.adapter["up_t"], out_f32=True)             # [N,W/4] = dz2 @ W_up
+        dz1 = ops.relu_bwd(da1, a1)
+        return ops.gemm_f32res(dz1, self.adapter["down_t"], None, d_out.contiguous())      # dz1 @ W_down + d_out
 
     # ------------------------------------------------------------------ prompt-tuning (fwd with saves + bwd)
     def _dgrad_weights(self):
@@ -249,6 +271,13 @@ class TextTower:
             x2 = ops.gemm_f32res(u, *blk["proj"], x1)
             saved["layers"].append((x, m1, r1, qkv, x1, m2, r2, v))
             x = x2
+        if self.adapter is not None:
+            xr = x.view(n, l, w)[torch.arange(n, device=x.device), eot_index].contiguous()
+            xr2, a1, z2 = self._adapter_fwd(xr)
+            h, _, mf, rf = ops.layernorm(xr2, *self.ln_final, save_stats=True)
+            saved["final"] = (xr2, mf, rf)
+            saved["adapter"] = (a1, z2)
+            return ops.gemm(h, self.text_proj_t, out_f32=True), saved
         h, _, mf, rf = ops.layernorm(x, *self.ln_final, save_stats=True)
         saved["final"] = (x, mf, rf)
         rows = h.view(n, l, w)[torch.arange(n, device=h.device), eot_index].contiguous()
@@ -259,10 +288,18 @@ class TextTower:
         wt = self._dgrad_weights()
         n, l, w = saved["n"], saved["l"], saved["w"]
         d_rows = ops.gemm(d_out.to(torch.bfloat16).contiguous(), self._text_proj, out_f32=True)      # [N,W]
-        dh = torch.zeros((n, l, w), device=d_out.device, dtype=torch.float32)
-        dh[torch.arange(n, device=d_out.device), saved["eot"]] = d_rows                               # only EOT rows see the loss
         xf, mf, rf = saved["final"]
-        dx, dxb = ops.layernorm_bwd(dh.view(n * l, w), xf, self.ln_final[0], mf, rf)
+        if "adapter" in saved:
+            d_xr2, _ = ops.layernorm_bwd(d_rows, xf, self.ln_final[0], mf, rf, want_bf16=False)       # N rows
+            d_xr = self._adapter_bwd(d_xr2, *saved["adapter"])
+            dx = torch.zeros((n, l, w), device=d_out.device, dtype=torch.float32)
+            dx[torch.arange(n, device=d_out.device), saved["eot"]] = d_xr                             # only EOT rows see the loss
+            dx = dx.view(n * l, w)
+            dxb = dx.to(torch.bfloat16)
+        else:
+            dh = torch.zeros((n, l, w), device=d_out.device, dtype=torch.float32)
+            dh[torch.arange(n, device=d_out.device), saved["eot"]] = d_rows                           # only EOT rows see the loss
+            dx, dxb = ops.layernorm_bwd(dh.view(n * l, w), xf, self.ln_final[0], mf, rf)
         for blk, t, (x0, m1, r1, qkv, x1, m2, r2, v) in zip(reversed(self.blocks), reversed(wt), reversed(saved["layers"])):
             du = ops.gemm(dxb, t["proj"])                                  # [M,4W] bf16
             dv = ops.quick_gelu_bwd(du, v)
@@ -287,6 +324,13 @@ class TextTower:
             h, _, _, _ = ops.layernorm(x, *blk["ln2"])
             u = ops.gemm(h, *blk["fc"], quick_gelu=True)
             x = ops.gemm_f32res(u, *blk["proj"], x)
+        if self.adapter is not None:
+            if sequence:
+                raise ops._lib.LecbError("the adapter text encoder is only used for prompts (EOT readout), not for sequences")
+            xr = x.view(n, l, w)[torch.arange(n, device=x.device), eot_index].contiguous()
+            xr2, _, _ = self._adapter_fwd(xr)
+            h, _, _, _ = ops.layernorm(xr2, *self.ln_final)
+            return ops.gemm(h, self.text_proj_t, out_f32=True)
         h, _, _, _ = ops.layernorm(x, *self.ln_final)
         if sequence:
             return ops.gemm(h, self.text_proj_t, out_f32=True).view(n, l, -1)

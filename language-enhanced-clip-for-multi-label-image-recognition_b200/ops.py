@@ -482,3 +482,21 @@ def resample_bce_fwd_bwd(logits, labels, freq_inv=None, init_bias=None, map_alph
                                         int(bool(focal)), float(focal_gamma), float(balance_param), float(loss_weight), _stream()),
           "lecb_resample_bce_fwd_bwd")
     return loss, grad
+
+
+def residual_relu_fwd(x, z):
+    """out = x + relu(z) on fp32 (the residual adapter, Caption_distill_double_adapter.py:109)."""
+    _need(x, torch.float32, "x")
+    _need(z, torch.float32, "z")
+    out = torch.empty_like(x)
+    check(lib.lecb_residual_relu_fwd(_ptr(x), _ptr(z), _ptr(out), x.numel(), _stream()), "lecb_residual_relu_fwd")
+    return out
+
+
+def relu_bwd(dy, z):
+    """bf16 dz = dy * 1[z > 0]; dy fp32, z fp32 (pre-activation) or bf16 (post-activation)."""
+    _need(dy, torch.float32, "dy")
+    assert z.is_cuda and z.is_contiguous() and z.dtype in (torch.float32, torch.bfloat16) and z.numel() == dy.numel()
+    dz = torch.empty(dy.shape, device=dy.device, dtype=torch.bfloat16)
+    check(lib.lecb_relu_bwd(_ptr(dy), _ptr(z), int(z.dtype == torch.bfloat16), _ptr(dz), dy.numel(), _stream()), "lecb_relu_bwd")
+    return dz

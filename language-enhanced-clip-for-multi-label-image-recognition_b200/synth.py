@@ -229,3 +229,11 @@ def labels(batch: int, n_cls: int, seed: int) -> torch.Tensor:
         idx = torch.randperm(n_cls, generator=g)[:k]
         y[b, idx] = 1.0
     return y
+
+
+def adapter_weights(seed: int, c_in: int = 512, reduction: int = 4):
+    """Seeded weights of the adapter trainer's `Adapter(512, 4)` (two bias-free linears, Caption_distill_double_adapter.py:304-317):
+    (down [c_in/r, c_in], up [c_in, c_in/r]), scaled so the residual branch is live but O(1)."""
+    down = _normal("adapter/down", seed, (c_in // reduction, c_in), c_in ** -0.5)
+    up = _normal("adapter/up", seed, (c_in, c_in // reduction), (c_in // reduction) ** -0.5)
+    return down, up

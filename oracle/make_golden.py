@@ -21,6 +21,7 @@ Fixtures written:
   train_ext_{tiny,rn50}.npz  the same step under TRAIN.ema / CSC / IF_LEARN_SCALE / co-occurrence ranking (round 2)
   losses_ext.npz             ranking_loss_with_cooccurrence + the KL terms of T:809-813 on [16,80]
   resample_loss.npz          ResampleLoss (trainers/dbl.py, LOSSFUNC 'dbl'): shipped, focal + logit_reg and unweighted settings
+  adapter_rn50.npz           AdapterDenseCLIP (trainers/Caption_distill_double_adapter.py): test / train tuples, loss, prompt gradients
   prompt_learner_tiny.npz    PromptLearner.forward(neg_prompt_wcls=True/False), CSC and generic, name_lens, state_dict
   vit_{tiny,b16_224,l14_224}.npz   reference VisionTransformer.forward (class-token feature) on synthetic weights
 """
@@ -265,6 +266,56 @@ def golden_losses_ext():
     np.savez_compressed(os.path.join(GOLD, "losses_ext.npz"), **out)
 
 
+def build_adapter_clip(arch, sd, classnames, n_ctx, seed):
+    """The reference `AdapterDenseCLIP` (TA:320-457) with the synthetic CLIP weights, seeded contexts and a seeded adapter
+    (its own init is nn.Linear's default from the process RNG: replaced so the consuming side can regenerate it)."""
+    ns = RX.adapter_trainer_classes()
+    clip_model = RX.build_reference_clip(arch, sd)
+    cfg = RX.make_cfg(arch.image_resolution, n_ctx=n_ctx)
+    model = ns["AdapterDenseCLIP"](cfg, classnames, clip_model)
+    w = arch.transformer_width
+    with torch.no_grad():
+        model.prompt_learner.ctx.copy_(synth.prompt_ctx(n_ctx, w, seed, "pos"))
+        model.prompt_learner.ctx_double.copy_(synth.prompt_ctx(n_ctx, w, seed, "neg"))
+        wd, wu = synth.adapter_weights(seed)
+        model.adapter_text_encoder.text_adapter.fc[0].weight.copy_(wd)
+        model.adapter_text_encoder.text_adapter.fc[2].weight.copy_(wu)
+    for name, p in model.named_parameters():
+        if "prompt_learner" not in name:
+            p.requires_grad_(False)          # TA:534-536
+    return model
+
+
+def golden_adapter(tag, arch, classnames, n_ctx, batch_img, batch_cap, seed):
+    """`AdapterDenseCLIP` (trainers/Caption_distill_double_adapter.py): test 4-tuple, train 4-tuple, ranking loss, prompt gradients."""
+    sd = synth.clip_state_dict(arch, seed=0)
+    L = RX.loss_functions()
+    model = build_adapter_clip(arch, sd, classnames, n_ctx, seed)
+    img = synth.images(batch_img, arch.image_resolution, seed)
+    caps = synth.captions(batch_cap, seed, vocab=arch.vocab_size)
+    y = synth.labels(batch_cap, len(classnames), seed)
+    out = {"image_checksum": checksum(img), "caption_checksum": checksum(caps.float()), "label_checksum": checksum(y),
+           "state_checksum": state_checksum(sd), "seed": np.int64(seed), "n_ctx": np.int64(n_ctx), "batch_img": np.int64(batch_img),
+           "batch_cap": np.int64(batch_cap), "state_keys": np.array(sorted(model.state_dict().keys()))}
+    with torch.no_grad():
+        r = model(img, if_test=True)
+    for name, t in zip(("logits", "logits_local", "neg_map", "pos_map"), r):
+        out["test_" + name] = t.float().numpy()
+    r = model(None, caps)
+    assert len(r) == 4
+    loss = L["ranking_loss"](r[0], y, scale_=1.0, margin_=1) + L["ranking_loss"](r[1], y, scale_=1.0, margin_=1)
+    loss.backward()
+    out["train_logits"] = r[0].detach().numpy()
+    out["train_logits_local"] = r[1].detach().numpy()
+    out["train_seq_feats"] = r[2].detach().numpy()[:, :2]
+    out["train_text_features"] = r[3].detach().numpy()
+    out["loss"] = np.float64(loss.item())
+    out["grad_ctx"] = model.prompt_learner.ctx.grad.numpy()
+    out["grad_ctx_double"] = model.prompt_learner.ctx_double.grad.numpy()
+    print(f"[adapter_{tag}] test logits absmax {np.abs(out['test_logits']).max():.4f}; train loss {loss.item():.6f}", flush=True)
+    np.savez_compressed(os.path.join(GOLD, f"adapter_{tag}.npz"), **out)
+
+
 RESAMPLE_CONFIGS = {
     # the loss the trainer builds for LOSSFUNC 'dbl' (T:823-830) and the commented alternative next to it (T:831-838)
     "shipped": dict(use_sigmoid=True, reweight_func="rebalance", focal=dict(focal=False, balance_param=2.0, gamma=2), logit_reg=dict(),
@@ -427,6 +478,7 @@ def main(which=None):
         "train_ext_rn50": lambda: golden_train_ext("rn50", synth.RN50(224), 4, classnames, 16, 1239),
         "losses_ext": golden_losses_ext,
         "resample": golden_resample,
+        "adapter_rn50": lambda: golden_adapter("rn50", synth.RN50(224), classnames, 16, 4, 4, 1244),
         "prompt_learner": lambda: golden_prompt_learner(classnames),
         "vit_tiny": lambda: golden_vit("tiny", synth.tiny_vit(), 3, 1250),
         "vit_b16_224": lambda: golden_vit("b16_224", synth.VITB16(224), 2, 1251),

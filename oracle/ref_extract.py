@@ -119,6 +119,23 @@ def trainer_classes(caption_text_feats, embed_dim=1024):
     return ns
 
 
+def adapter_trainer_classes():
+    """-> namespace with the reference `TextEncoder`, `AdapterTextEncoder`, `PromptLearner`, `Adapter`, `AdapterDenseCLIP` of
+    trainers/Caption_distill_double_adapter.py (TA:41-457), AST-extracted and executed unmodified like `trainer_classes`."""
+    import torch
+    import torch.nn as nn
+    from torch.nn import functional as F
+    from torchvision.models._utils import IntermediateLayerGetter
+
+    clip_pkg = clip_package()
+    code = _extract(os.path.join(MC, "trainers", "Caption_distill_double_adapter.py"),
+                    ["TextEncoder", "AdapterTextEncoder", "PromptLearner", "Adapter", "AdapterDenseCLIP"])
+    ns = {"torch": torch, "nn": nn, "F": F, "IntermediateLayerGetter": IntermediateLayerGetter, "clip": clip_pkg.clip,
+          "_tokenizer": clip_pkg.simple_tokenizer.SimpleTokenizer(), "__name__": "_lecb_ref_adapter_trainer"}
+    exec(code, ns)
+    return ns
+
+
 def loss_functions():
     """-> namespace with the reference `ranking_loss`, `AsymmetricLoss_partial`, `dualcoop_loss`,
     `ASL_loss`, `ranking_loss_with_cooccurrence` (trainers/utils.py:85-190)."""

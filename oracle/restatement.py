@@ -178,6 +178,21 @@ def text_encode(sd, prompts, eot_index=None, heads=8, sequence=False, prefix="tr
     return x[torch.arange(x.shape[0]), eot_index] @ sd["text_projection"]
 
 
+def text_encode_adapter(sd, prompts, eot_index, heads, w_down, w_up, prefix="transformer"):
+    """`AdapterTextEncoder.forward` (Caption_distill_double_adapter.py:99-125): transformer, x + Adapter(x) with
+    Adapter(x) = relu(relu(x W_down^T) W_up^T) (TA:304-317), ln_final, EOT row @ text_projection."""
+    x = prompts + sd["positional_embedding"]
+    l = x.shape[1]
+    mask = torch.full((l, l), float("-inf")).triu_(1)
+    i = 0
+    while f"{prefix}.resblocks.{i}.ln_1.weight" in sd:
+        x = _res_block(sd, f"{prefix}.resblocks.{i}", x, heads, mask)
+        i += 1
+    x = x + torch.relu(torch.relu(x @ w_down.t()) @ w_up.t())
+    x = F.layer_norm(x, (x.shape[-1],), sd["ln_final.weight"], sd["ln_final.bias"], 1e-5)
+    return x[torch.arange(x.shape[0]), eot_index] @ sd["text_projection"]
+
+
 def embed_tokens(sd, token_ids):
     """M:326 token embedding gather."""
     return sd["token_embedding.weight"][token_ids]
@@ -299,6 +314,27 @@ def dense_clip_train(sd, arch, captions, pl_state, token_ids, use_evidence=False
     feats = prompt_features(sd, pl_state, token_ids, arch.transformer_heads, use_evidence)
     t_evi = feats[2] if use_evidence else None
     return head_train(seq, captions, feats[0], feats[1], t_evi, logit_scale, spatial_scale)
+
+
+def adapter_dense_clip_test(sd, arch, image, pl_state, token_ids, w_down, w_up, logit_scale=4.0, spatial_scale=50.0):
+    """`AdapterDenseCLIP.forward(image, if_test=True)` (Caption_distill_double_adapter.py:365-412): no evidence, no retrieval."""
+    feat = rn_trunk(sd, image, arch.vision_layers)
+    local = local_features(sd, feat)
+    g = attnpool_global(sd, feat, arch.vision_width * 32 // 64)
+    eot = token_ids.argmax(dim=-1)
+    tf = [_unit(text_encode_adapter(sd, assemble_prompts(pl_state["token_prefix"], pl_state[k], pl_state["token_suffix"]), eot,
+                                    arch.transformer_heads, w_down, w_up)) for k in ("ctx", "ctx_double")]
+    return head_test(g, local, tf[0], tf[1], None, None, logit_scale, spatial_scale)[:4]
+
+
+def adapter_dense_clip_train(sd, arch, captions, pl_state, token_ids, w_down, w_up, logit_scale=4.0, spatial_scale=50.0):
+    """`AdapterDenseCLIP.forward(None, captions)` (Caption_distill_double_adapter.py:413-457): captions through the plain text
+    encoder, prompts through the adapter encoder."""
+    seq = text_encode(sd, embed_tokens(sd, captions), None, arch.transformer_heads, sequence=True)
+    eot = token_ids.argmax(dim=-1)
+    tf = [text_encode_adapter(sd, assemble_prompts(pl_state["token_prefix"], pl_state[k], pl_state["token_suffix"]), eot,
+                              arch.transformer_heads, w_down, w_up) for k in ("ctx", "ctx_double")]
+    return head_train(seq, captions, tf[0], tf[1], None, logit_scale, spatial_scale)
 
 
 # --------------------------------------------------------------------------------------------

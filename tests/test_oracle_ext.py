@@ -198,3 +198,44 @@ def test_resample_loss_matches_reference():
         assert abs(loss.item() - ref) < 1e-5 * max(1.0, abs(ref)), name
         np.testing.assert_allclose(a.grad.numpy(), g["grad_" + name], atol=1e-7, rtol=1e-4, err_msg=name)
         np.testing.assert_array_equal(a.detach().numpy(), g["x"])
+
+
+def adapter_case():
+    g = C.load("adapter_rn50.npz")
+    arch = synth.RN50(224)
+    seed = int(g["seed"])
+    sd = synth.clip_state_dict(arch, 0)
+    toks, n_ctx, names = C.tokens_for("coco")
+    img = synth.images(int(g["batch_img"]), arch.image_resolution, seed)
+    caps = synth.captions(int(g["batch_cap"]), seed, vocab=arch.vocab_size)
+    y = synth.labels(int(g["batch_cap"]), len(names), seed)
+    np.testing.assert_allclose(C.checksum(img), g["image_checksum"], rtol=1e-12, err_msg="RNG drift: images")
+    np.testing.assert_allclose(C.checksum(caps.float()), g["caption_checksum"], rtol=1e-12, err_msg="RNG drift: captions")
+    w = arch.transformer_width
+    pl = R.prompt_learner_state(sd, toks, n_ctx, synth.prompt_ctx(n_ctx, w, seed, "pos"), synth.prompt_ctx(n_ctx, w, seed, "neg"),
+                                synth.prompt_ctx(n_ctx, w, seed, "evi"))
+    return dict(arch=arch, sd=sd, image=img, captions=caps, labels=y, tokens=toks, n_ctx=n_ctx, names=names, gold=g, seed=seed,
+                pl_state=pl, adapter=synth.adapter_weights(seed))
+
+
+def test_adapter_model_matches_reference():
+    """`AdapterDenseCLIP` (trainers/Caption_distill_double_adapter.py:320-457): restatement vs the reference class."""
+    c = adapter_case()
+    g = c["gold"]
+    wd, wu = c["adapter"]
+    with torch.no_grad():
+        out = R.adapter_dense_clip_test(c["sd"], c["arch"], c["image"], c["pl_state"], c["tokens"], wd, wu)
+    for name, t in zip(("logits", "logits_local", "neg_map", "pos_map"), out):
+        np.testing.assert_allclose(t.numpy(), g["test_" + name], atol=ATOL, rtol=1e-4, err_msg=name)
+    pl = {k: (v.clone().requires_grad_(True) if k in ("ctx", "ctx_double") else v) for k, v in c["pl_state"].items()}
+    r = R.adapter_dense_clip_train(c["sd"], c["arch"], c["captions"], pl, c["tokens"], wd, wu)
+    loss = R.ranking_loss(r[0], c["labels"], 1.0, 1.0) + R.ranking_loss(r[1], c["labels"], 1.0, 1.0)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < 1e-4 * max(1.0, abs(float(g["loss"])))
+    np.testing.assert_allclose(r[0].detach().numpy(), g["train_logits"], atol=ATOL)
+    np.testing.assert_allclose(r[1].detach().numpy(), g["train_logits_local"], atol=ATOL)
+    np.testing.assert_allclose(r[3].detach().numpy(), g["train_text_features"], atol=1e-5)
+    for pname in ("ctx", "ctx_double"):
+        gref = g["grad_" + pname]
+        scale = np.abs(gref).max()
+        np.testing.assert_allclose(pl[pname].grad.numpy() / scale, gref / scale, atol=2e-4, err_msg=pname)

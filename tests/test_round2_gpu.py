@@ -536,3 +536,61 @@ def test_window_pipeline_matches_host_pipeline():
     assert (got["output_blocks"][0].cpu() - o[1:]).abs().max().item() <= 1e-5
     assert (got["output_final"].cpu() - want).abs().max().item() <= 1e-4
     assert (got["output_pos_final"].cpu() - want_pos).abs().max().item() <= 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the adapter variant of the model (trainers/Caption_distill_double_adapter.py)
+# ---------------------------------------------------------------------------------------------------------------------
+def test_adapter_model_matches_reference():
+    """`AdapterDenseCLIPB200` vs the reference `AdapterDenseCLIP`: state_dict keys, test 4-tuple, train 4-tuple, ranking loss and
+    the gradients of ctx / ctx_double through the frozen residual adapter."""
+    from lecb200.adapter_clip import AdapterDenseCLIPB200
+    from lecb200.clip_model import CLIPParams
+    from oracle.ref_extract import make_cfg
+    from .test_oracle_ext import adapter_case
+    L = _losses()
+    c = adapter_case()
+    g = c["gold"]
+    arch = c["arch"]
+    clip = CLIPParams(*arch.ctor_args())
+    clip.load_state_dict(c["sd"], strict=False)
+    clip = clip.float().cuda().eval()
+    model = AdapterDenseCLIPB200(make_cfg(arch.image_resolution, n_ctx=c["n_ctx"]), c["names"], clip, tokenized_prompts=c["tokens"]).cuda()
+    assert sorted(model.state_dict().keys()) == [str(k) for k in g["state_keys"]]
+    wd, wu = c["adapter"]
+    with torch.no_grad():
+        model.prompt_learner.ctx.copy_(c["pl_state"]["ctx"])
+        model.prompt_learner.ctx_double.copy_(c["pl_state"]["ctx_double"])
+        model.adapter_text_encoder.text_adapter.fc[0].weight.copy_(wd)
+        model.adapter_text_encoder.text_adapter.fc[2].weight.copy_(wu)
+    model.adapter_text_encoder.refresh_adapter()
+    for name, p in model.named_parameters():
+        if "prompt_learner" not in name:
+            p.requires_grad_(False)          # TA:534-536
+    out = model(c["image"].cuda(), if_test=True)
+    assert len(out) == 4
+    errs = [np.abs(t.float().cpu().numpy() - g["test_" + n]).max() for t, n in zip(out, ("logits", "logits_local", "neg_map", "pos_map"))]
+    print(f"[adapter] test errors {errs}")
+    assert max(errs) <= LOGIT_TOL
+    r = model(None, c["captions"].cuda())
+    assert len(r) == 4
+    y = c["labels"].cuda()
+    loss = L.ranking_loss(r[0], y, scale_=1.0, margin_=1) + L.ranking_loss(r[1], y, scale_=1.0, margin_=1)
+    loss.backward()
+    torch.cuda.synchronize()
+    e1 = np.abs(r[0].detach().cpu().numpy() - g["train_logits"]).max()
+    e2 = np.abs(r[1].detach().cpu().numpy() - g["train_logits_local"]).max()
+    print(f"[adapter] train logits err {e1:.5f} local err {e2:.5f} loss {loss.item():.4f} vs {float(g['loss']):.4f}")
+    assert e1 <= LOGIT_TOL and e2 <= LOGIT_TOL
+    assert abs(loss.item() - float(g["loss"])) <= 1e-2 * max(1.0, abs(float(g["loss"])))
+    np.testing.assert_allclose(r[3].detach().cpu().numpy(), g["train_text_features"], atol=5e-3)
+    for pname in ("ctx", "ctx_double"):
+        gref = g["grad_" + pname]
+        got = getattr(model.prompt_learner, pname).grad.cpu().numpy()
+        err = np.abs(got - gref).max() / np.abs(gref).max()
+        cos = float((got.flatten() @ gref.flatten()) / (np.linalg.norm(got) * np.linalg.norm(gref)))
+        print(f"[adapter] grad {pname}: max err / max ref = {err:.4f}, cosine = {cos:.5f}")
+        assert err < 5e-2 and cos > 0.999, (pname, err, cos)
+    for name, p in model.named_parameters():
+        if "prompt_learner" not in name:
+            assert p.grad is None, name
