@@ -657,7 +657,7 @@ def bench_train(cx, per_gpu_batch, steps, warmup, use_graph=True):
                       "per_gpu_batch": b, "global_batch": world * b, "parallelism": f"dp{world}"},
            "cuda_graph": graphed, "gpu_launches": int(launches if not graphed else launches_eager),
            "caption_positions_run": int(model.caption_len_hint), "caption_positions_total": int(caps.shape[1]),
-           "final_loss": float(loss), "finite": bool(torch.isfinite(loss))}
+           "final_loss": float(loss.detach()), "finite": bool(torch.isfinite(loss.detach()))}
     del model
     torch.cuda.empty_cache()
     return out

@@ -116,17 +116,29 @@ asl_fwd_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, flo
 constexpr int kRankWarps = 8;
 constexpr int kRankMaxK = 512;       // columns per row a warp keeps in registers (kRankChunks * 32); 3 lists of K floats per warp in smem
 constexpr int kRankChunks = kRankMaxK / 32;
+constexpr int kRankSmemWtK = 96;     // co-occurrence: the [K,K] pair weights are staged (transposed) in shared memory up to this K
 
 template <int CH, bool kCooc>
 __global__ void __launch_bounds__(kRankWarps * 32)
 ranking_fwd_bwd_kernel(const float* __restrict__ ypred, const float* __restrict__ ytrue, const float* __restrict__ wt,
                        float* __restrict__ grad, float* __restrict__ loss_out, int64_t B, int K, float scale, float margin,
                        float inv_batch) {
-  extern __shared__ float sm[];                  // per warp: [K] scaled score of list entry, [K] its target, [K] its column
+  extern __shared__ float sm[];                  // per warp: [K] scaled score of list entry, [K] its target, [K] its column;
+                                                 // then (co-occurrence, K <= kRankSmemWtK) the pair weights, transposed
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* l_y = sm + warp * 3 * K;
   float* l_t = l_y + K;
   int* l_j = reinterpret_cast<int*>(l_t + K);
+  const float* wt_t = nullptr;                   // wt_t[j * K + i] = Wt[i, j]: lanes walk i, so the transposed copy is conflict-free
+  if (kCooc && K <= kRankSmemWtK) {
+    float* dst = sm + kRankWarps * 3 * K;
+    for (int e = threadIdx.x; e < K * K; e += blockDim.x) {
+      const int i = e / K, j = e - i * K;
+      dst[j * K + i] = __ldg(wt + e);
+    }
+    wt_t = dst;
+    __syncthreads();
+  }
   float acc = 0.f;
   // The row loop is software-pipelined: the next row's scores and targets are requested before this row is processed, so a
   // warp always has two rows of loads in flight (one row per warp left the kernel latency-bound at 0.27 of HBM peak).
@@ -144,11 +156,11 @@ ranking_fwd_bwd_kernel(const float* __restrict__ ypred, const float* __restrict_
   }
   for (int64_t b = static_cast<int64_t>(blockIdx.x) * kRankWarps + warp; b < B; b += row_step) {
     float y[CH], t[CH], g[CH];
-    int n_pos = 0;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       y[c] = yn[c] * scale;
       t[c] = tn[c];
+      g[c] = 0.f;
     }
     {
       const int64_t bn = b + row_step;
@@ -160,75 +172,85 @@ ranking_fwd_bwd_kernel(const float* __restrict__ ypred, const float* __restrict_
         tn[c] = in ? __ldcs(ytrue + bn * K + k) : 0.f;
       }
     }
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int k = c * 32 + lane;
-      const bool in = k < K;
-      g[c] = 0.f;
-      const unsigned m = __ballot_sync(0xffffffffu, in && t[c] != 0.f);
-      if (in && t[c] != 0.f) {
-        const int slot = n_pos + __popc(m & ((1u << lane) - 1u));
-        l_y[slot] = y[c];
-        l_t[slot] = t[c];
-        l_j[slot] = k;
-      }
-      n_pos += __popc(m);
-    }
-    __syncwarp();
-    // Multi-hot {0,1} targets (every shipped configuration) without pair weights: the pair weight is the indicator
-    // "j positive, i negative", so the positives' gradient is a COUNT — one ballot + popcount per chunk instead of a
-    // five-step shuffle reduction per list entry — and the loss needs no per-pair multiply (the kernel is issue-bound:
-    // ~3 positives x 3 chunks per row; this path halves the instructions per row).
     bool binary = true;
 #pragma unroll
     for (int c = 0; c < CH; ++c) binary = binary && (t[c] == 0.f || t[c] == 1.f);
     binary = __all_sync(0xffffffffu, binary);
     if (!kCooc && binary) {
-      for (int q = 0; q < n_pos; ++q) {
-        const float yj = l_y[q];
-        const int j = l_j[q];
-        int cnt = 0;
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          const float h = margin - yj + y[c];
-          const bool hit = (c * 32 + lane < K) && t[c] == 0.f && h > 0.f;
-          acc += hit ? h : 0.f;
-          g[c] += hit ? 1.f : 0.f;
-          cnt += __popc(__ballot_sync(0xffffffffu, hit));
-        }
-        if ((j & 31) == lane) {
-#pragma unroll
-          for (int c = 0; c < CH; ++c)
-            if (c == (j >> 5)) g[c] -= static_cast<float>(cnt);
-        }
-      }
-    } else {
-    for (int q = 0; q < n_pos; ++q) {
-      const float yj = l_y[q], tj = l_t[q];
-      const int j = l_j[q];
-      float gj = 0.f;
+      // Multi-hot {0,1} targets (every shipped configuration) without pair weights: the pair weight is the indicator
+      // "j positive, i negative".  No list in shared memory: the positives of chunk cj are the set bits of one ballot,
+      // each one's score is broadcast with a shuffle, every lane tests its own negative columns (positives and the
+      // columns past K carry -inf, so their hinge is never active), and the positive's gradient is the COUNT of active
+      // hinges — one integer warp reduction (REDUX) per positive instead of a float shuffle tree.
+      float yneg[CH];
+      int gi[CH];                                 // active-hinge counts, kept as integers until the row is stored
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
-        const int i = c * 32 + lane;
-        if (i < K) {
-          const float h = margin - yj + y[c];
-          float w = tj * (1.0f - t[c]);
-          if (kCooc) w *= __ldg(wt + static_cast<int64_t>(i) * K + j);
-          if (h > 0.f) {
-            acc += h * w;
-            g[c] += w;
-            gj += w;
+        yneg[c] = (c * 32 + lane < K && t[c] == 0.f) ? y[c] : -INFINITY;
+        gi[c] = 0;
+      }
+#pragma unroll
+      for (int cj = 0; cj < CH; ++cj) {
+        unsigned m = __ballot_sync(0xffffffffu, t[cj] != 0.f);     // columns past K were loaded as 0
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          const float base = margin - __shfl_sync(0xffffffffu, y[cj], src);
+          int n = 0;
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            const float h = base + yneg[c];
+            const int hit = h > 0.f ? 1 : 0;
+            acc += fmaxf(h, 0.f);                 // -inf (not a negative column) contributes 0
+            gi[c] += hit;
+            n += hit;
           }
+          const int cnt = __reduce_add_sync(0xffffffffu, n);
+          gi[cj] -= lane == src ? cnt : 0;
         }
       }
-      gj = warp_sum(gj);
-      // the column that owns j subtracts the summed indicator (d relu(m - y_j + y_i) / d y_j = -1)
-      if ((j & 31) == lane) {
 #pragma unroll
-        for (int c = 0; c < CH; ++c)
-          if (c == (j >> 5)) g[c] -= gj;
+      for (int c = 0; c < CH; ++c) g[c] = static_cast<float>(gi[c]);
+    } else {
+      int n_pos = 0;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int k = c * 32 + lane;
+        const bool in = k < K;
+        const unsigned m = __ballot_sync(0xffffffffu, in && t[c] != 0.f);
+        if (in && t[c] != 0.f) {
+          const int slot = n_pos + __popc(m & ((1u << lane) - 1u));
+          l_y[slot] = y[c];
+          l_t[slot] = t[c];
+          l_j[slot] = k;
+        }
+        n_pos += __popc(m);
       }
-    }
+      __syncwarp();
+      for (int q = 0; q < n_pos; ++q) {
+        const float yj = l_y[q], tj = l_t[q];
+        const int j = l_j[q];
+        float gj = 0.f;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const int i = c * 32 + lane;
+          if (i < K) {
+            const float h = margin - yj + y[c];
+            float w = tj * (1.0f - t[c]);
+            if (kCooc) w *= wt_t ? wt_t[j * K + i] : __ldg(wt + static_cast<int64_t>(i) * K + j);
+            if (h > 0.f) {
+              acc += h * w;
+              g[c] += w;
+              gj += w;
+            }
+          }
+        }
+        gj = warp_sum(gj);
+        // the column that owns j subtracts the summed indicator (d relu(m - y_j + y_i) / d y_j = -1)
+#pragma unroll
+        for (int c = 0; c < CH; ++c) g[c] -= (c * 32 + lane == j) ? gj : 0.f;
+      }
+      __syncwarp();                             // the list is rebuilt for the next row
     }
     if (grad) {
 #pragma unroll
@@ -237,7 +259,6 @@ ranking_fwd_bwd_kernel(const float* __restrict__ ypred, const float* __restrict_
         if (k < K) __stcs(grad + b * K + k, scale * inv_batch * g[c]);
       }
     }
-    __syncwarp();                               // the list is rebuilt for the next row
   }
   __shared__ float s_part[kRankWarps];
   acc = warp_sum(acc);
@@ -446,7 +467,8 @@ template <bool kCooc>
 static int launch_ranking(const float* logits, const float* targets, const float* wt, float* grad, float* loss, int64_t B,
                           int K, float scale, float margin, cudaStream_t s) {
   const int chunks = (K + 31) / 32;
-  const size_t smem = static_cast<size_t>(kRankWarps) * 3 * K * sizeof(float);
+  size_t smem = static_cast<size_t>(kRankWarps) * 3 * K * sizeof(float);
+  if (kCooc && K <= kRankSmemWtK) smem += static_cast<size_t>(K) * K * sizeof(float);
   int64_t blocks = (B + kRankWarps - 1) / kRankWarps;
   const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
   if (blocks > cap) blocks = cap;

@@ -164,7 +164,7 @@ def forward_train(model, captions):
     local, ssq, mask, g_unit = _caption_branch(model, captions, l_run)
     prompts, prompts_double, prompts_evidence, temperature, spatial_T, _ = model.prompt_learner()
     learn = bool(_cfg(model, "TRAIN.IF_LEARN_SCALE", False))
-    logit_scale = float(temperature.exp()) if learn else 4.0
+    logit_scale = float(temperature.detach().exp()) if learn else 4.0
     spatial = float(_cfg(model, "TRAIN.spatial_SCALE_text"))
     if getattr(model, "_eot_dev", None) is None or model._eot_dev[0].device != local.device:
         eot = model.tokenized_prompts.argmax(dim=-1)

@@ -590,7 +590,40 @@ def test_adapter_model_matches_reference():
         err = np.abs(got - gref).max() / np.abs(gref).max()
         cos = float((got.flatten() @ gref.flatten()) / (np.linalg.norm(got) * np.linalg.norm(gref)))
         print(f"[adapter] grad {pname}: max err / max ref = {err:.4f}, cosine = {cos:.5f}")
-        assert err < 5e-2 and cos > 0.999, (pname, err, cos)
+        # The two ReLUs of the adapter make this gradient discontinuous in the adapter's input: the REFERENCE's own fp32
+        # gradient moves by 5-11 % of its max (cosine 0.995-0.999) when that input is perturbed by 1e-3 relative or the
+        # adapter's operands are rounded to bf16, and by 14-18 % (cosine 0.987-0.990) at 5e-3 — the bf16 transformer's
+        # error band (tools/adapter_grad_sensitivity.py).  The backward kernels themselves are pinned to 1e-2 with the
+        # masks held fixed in test_adapter_backward_chain_matches_fp32.
+        assert err < 0.2 and cos > 0.985, (pname, err, cos)
     for name, p in model.named_parameters():
         if "prompt_learner" not in name:
             assert p.grad is None, name
+
+
+@pytest.mark.gpu
+def test_adapter_backward_chain_matches_fp32():
+    """TextTower._adapter_fwd / _adapter_bwd against fp32 torch with the ReLU masks taken from the kernel's own forward
+    (a1 > 0, z2 > 0), so that a mask flip at a rounding-level pre-activation cannot hide or fake a backward error."""
+    from lecb200 import synth
+    from lecb200.engine import TextTower
+    tower = TextTower.__new__(TextTower)
+    tower.device = torch.device("cuda")
+    wd, wu = synth.adapter_weights(5)
+    tower.set_adapter(wd, wu)
+    gen = torch.Generator().manual_seed(11)
+    xr = torch.randn((160, 512), generator=gen).cuda()
+    d_out = torch.randn((160, 512), generator=gen).cuda()
+    out, a1, z2 = tower._adapter_fwd(xr)
+    wdf, wuf = wd.cuda().bfloat16().float(), wu.cuda().bfloat16().float()
+    xb = xr.bfloat16().float()
+    a1_ref = torch.relu(xb @ wdf.t())
+    ref = xr + torch.relu(a1_ref.bfloat16().float() @ wuf.t())
+    assert (out - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    assert (a1.float() - a1_ref).abs().max().item() <= 2e-2 * a1_ref.abs().max().item()
+    got = tower._adapter_bwd(d_out, a1, z2)
+    m2, m1 = (z2 > 0).float(), (a1.float() > 0).float()
+    want = d_out + (((d_out * m2) @ wuf) * m1) @ wdf
+    err = (got - want).abs().max().item() / want.abs().max().item()
+    print(f"[adapter bwd chain] max err / max = {err:.5f}")
+    assert err <= 1e-2
