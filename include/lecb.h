@@ -42,6 +42,9 @@ enum lecb_status {
 #define LECB_GEMM_F16_OPERANDS 16u /* A and W hold IEEE fp16 instead of bf16 (retrieval, T:445)  */
 #define LECB_EPI_AVGPOOL2 32u   /* lecb_conv3x3_bf16 only: 2x2 average pool after the activation (M:147,177 stem avgpool; */
                                 /* M:27,46 Bottleneck avgpool) fused into the epilogue; out is [B,H/2,W/2,Cout]            */
+#define LECB_EPI_MUL_QGELU_GRAD 64u /* lecb_gemm_bf16 only, bf16 out: `residual` holds the MLP pre-activation v (bf16 [M,N]) and  */
+                                /* y = (A W^T + bias) * QuickGELU'(v): the backward of M:202-204 fused into the data-gradient */
+                                /* GEMM of c_proj (autograd of M:226-227); excludes RELU / QUICKGELU / OUT_F32 / RES_F32      */
 
 int lecb_abi_version(void);
 const char* lecb_last_error(void);

@@ -84,7 +84,7 @@ SIGNATURES = {
                                    c_void_p]),
 }
 
-EPI_RELU, EPI_QUICKGELU, EPI_OUT_F32, EPI_RES_F32, GEMM_F16_OPERANDS, EPI_AVGPOOL2 = 1, 2, 4, 8, 16, 32
+EPI_RELU, EPI_QUICKGELU, EPI_OUT_F32, EPI_RES_F32, GEMM_F16_OPERANDS, EPI_AVGPOOL2, EPI_MUL_QGELU_GRAD = 1, 2, 4, 8, 16, 32, 64
 
 
 class LecbError(RuntimeError):

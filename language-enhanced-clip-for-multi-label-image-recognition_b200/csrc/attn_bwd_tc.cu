@@ -12,7 +12,10 @@
 //   dQ = dS K           A = dS (K-major)    B = K  (MN-major)    N = 64, K = j
 // The transposed operands are never materialised: the same shared-memory tiles are re-read through MN-major
 // descriptors.  K loops stop at ceil(L / 16) steps.
-// TMEM: S [0,128) | dP [128,256) | dV [256,320) | dK [320,384) | dQ [384,448).
+// TMEM (256 columns, so two CTAs share an SM): S [0,128) | dP [128,256) for the first two MMAs; once the row math has
+// read them, dV [0,64) | dK [64,128) | dQ [128,192) reuse the same columns.  Shared memory (112 KB, two CTAs per SM):
+// Q | K | dO | P(keys 0-63) | V | dS, and the second 64-key block of P is written over V, which only the dP MMA reads.
+// One CTA per SM (round 1: 512 columns, 128 KB) left every phase — TMA latency, MMA, row math, epilogue — exposed.
 #include "lecb_common.cuh"
 #include "lecb_host.h"
 
@@ -22,12 +25,14 @@ constexpr int kAbTile = 128;
 constexpr int kAbDh = 64;
 constexpr int kAbThreads = 160;                       // warps 0-3 row math + epilogue, warp 4 TMA + MMA issue
 constexpr int kAbTileBytes = kAbTile * kAbDh * 2;     // 16 KB
-constexpr int kAbSmemQ = 0, kAbSmemK = kAbTileBytes, kAbSmemV = 2 * kAbTileBytes, kAbSmemO = 3 * kAbTileBytes;
-constexpr int kAbSmemP = 4 * kAbTileBytes;            // [128 x 128] bf16 as two 64-column blocks
-constexpr int kAbSmemS = 6 * kAbTileBytes;            // dS, same shape
-constexpr int kAbSmemBars = 8 * kAbTileBytes;
+constexpr int kAbSmemQ = 0, kAbSmemK = kAbTileBytes, kAbSmemO = 2 * kAbTileBytes;
+constexpr int kAbSmemP = 3 * kAbTileBytes;            // [128 x 128] bf16 as two 64-column blocks; the second one IS the V tile
+constexpr int kAbSmemV = 4 * kAbTileBytes;
+constexpr int kAbSmemS = 5 * kAbTileBytes;            // dS, same shape
+constexpr int kAbSmemBars = 7 * kAbTileBytes;
 constexpr int kAbSmemBytes = kAbSmemBars + 64;
-constexpr int kAbTmemCols = 512;
+constexpr int kAbTmemCols = 256;
+constexpr uint32_t kAbColDV = 0, kAbColDK = 64, kAbColDQ = 128;      // reuse of the S / dP columns
 
 struct AttnBwdParams {
   __nv_bfloat16* dqkv;
@@ -66,7 +71,7 @@ __device__ __forceinline__ float ab_exp2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(kAbThreads, 1)
+__global__ void __launch_bounds__(kAbThreads, 2)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const AttnBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -137,14 +142,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       tc_fence_after();
       for (int ks = 0; ks < nk; ++ks) {           // dV = P^T dO, dK = dS^T Q (K = query index i, 16 rows = 2048 B)
         const uint32_t off = static_cast<uint32_t>(ks) * 2048u;
-        umma_f16(tmem_base + 256u, ab_desc(smem_u32(sP) + off, kAbTileBytes, 1024), ab_desc(smem_u32(sO) + off, 16, 1024),
+        umma_f16(tmem_base + kAbColDV, ab_desc(smem_u32(sP) + off, kAbTileBytes, 1024), ab_desc(smem_u32(sO) + off, 16, 1024),
                  id_mm64, ks != 0 ? 1u : 0u);
-        umma_f16(tmem_base + 320u, ab_desc(smem_u32(sS) + off, kAbTileBytes, 1024), ab_desc(smem_u32(sQ) + off, 16, 1024),
+        umma_f16(tmem_base + kAbColDK, ab_desc(smem_u32(sS) + off, kAbTileBytes, 1024), ab_desc(smem_u32(sQ) + off, 16, 1024),
                  id_mm64, ks != 0 ? 1u : 0u);
       }
       for (int ks = 0; ks < nk; ++ks) {           // dQ = dS K (K = key index j: 64-key blocks, 32 B per step inside)
         const uint32_t a_off = static_cast<uint32_t>(ks >> 2) * kAbTileBytes + static_cast<uint32_t>(ks & 3) * 32u;
-        umma_f16(tmem_base + 384u, ab_desc(smem_u32(sS) + a_off, 16, 1024),
+        umma_f16(tmem_base + kAbColDQ, ab_desc(smem_u32(sS) + a_off, 16, 1024),
                  ab_desc(smem_u32(sK) + static_cast<uint32_t>(ks) * 2048u, 16, 1024), id_km64, ks != 0 ? 1u : 0u);
       }
       umma_commit(mma2);
@@ -221,7 +226,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     __nv_bfloat16* orow = p.dqkv + (static_cast<int64_t>(n) * L + i) * 3 * p.W + h * kAbDh;
 #pragma unroll 1
     for (int which = 0; which < 3; ++which) {       // 0: dQ, 1: dK, 2: dV
-      const uint32_t col = which == 0 ? 384u : (which == 1 ? 320u : 256u);
+      const uint32_t col = which == 0 ? kAbColDQ : (which == 1 ? kAbColDK : kAbColDV);
       uint32_t r0[32], r1[32];
       tmem_ld_32x32(tmem_base + lane_base + col, r0);
       tmem_ld_32x32(tmem_base + lane_base + col + 32u, r1);
@@ -269,6 +274,8 @@ extern "C" int lecb_attn_causal_bwd(const void* qkv, const void* dout, void* dqk
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmemBytes);
     if (e != cudaSuccess) return fail(LECB_ERR_CUDA, "cudaFuncSetAttribute(attn bwd smem=%d): %s", kAbSmemBytes, cudaGetErrorString(e));
+    e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return fail(LECB_ERR_CUDA, "cudaFuncSetAttribute(attn bwd carveout): %s", cudaGetErrorString(e));
     configured = true;
   }
   CUtensorMap tmQKV, tmDO;

@@ -302,6 +302,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quarter = warp & 3;
     const bool relu = p.flags & LECB_EPI_RELU;
     const bool gelu = p.flags & LECB_EPI_QUICKGELU;
+    const bool mul_gelu_grad = p.flags & LECB_EPI_MUL_QGELU_GRAD;
     const uint32_t erow = static_cast<uint32_t>(quarter * 32 + lane);
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
     for (int tile_seq = 0; tile_seq < my_tiles; ++tile_seq) {
@@ -399,13 +400,24 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           if (p.residual != nullptr) {
+            if (mul_gelu_grad) {        // `residual` holds the fc pre-activation v: y = (A W^T) * QuickGELU'(v)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 u = *reinterpret_cast<const uint4*>(cbuf + swizzled_chunk_offset(erow, half * 4 + q, 128));
-              v2[q * 4 + 0] = fadd2(v2[q * 4 + 0], unpack_bf16(u.x));
-              v2[q * 4 + 1] = fadd2(v2[q * 4 + 1], unpack_bf16(u.y));
-              v2[q * 4 + 2] = fadd2(v2[q * 4 + 2], unpack_bf16(u.z));
-              v2[q * 4 + 3] = fadd2(v2[q * 4 + 3], unpack_bf16(u.w));
+              for (int q = 0; q < 4; ++q) {
+                const uint4 u = *reinterpret_cast<const uint4*>(cbuf + swizzled_chunk_offset(erow, half * 4 + q, 128));
+                v2[q * 4 + 0] = mul_quick_gelu_grad(v2[q * 4 + 0], unpack_bf16(u.x));
+                v2[q * 4 + 1] = mul_quick_gelu_grad(v2[q * 4 + 1], unpack_bf16(u.y));
+                v2[q * 4 + 2] = mul_quick_gelu_grad(v2[q * 4 + 2], unpack_bf16(u.z));
+                v2[q * 4 + 3] = mul_quick_gelu_grad(v2[q * 4 + 3], unpack_bf16(u.w));
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 u = *reinterpret_cast<const uint4*>(cbuf + swizzled_chunk_offset(erow, half * 4 + q, 128));
+                v2[q * 4 + 0] = fadd2(v2[q * 4 + 0], unpack_bf16(u.x));
+                v2[q * 4 + 1] = fadd2(v2[q * 4 + 1], unpack_bf16(u.y));
+                v2[q * 4 + 2] = fadd2(v2[q * 4 + 2], unpack_bf16(u.z));
+                v2[q * 4 + 3] = fadd2(v2[q * 4 + 3], unpack_bf16(u.w));
+              }
             }
           }
           if (gelu) {

@@ -456,6 +456,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int quarter = warp & 3;                // TMEM lane quarter this warp may read
     const bool relu = p.flags & LECB_EPI_RELU;
     const bool gelu = p.flags & LECB_EPI_QUICKGELU;
+    const bool mul_gelu_grad = p.flags & LECB_EPI_MUL_QGELU_GRAD;
     const bool res_f32 = p.flags & LECB_EPI_RES_F32;
     const uint32_t erow = static_cast<uint32_t>(quarter * 32 + lane);   // row inside the tile == TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
@@ -614,13 +615,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
             }
             if (p.residual != nullptr) {
+              if (mul_gelu_grad) {        // `residual` holds the fc pre-activation v: y = (A W^T) * QuickGELU'(v)
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint4 u = *reinterpret_cast<const uint4*>(cbuf + swizzled_chunk_offset(erow, half * 4 + q, kCCols * 2));
-                v2[q * 4 + 0] = fadd2(v2[q * 4 + 0], unpack_bf16(u.x));
-                v2[q * 4 + 1] = fadd2(v2[q * 4 + 1], unpack_bf16(u.y));
-                v2[q * 4 + 2] = fadd2(v2[q * 4 + 2], unpack_bf16(u.z));
-                v2[q * 4 + 3] = fadd2(v2[q * 4 + 3], unpack_bf16(u.w));
+                for (int q = 0; q < 4; ++q) {
+                  const uint4 u = *reinterpret_cast<const uint4*>(cbuf + swizzled_chunk_offset(erow, half * 4 + q, kCCols * 2));
+                  v2[q * 4 + 0] = mul_quick_gelu_grad(v2[q * 4 + 0], unpack_bf16(u.x));
+                  v2[q * 4 + 1] = mul_quick_gelu_grad(v2[q * 4 + 1], unpack_bf16(u.y));
+                  v2[q * 4 + 2] = mul_quick_gelu_grad(v2[q * 4 + 2], unpack_bf16(u.z));
+                  v2[q * 4 + 3] = mul_quick_gelu_grad(v2[q * 4 + 3], unpack_bf16(u.w));
+                }
+              } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const uint4 u = *reinterpret_cast<const uint4*>(cbuf + swizzled_chunk_offset(erow, half * 4 + q, kCCols * 2));
+                  v2[q * 4 + 0] = fadd2(v2[q * 4 + 0], unpack_bf16(u.x));
+                  v2[q * 4 + 1] = fadd2(v2[q * 4 + 1], unpack_bf16(u.y));
+                  v2[q * 4 + 2] = fadd2(v2[q * 4 + 2], unpack_bf16(u.z));
+                  v2[q * 4 + 3] = fadd2(v2[q * 4 + 3], unpack_bf16(u.w));
+                }
               }
             }
             if (gelu) {
@@ -987,6 +999,10 @@ extern "C" int lecb_gemm_bf16(const void* A, const void* W, const float* bias, c
   LECB_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
                  "lecb_gemm_bf16: operands must be 16-byte aligned");
+  if (flags & LECB_EPI_MUL_QGELU_GRAD)
+    LECB_CHECK_ARG(residual != nullptr && !(flags & (LECB_EPI_RELU | LECB_EPI_QUICKGELU | LECB_EPI_OUT_F32 | LECB_EPI_RES_F32)),
+                   "lecb_gemm_bf16: LECB_EPI_MUL_QGELU_GRAD needs the bf16 pre-activation in `residual`, a bf16 output and no "
+                   "other activation");
   // (a bf16 residual with an fp32 output stays on the single-CTA kernel's direct path)
   if (pair_gemm_eligible(M, N, K, flags, (flags & LECB_EPI_OUT_F32) && residual != nullptr && !(flags & LECB_EPI_RES_F32)))
     return launch_pair_gemm(A, W, bias, residual, out, row_sumsq, M, N, K, flags, static_cast<cudaStream_t>(stream));

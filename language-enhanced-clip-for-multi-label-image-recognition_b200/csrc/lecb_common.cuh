@@ -296,5 +296,15 @@ __device__ __forceinline__ float quick_gelu(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
   return x * r;
 }
+// d/dv [v * sigmoid(1.702 v)] = s * (1 + 1.702 v (1 - s)), same two MUFU ops
+__device__ __forceinline__ float quick_gelu_grad(float v) {
+  float e, s;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.702f * 1.4426950408889634f * v));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(1.0f + e));
+  return s * fmaf(1.702f * v, 1.0f - s, 1.0f);
+}
+__device__ __forceinline__ float2 mul_quick_gelu_grad(float2 g, float2 v) {
+  return make_float2(g.x * quick_gelu_grad(v.x), g.y * quick_gelu_grad(v.y));
+}
 
 }  // namespace lecb

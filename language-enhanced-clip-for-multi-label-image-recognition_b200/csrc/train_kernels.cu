@@ -456,41 +456,103 @@ head_aggregate_bwd_kernel(const float* __restrict__ dots, int ldn, const float* 
 
 // ---------------------------------------------------------------------------------------------
 // out[J,D] (+)= sum_r a[r,J] * b[r,D];  a fp32 [R,lda], b bf16 or fp32 [R,D].  Each CTA owns a 16 x 64 output
-// tile and strides over R; fp32 accumulate.  (J = n_txt*K = 160..240, D <= 1024, R = B*L: ~2.4 GFLOP.)
+// tile and walks R in 64-row chunks: the next chunk's global loads (16-byte vectors when the operands allow) are in
+// flight in registers while the current one is consumed from shared memory; a thread owns 1 x 4 outputs (one
+// broadcast LDS + one LDS.128 per four FMAs); fp32 accumulate in a fixed order, so the result is reproducible.
+// (J = n_txt*K = 160..240, D <= 1024, R = B*L: ~0.6-2.4 GFLOP.  The first version — scalar loads, 32-row chunks,
+// nothing in flight across the barrier — took 253 us for R = 1792, J = 160, D = 1024.)
 // ---------------------------------------------------------------------------------------------
+constexpr int kTnRows = 64;
 template <typename TB>
 __global__ void __launch_bounds__(256)
 tn_gemm_small_kernel(const float* __restrict__ a, int lda, const TB* __restrict__ b, float* __restrict__ out, int R,
-                     int J, int D, float alpha, int accumulate) {
-  __shared__ float sA[32][17];
-  __shared__ float sB[32][65];
+                     int J, int D, float alpha, int accumulate, int a_vec, int b_vec) {
+  constexpr bool kBf16 = sizeof(TB) == 2;
+  constexpr int kBPer = kBf16 ? 2 : 4;           // 16-byte vectors of b per thread and chunk (64 x 64 elements)
+  constexpr int kBElems = kBf16 ? 8 : 4;         // elements per vector
+  constexpr int kBVecRow = 64 / kBElems;         // vectors per 64-element row
+  __shared__ __align__(16) float sA[kTnRows][16];
+  __shared__ __align__(16) float sB[kTnRows][64];
   const int j0 = blockIdx.y * 16, d0 = blockIdx.x * 64;
   const int tid = threadIdx.x;
-  const int tj = tid / 16;          // 0..15
-  const int td = (tid % 16) * 4;    // 0..60
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int r0 = 0; r0 < R; r0 += 32) {
-    for (int i = tid; i < 32 * 16; i += 256) {
-      const int r = i / 16, j = i % 16;
-      sA[r][j] = (r0 + r < R && j0 + j < J) ? a[static_cast<int64_t>(r0 + r) * lda + j0 + j] : 0.f;
+  const int tj = tid >> 4;           // 0..15
+  const int td = (tid & 15) * 4;     // 0..60
+  const int ar = tid >> 2, aj = (tid & 3) * 4;   // this thread's float4 of the a chunk
+  float4 ra;
+  float rb[kBPer][kBElems];
+  auto fetch = [&](int r0) {
+    const int r = r0 + ar;
+    const float* src = a + static_cast<int64_t>(r) * lda + j0 + aj;
+    if (r < R && a_vec && j0 + aj + 3 < J) {
+      ra = __ldg(reinterpret_cast<const float4*>(src));
+    } else {
+      ra.x = (r < R && j0 + aj + 0 < J) ? __ldg(src + 0) : 0.f;
+      ra.y = (r < R && j0 + aj + 1 < J) ? __ldg(src + 1) : 0.f;
+      ra.z = (r < R && j0 + aj + 2 < J) ? __ldg(src + 2) : 0.f;
+      ra.w = (r < R && j0 + aj + 3 < J) ? __ldg(src + 3) : 0.f;
     }
-    for (int i = tid; i < 32 * 64; i += 256) {
-      const int r = i / 64, d = i % 64;
-      float v = 0.f;
-      if (r0 + r < R && d0 + d < D) {
-        if constexpr (sizeof(TB) == 2) v = __bfloat162float(b[static_cast<int64_t>(r0 + r) * D + d0 + d]);
-        else v = b[static_cast<int64_t>(r0 + r) * D + d0 + d];
-      }
-      sB[r][d] = v;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int r = 0; r < 32; ++r) {
-      const float av = sA[r][tj];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q] = fmaf(av, sB[r][td + q], acc[q]);
+    for (int q = 0; q < kBPer; ++q) {
+      const int idx = tid + 256 * q;
+      const int rr = r0 + idx / kBVecRow, dd = d0 + (idx % kBVecRow) * kBElems;
+      const TB* bs = b + static_cast<int64_t>(rr) * D + dd;
+      if (rr < R && b_vec && dd + kBElems - 1 < D) {
+        if constexpr (kBf16) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(bs));
+          const uint32_t* vi = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = unpack_bf16(vi[e]);
+            rb[q][2 * e] = f.x;
+            rb[q][2 * e + 1] = f.y;
+          }
+        } else {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(bs));
+          rb[q][0] = v.x;
+          rb[q][1] = v.y;
+          rb[q][2] = v.z;
+          rb[q][3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < kBElems; ++e) {
+          float v = 0.f;
+          if (rr < R && dd + e < D) {
+            if constexpr (kBf16) v = __bfloat162float(bs[e]);
+            else v = bs[e];
+          }
+          rb[q][e] = v;
+        }
+      }
     }
+  };
+  auto stash = [&]() {
+    *reinterpret_cast<float4*>(&sA[ar][aj]) = ra;
+#pragma unroll
+    for (int q = 0; q < kBPer; ++q) {
+      const int idx = tid + 256 * q;
+      float* dst = &sB[idx / kBVecRow][(idx % kBVecRow) * kBElems];
+#pragma unroll
+      for (int e = 0; e < kBElems; e += 4)
+        *reinterpret_cast<float4*>(dst + e) = make_float4(rb[q][e], rb[q][e + 1], rb[q][e + 2], rb[q][e + 3]);
+    }
+  };
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  fetch(0);
+  for (int r0 = 0; r0 < R; r0 += kTnRows) {
+    __syncthreads();                 // the previous chunk has been consumed
+    stash();
     __syncthreads();
+    if (r0 + kTnRows < R) fetch(r0 + kTnRows);
+#pragma unroll 16
+    for (int r = 0; r < kTnRows; ++r) {
+      const float av = sA[r][tj];
+      const float4 bv = *reinterpret_cast<const float4*>(&sB[r][td]);
+      acc[0] = fmaf(av, bv.x, acc[0]);
+      acc[1] = fmaf(av, bv.y, acc[1]);
+      acc[2] = fmaf(av, bv.z, acc[2]);
+      acc[3] = fmaf(av, bv.w, acc[3]);
+    }
   }
   if (j0 + tj < J) {
 #pragma unroll
@@ -643,10 +705,13 @@ extern "C" int lecb_tn_gemm_small(const float* a, int lda, const void* b, int b_
   LECB_CHECK_ARG(a && b && out && R > 0 && J > 0 && D > 0 && lda >= J, "lecb_tn_gemm_small: bad argument");
   dim3 grid((D + 63) / 64, (J + 15) / 16);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int a_vec = (lda % 4 == 0) && (reinterpret_cast<uintptr_t>(a) & 15) == 0;
+  const int b_vec = (D % (b_is_bf16 ? 8 : 4) == 0) && (reinterpret_cast<uintptr_t>(b) & 15) == 0;
   if (b_is_bf16)
-    tn_gemm_small_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(a, lda, static_cast<const __nv_bfloat16*>(b), out, R, J, D, alpha, accumulate);
+    tn_gemm_small_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(a, lda, static_cast<const __nv_bfloat16*>(b), out, R, J, D, alpha,
+                                                             accumulate, a_vec, b_vec);
   else
-    tn_gemm_small_kernel<float><<<grid, 256, 0, s>>>(a, lda, static_cast<const float*>(b), out, R, J, D, alpha, accumulate);
+    tn_gemm_small_kernel<float><<<grid, 256, 0, s>>>(a, lda, static_cast<const float*>(b), out, R, J, D, alpha, accumulate, a_vec, b_vec);
   count_launch();
   return check_launch("tn_gemm_small_kernel");
 }

@@ -301,8 +301,7 @@ class TextTower:
             dh[torch.arange(n, device=d_out.device), saved["eot"]] = d_rows                           # only EOT rows see the loss
             dx, dxb = ops.layernorm_bwd(dh.view(n * l, w), xf, self.ln_final[0], mf, rf)
         for blk, t, (x0, m1, r1, qkv, x1, m2, r2, v) in zip(reversed(self.blocks), reversed(wt), reversed(saved["layers"])):
-            du = ops.gemm(dxb, t["proj"])                                  # [M,4W] bf16
-            dv = ops.quick_gelu_bwd(du, v)
+            dv = ops.gemm_mul_quick_gelu_grad(dxb, t["proj"], v)          # [M,4W] bf16: (dx @ W_proj) * QuickGELU'(v)
             dh2 = ops.gemm(dv, t["fc"], out_f32=True)
             dx1, dx1b = ops.layernorm_bwd(dh2, x1, blk["ln2"][0], m2, r2, dx_in=dx)
             da = ops.gemm(dx1b, t["out"])

@@ -51,6 +51,22 @@ def gemm(a, w, bias=None, residual=None, relu=False, quick_gelu=False, out_f32=F
     return out
 
 
+def gemm_mul_quick_gelu_grad(a, w, v, out=None):
+    """out[M,N] = (a[M,K] @ w[N,K]^T) * QuickGELU'(v[M,N]), all bf16: the c_proj data gradient and the QuickGELU backward
+    (autograd of M:202-204, 226-227) in one launch; the product is rounded to bf16 once."""
+    _need(a, torch.bfloat16, "a")
+    _need(w, torch.bfloat16, "w")
+    _need(v, torch.bfloat16, "v")
+    m, k = a.shape
+    n, k2 = w.shape
+    assert k == k2 and tuple(v.shape) == (m, n), (a.shape, w.shape, v.shape)
+    if out is None:
+        out = torch.empty((m, n), device=a.device, dtype=torch.bfloat16)
+    check(lib.lecb_gemm_bf16(_ptr(a), _ptr(w), None, _ptr(v), _ptr(out), None, m, n, k, _lib.EPI_MUL_QGELU_GRAD, _stream()),
+          "lecb_gemm_bf16")
+    return out
+
+
 def conv3x3(x, w, bias=None, relu=True, out=None, pool=False):
     """x NHWC bf16 [B,H,W,Cin]; w bf16 [Cout,3,3,Cin] (BN folded); -> NHWC bf16 [B,H,W,Cout].
     pool=True appends the 2x2 average pool that follows the conv in the reference (M:147, M:27): fused into the conv

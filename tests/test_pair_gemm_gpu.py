@@ -119,3 +119,61 @@ def test_pair_gemm_f32_out_and_residual(m, n, k, pair_switch):
     torch.cuda.synchronize()
     want = out.pow(2).sum(-1)
     assert ((ssq - want).abs() / (want + 1e-6)).max().item() < 1e-4
+
+
+@pytest.mark.parametrize("m,n,k", [(12320, 2048, 512), (1792, 2048, 512), (300, 256, 64), (40000, 320, 256), (129, 64, 96)])
+def test_gemm_mul_quick_gelu_grad_epilogue(m, n, k, pair_switch):
+    """LECB_EPI_MUL_QGELU_GRAD — (A W^T) * QuickGELU'(v), the c_proj data gradient fused with the QuickGELU backward — on both
+    kernels, against fp32 torch (autograd of v * sigmoid(1.702 v)) and against the two-launch path it replaces."""
+    from lecb200 import ops
+    a = _rand((m, k), 31).bfloat16()
+    w = _rand((n, k), 32, k ** -0.5).bfloat16()
+    v = _rand((m, n), 33, 1.5).bfloat16()
+    vf = v.float().requires_grad_(True)
+    (vf * torch.sigmoid(1.702 * vf)).sum().backward()
+    want = (a.float() @ w.float().t()) * vf.grad
+    outs = []
+    for sw in (1, 0):
+        pair_switch(sw)
+        got = ops.gemm_mul_quick_gelu_grad(a, w, v)
+        torch.cuda.synchronize()
+        _check(got, want, f"mul-gelu-grad {m}x{n}x{k} pair={sw}")
+        outs.append(got)
+    assert torch.equal(outs[0], outs[1])
+    two = ops.quick_gelu_bwd(ops.gemm(a, w), v) if (m * n) % 8 == 0 else None
+    if two is not None:
+        _check(two, want, "two-launch path")
+    with pytest.raises(RuntimeError):
+        from lecb200 import _lib
+        out = torch.empty((m, n), device="cuda", dtype=torch.bfloat16)
+        _lib.check(_lib.lib.lecb_gemm_bf16(a.data_ptr(), w.data_ptr(), None, None, out.data_ptr(), None, m, n, k,
+                                           _lib.EPI_MUL_QGELU_GRAD, None), "lecb_gemm_bf16")
+
+
+@pytest.mark.parametrize("r,j,d,lda,bf16", [(1792, 160, 1024, 160, True), (1792, 240, 1024, 240, True), (64, 80, 1024, 80, False),
+                                            (77, 13, 100, 19, True), (130, 33, 72, 36, False), (5, 1, 3, 1, True),
+                                            (4928, 160, 512, 168, True)])
+def test_tn_gemm_small_matches_torch(r, j, d, lda, bf16):
+    """out[J,D] (+)= alpha * a[:, :J]^T @ b — the prompt-feature gradient product (T:496-514 backward) — incl. ragged R / J / D,
+    lda > J, operands that force the scalar loads, fp32 and bf16 b, accumulate; and that the result is reproducible."""
+    from lecb200 import ops
+    a = _rand((r, lda), 41)
+    b = _rand((r, d), 42)
+    b = b.bfloat16() if bf16 else b
+    want = a[:, :j].double().t() @ b.double()
+    got = ops.tn_gemm_small(a, b, j)
+    torch.cuda.synchronize()
+    tol = 1e-5 * max(1.0, want.abs().max().item()) * max(1.0, r ** 0.5 / 8)
+    assert (got.double() - want).abs().max().item() <= tol
+    again = ops.tn_gemm_small(a, b, j)
+    assert torch.equal(got, again)
+    base = _rand((j, d), 43)
+    acc = base.clone()
+    ops.tn_gemm_small(a, b, j, out=acc, alpha=0.5, accumulate=True)
+    assert (acc.double() - (base.double() + 0.5 * want)).abs().max().item() <= tol
+    # operands that start off a 16-byte boundary: the vector loads must not be taken
+    a_un = torch.empty((r * lda + 1,), device="cuda")[1:].view(r, lda).copy_(a)
+    b_un = torch.empty((r * d + 1,), device="cuda", dtype=b.dtype)[1:].view(r, d).copy_(b)
+    assert a_un.data_ptr() % 16 != 0 and b_un.data_ptr() % 16 != 0 and a_un.is_contiguous()
+    got2 = ops.tn_gemm_small(a_un, b_un, j)
+    assert torch.equal(got2, got)
