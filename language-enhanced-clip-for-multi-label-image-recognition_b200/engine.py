@@ -255,33 +255,53 @@ class TextTower:
             self._text_proj = self.text_proj_t.t().contiguous()              # [W, D]: W-operand of d_rows = dT @ P^T
         return self._wt
 
-    def forward_train(self, x, eot_index):
-        """Like forward(x, eot_index) but keeps what the backward needs.  x fp32 [N,L,W] -> (T_raw fp32 [N,D], saved)."""
+    def forward_train(self, x, eot_index, rider=None):
+        """Like forward(x, eot_index) but keeps what the backward needs.  x fp32 [N,L,W] -> (T_raw fp32 [N,D], saved).
+
+        `rider` = fp32 [Nc,Lc,W]: a second, gradient-free batch of sequences (the caption branch of the prompt-tuning step,
+        T:474-477) carried through the SAME per-layer launches — LayerNorm, the four GEMMs and QuickGELU are row-wise, so
+        its rows are appended to the prompt rows and only the attention runs once per group (different N and L).  Halves the
+        launches of a step that is bound by them.  Returns (T_raw, saved, rider rows before ln_final fp32 [Nc*Lc,W])."""
         n, l, w = x.shape
-        x = x.reshape(n * l, w).contiguous()
+        x = x.reshape(n * l, w)
+        rp = n * l
+        if rider is not None:
+            nc, lc, _ = rider.shape
+            x = torch.cat([x, rider.reshape(nc * lc, w)], 0)
+        x = x.contiguous()
         saved = {"n": n, "l": l, "w": w, "eot": eot_index, "layers": []}
         for blk in self.blocks:
             h, _, m1, r1 = ops.layernorm(x, *blk["ln1"], save_stats=True)
             qkv = ops.gemm(h, *blk["qkv"])
-            a = ops.causal_attn(qkv, n, l, w, self.heads)      # bwd (lecb_attn_causal_bwd) rounds P to bf16 the same way
+            if rider is None:
+                a = ops.causal_attn(qkv, n, l, w, self.heads)  # bwd (lecb_attn_causal_bwd) rounds P to bf16 the same way
+            else:
+                a = torch.empty((x.shape[0], w), device=x.device, dtype=torch.bfloat16)
+                ops.attn_fwd(qkv[:rp], n, l, w, self.heads, causal=True, out=a[:rp])
+                ops.attn_fwd(qkv[rp:], nc, lc, w, self.heads, causal=True, out=a[rp:])
             x1 = ops.gemm_f32res(a, *blk["out"], x)
             h, _, m2, r2 = ops.layernorm(x1, *blk["ln2"], save_stats=True)
             v = ops.gemm(h, *blk["fc"])                         # pre-activation kept for the QuickGELU backward
             u = ops.quick_gelu_fwd(v)
             x2 = ops.gemm_f32res(u, *blk["proj"], x1)
-            saved["layers"].append((x, m1, r1, qkv, x1, m2, r2, v))
+            saved["layers"].append((x[:rp], m1[:rp], r1[:rp], qkv[:rp], x1[:rp], m2[:rp], r2[:rp], v[:rp]))
             x = x2
+        tail = None
+        if rider is not None:
+            tail, x = x[rp:], x[:rp]
         if self.adapter is not None:
             xr = x.view(n, l, w)[torch.arange(n, device=x.device), eot_index].contiguous()
             xr2, a1, z2 = self._adapter_fwd(xr)
             h, _, mf, rf = ops.layernorm(xr2, *self.ln_final, save_stats=True)
             saved["final"] = (xr2, mf, rf)
             saved["adapter"] = (a1, z2)
-            return ops.gemm(h, self.text_proj_t, out_f32=True), saved
-        h, _, mf, rf = ops.layernorm(x, *self.ln_final, save_stats=True)
-        saved["final"] = (x, mf, rf)
-        rows = h.view(n, l, w)[torch.arange(n, device=h.device), eot_index].contiguous()
-        return ops.gemm(rows, self.text_proj_t, out_f32=True), saved
+            t_raw = ops.gemm(h, self.text_proj_t, out_f32=True)
+        else:
+            h, _, mf, rf = ops.layernorm(x, *self.ln_final, save_stats=True)
+            saved["final"] = (x, mf, rf)
+            rows = h.view(n, l, w)[torch.arange(n, device=h.device), eot_index].contiguous()
+            t_raw = ops.gemm(rows, self.text_proj_t, out_f32=True)
+        return (t_raw, saved) if rider is None else (t_raw, saved, tail)
 
     def backward(self, saved, d_out):
         """d_out fp32 [N,D] = dL/dT_raw  ->  dL/dx fp32 [N,L,W] (x = prompt embeddings + positional embedding)."""

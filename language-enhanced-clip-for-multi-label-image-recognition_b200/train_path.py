@@ -22,6 +22,9 @@ class _DualPromptHead(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pack, logit_scale_t, *prompts):
         tower, (tok_prompts, l_eff), local, ssq, mask, g_unit, b, l, logit_scale, spatial, shard_group = pack
+        rider = None
+        if isinstance(local, dict):              # the caption branch has not run yet: it rides along with the prompt rows
+            rider = local
         n_txt = len(prompts)
         k = prompts[0].shape[0]
         # The mask is causal (M:364-370) and only the EOT row of a prompt is used (T:100), so positions after the
@@ -31,17 +34,23 @@ class _DualPromptHead(torch.autograd.Function):
         x = (torch.cat([p.detach().float() for p in prompts], 0) + tower.pos)[:, :l_eff].contiguous()   # [n*K, l_eff, W]
         eot = tok_prompts.repeat(n_txt)          # EOT index per prompt sequence, already on the device
         ctx.rows = None
-        if shard_group is None:
-            t_raw, saved = tower.forward_train(x, eot)                                            # [n*K, D] fp32
-        else:
+        xr, er, group = x, eot, None
+        if shard_group is not None:
             # class-sharded prompt branch (dist.py): the tower runs on this rank's rows, the features are all-gathered
             group = None if shard_group is True else shard_group
             lo, hi, _ = dist.my_chunk(x.shape[0], group)
             if hi <= lo:
                 raise RuntimeError(f"shard_prompt_branch: {x.shape[0]} prompt sequences cannot feed every rank")
-            t_own, saved = tower.forward_train(x[lo:hi].contiguous(), eot[lo:hi].contiguous())
-            t_raw = dist.gather_rows(t_own, x.shape[0], group)
+            xr, er = x[lo:hi].contiguous(), eot[lo:hi].contiguous()
             ctx.rows = (lo, hi, group, x.shape[0], x.shape[1], x.shape[2])
+        if rider is not None:
+            t_raw, saved, tail = tower.forward_train(xr, er, rider=rider["x"])
+            local, ssq, mask, g_unit = _caption_tail(tower, tail, rider["captions"])
+            rider["out"] = (local, ssq, mask, g_unit)
+        else:
+            t_raw, saved = tower.forward_train(xr, er)                                            # [n*K, D] fp32
+        if shard_group is not None:
+            t_raw = dist.gather_rows(t_raw, x.shape[0], group)
         t_hat = ops.l2norm_rows(t_raw)
         pad = (-t_hat.shape[0]) % 8
         t_cat = t_hat if not pad else torch.cat([t_hat, t_hat.new_zeros((pad, t_hat.shape[1]))], 0)
@@ -105,15 +114,35 @@ def caption_run_length(model, captions):
     return max(1, min(l, int(captions.argmax(dim=-1).max()) + 1))
 
 
+def _caption_inputs(model, captions, l_run=None):
+    """T:474-475: token embedding + positional embedding of the first l_run caption positions -> (fp32 [B,l,W], captions[:, :l])."""
+    tw = model.text_encoder.tower()
+    if l_run is not None and l_run < captions.shape[1]:
+        captions = captions[:, :l_run].contiguous()
+    l = captions.shape[1]
+    return (tw.tok[captions] + tw.pos[:l]).contiguous(), captions
+
+
+def _caption_tail(tw, xs, captions):
+    """T:476-477,485-486,491 after the transformer: ln_final, projection (+ row sum of squares), the EOT row as the global feature,
+    the padding mask.  xs fp32 [B*l, W]."""
+    b, l = captions.shape
+    h, _, _, _ = ops.layernorm(xs, *tw.ln_final)
+    ssq = torch.zeros((b * l,), device=xs.device, dtype=torch.float32)
+    local = ops.gemm(h, tw.text_proj_t, row_sumsq=ssq)                       # bf16 [B*L, D] + row sum of squares
+    eot = captions.argmax(dim=-1)
+    g = local.view(b, l, -1)[torch.arange(b, device=xs.device), eot].float().contiguous()
+    g_unit = ops.l2norm_rows(g)
+    mask = (captions == 0).to(torch.uint8).reshape(-1).contiguous()          # token id 0 = padding (T:491)
+    return local, ssq, mask, g_unit
+
+
 @torch.no_grad()
 def _caption_branch(model, captions, l_run=None):
     """T:474-477,485-486,491: per-token caption features (frozen path) for the first l_run positions."""
     tw = model.text_encoder.tower()
-    if l_run is not None and l_run < captions.shape[1]:
-        captions = captions[:, :l_run].contiguous()
-    b, l = captions.shape
-    x = (tw.tok[captions] + tw.pos[:l]).contiguous()
-    n, _, w = x.shape
+    x, captions = _caption_inputs(model, captions, l_run)
+    n, l, w = x.shape
     xs = x.reshape(n * l, w)
     for blk in tw.blocks:
         h, _, _, _ = ops.layernorm(xs, *blk["ln1"])
@@ -123,14 +152,7 @@ def _caption_branch(model, captions, l_run=None):
         h, _, _, _ = ops.layernorm(xs, *blk["ln2"])
         u = ops.gemm(h, *blk["fc"], quick_gelu=True)
         xs = ops.gemm_f32res(u, *blk["proj"], xs)
-    h, _, _, _ = ops.layernorm(xs, *tw.ln_final)
-    ssq = torch.zeros((b * l,), device=x.device, dtype=torch.float32)
-    local = ops.gemm(h, tw.text_proj_t, row_sumsq=ssq)                       # bf16 [B*L, D] + row sum of squares
-    eot = captions.argmax(dim=-1)
-    g = local.view(b, l, -1)[torch.arange(b, device=x.device), eot].float().contiguous()
-    g_unit = ops.l2norm_rows(g)
-    mask = (captions == 0).to(torch.uint8).reshape(-1).contiguous()          # token id 0 = padding (T:491)
-    return local, ssq, mask, g_unit
+    return _caption_tail(tw, xs, captions)
 
 
 def _prompt_logits_nograd(model, learner, local, ssq, mask, g_unit, b, l, logit_scale, spatial, use_evidence):
@@ -161,15 +183,14 @@ def forward_train(model, captions):
     captions = captions.to(model.text_encoder.positional_embedding.device)
     b = captions.shape[0]
     l = l_run
-    local, ssq, mask, g_unit = _caption_branch(model, captions, l_run)
     prompts, prompts_double, prompts_evidence, temperature, spatial_T, _ = model.prompt_learner()
     learn = bool(_cfg(model, "TRAIN.IF_LEARN_SCALE", False))
     logit_scale = float(temperature.detach().exp()) if learn else 4.0
     spatial = float(_cfg(model, "TRAIN.spatial_SCALE_text"))
-    if getattr(model, "_eot_dev", None) is None or model._eot_dev[0].device != local.device:
+    if getattr(model, "_eot_dev", None) is None or model._eot_dev[0].device != captions.device:
         eot = model.tokenized_prompts.argmax(dim=-1)
         # cached (EOT indices on the device, live prompt length): keeps the step free of host syncs / graph-capturable
-        model._eot_dev = (eot.to(local.device), int(eot.max()) + 1)
+        model._eot_dev = (eot.to(captions.device), int(eot.max()) + 1)
     shard = getattr(model, "shard_prompt_branch", False)
     if shard and not dist.multi_rank(None if shard is True else shard):
         shard = False                    # single process: nothing to shard over
@@ -182,10 +203,23 @@ def forward_train(model, captions):
         n_rows = (3 if use_evidence else 2) * prompts.shape[0]
         if -(-n_rows // world) * (world - 1) >= n_rows:
             shard = False
-    pack = (model.text_encoder.tower(), model._eot_dev, local, ssq, mask, g_unit, b, l, logit_scale, spatial,
-            (True if shard is True else shard) if shard else None)
     plist = (prompts, prompts_double, prompts_evidence) if use_evidence else (prompts, prompts_double)
+    # One tower pass for both branches (the frozen caption rows ride along with the prompt rows — this rank's, when the prompt
+    # branch is sharded — through every row-wise launch: TextTower.forward_train) unless the model asks for two passes.
+    joint = bool(getattr(model, "joint_text_pass", True)) and torch.is_grad_enabled() and any(p.requires_grad for p in plist)
+    if joint:
+        with torch.no_grad():
+            cx, ccaps = _caption_inputs(model, captions, l_run)
+        rider = {"x": cx, "captions": ccaps}
+        pack = (model.text_encoder.tower(), model._eot_dev, rider, None, None, None, b, l, logit_scale, spatial,
+                (True if shard is True else shard) if shard else None)
+    else:
+        local, ssq, mask, g_unit = _caption_branch(model, captions, l_run)
+        pack = (model.text_encoder.tower(), model._eot_dev, local, ssq, mask, g_unit, b, l, logit_scale, spatial,
+                (True if shard is True else shard) if shard else None)
     logits, logits_local, text_features = _DualPromptHead.apply(pack, temperature if learn else None, *plist)
+    if joint:
+        local, ssq, mask, g_unit = rider.pop("out")
     with torch.no_grad():
         feats = ops.l2norm_rows(local, out_dtype=torch.float32).view(b, l, -1)
         if l < l_full:

@@ -218,9 +218,12 @@ def test_ema_step_matches_reference(ev):
     assert abs(r_loss.item() - float(g["r_loss" + sfx])) <= 1e-2 * max(1.0, abs(float(g["r_loss" + sfx])))
     # kernel vs the oracle's expression at the product's own logits (tight), and vs the reference's number (the 10000 x
     # local KL sees the bf16-level logit error of live and twin: 5 %)
+    # (in float64: the 10000 x local term is a sum of q * (log q - log p) with log differences of ~1e-3 between logs of ~4,
+    # so ANY fp32 evaluation — the kernel's, torch's — carries ~1e-3 of relative rounding noise)
     with torch.no_grad():
-        want = R.ema_loss(*(out[i].detach().float().cpu() for i in (0, 4, 1, 5)))
-    assert abs(ema_loss.item() - want.item()) <= 1e-3 * max(1.0, abs(want.item()))
+        want = R.ema_loss(*(out[i].detach().double().cpu() for i in (0, 4, 1, 5)))
+    print(f"[{sfx}] ema_loss kernel {ema_loss.item():.6f} vs float64 oracle at the same logits {want.item():.6f}")
+    assert abs(ema_loss.item() - want.item()) <= 3e-3 * max(1.0, abs(want.item()))
     ref_ema = float(g["ema_loss" + sfx])
     print(f"[{sfx}] ema_loss {ema_loss.item():.5f} vs reference {ref_ema:.5f}")
     assert abs(ema_loss.item() - ref_ema) <= 5e-2 * max(1.0, abs(ref_ema))
