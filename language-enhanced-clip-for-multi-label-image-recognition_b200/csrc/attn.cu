@@ -18,6 +18,7 @@ __global__ void __launch_bounds__(256)
 attnpool_query0_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ kmat,
                        const __nv_bfloat16* __restrict__ vmat, __nv_bfloat16* __restrict__ out, int P, int C,
                        float qscale) {
+  pdl_grid_sync();
   extern __shared__ float s_scores[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
@@ -104,6 +105,7 @@ constexpr int kKvPitch = kDh + 2;
 __global__ void __launch_bounds__(128)
 causal_attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int L, int W,
                        float scale) {
+  pdl_grid_sync();
   __shared__ __nv_bfloat16 sK[kLMax * kKvPitch];
   __shared__ __nv_bfloat16 sV[kLMax * kKvPitch];
   __shared__ float sP[4][kLMax];
@@ -171,7 +173,7 @@ extern "C" int lecb_attnpool_query0(const float* q, const void* kmat, const void
   const size_t smem = static_cast<size_t>(8) * (P + 1) * sizeof(float);
   LECB_CHECK_ARG(smem <= 48 * 1024, "lecb_attnpool_query0: P=%d too large", P);
   dim3 grid(heads / 8, B);
-  attnpool_query0_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(attnpool_query0_kernel, dim3(grid), dim3(256), smem, static_cast<cudaStream_t>(stream), 
       q, static_cast<const __nv_bfloat16*>(kmat), static_cast<const __nv_bfloat16*>(vmat),
       static_cast<__nv_bfloat16*>(out), P, C, 1.0f / sqrtf(static_cast<float>(kDh)));
   count_launch();
@@ -183,7 +185,7 @@ extern "C" int lecb_causal_attn_fwd(const void* qkv, void* out, int N, int L, in
   LECB_CHECK_ARG(N > 0 && L > 0 && L <= kLMax, "lecb_causal_attn_fwd: need 0 < L <= %d (L=%d)", kLMax, L);
   LECB_CHECK_ARG(W == heads * kDh, "lecb_causal_attn_fwd: head dim must be 64 (W=%d heads=%d)", W, heads);
   dim3 grid(heads, N);
-  causal_attn_fwd_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(causal_attn_fwd_kernel, dim3(grid), dim3(128), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), L, W, 1.0f / sqrtf(static_cast<float>(kDh)));
   count_launch();
   return check_launch("causal_attn_fwd_kernel");

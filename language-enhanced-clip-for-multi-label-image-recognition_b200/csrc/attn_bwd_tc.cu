@@ -114,6 +114,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync();       // prologue done while the previous kernel drained; no global access before this point
 
   if (warp == 4) {
     if (lane == 0) {
@@ -289,7 +290,7 @@ extern "C" int lecb_attn_causal_bwd(const void* qkv, const void* dout, void* dqk
   p.L = L;
   p.W = W;
   p.scale = 0.125f;
-  attn_bwd_kernel<<<dim3(heads, N), kAbThreads, kAbSmemBytes, static_cast<cudaStream_t>(stream)>>>(tmQKV, tmDO, p);
+  launch_k(attn_bwd_kernel, dim3(dim3(heads, N)), dim3(kAbThreads), kAbSmemBytes, static_cast<cudaStream_t>(stream), tmQKV, tmDO, p);
   count_launch();
   return check_launch("attn_bwd_kernel");
 }

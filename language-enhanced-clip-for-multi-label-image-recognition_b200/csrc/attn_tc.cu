@@ -143,6 +143,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync();       // prologue done while the previous kernel drained; no global access before this point
 
   if (warp == 4) {
     // ------------------------------- TMA producer -------------------------------
@@ -404,7 +405,7 @@ static int launch_attn(const CUtensorMap& tm, const AttnParams& p, int grid, cud
     cudaFuncSetAttribute(attn_fwd_kernel<kPoly>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
-  attn_fwd_kernel<kPoly><<<grid, kAtThreads, kAtSmemBytes, stream>>>(tm, p);
+  launch_k(attn_fwd_kernel<kPoly>, dim3(grid), dim3(kAtThreads), kAtSmemBytes, stream, tm, p);
   count_launch();
   return check_launch("attn_fwd_kernel");
 }

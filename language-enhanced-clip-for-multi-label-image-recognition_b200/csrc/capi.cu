@@ -1,6 +1,7 @@
 // C-ABI plumbing: thread-local error slot, launch counter, device queries, TMA descriptor encoders.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -20,6 +21,14 @@ int fail(int status, const char* fmt, ...) {
 }
 
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("LECB_NO_PDL");
+    return !(e != nullptr && e[0] != '\0' && e[0] != '0');
+  }();
+  return on;
+}
 
 int sm_count() {
   static int cached_dev = -1;

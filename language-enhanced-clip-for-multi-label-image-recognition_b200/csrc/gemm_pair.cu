@@ -185,6 +185,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   cluster_sync_all();              // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync();       // prologue done while the previous kernel drained; no global access before this point
 
   if (warp == kPWarpTma) {
     // ------------------------------- TMA producer (both CTAs) -------------------------------
@@ -482,7 +483,7 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   const int tiles = p.num_m_pairs * p.num_n_tiles;
   int clusters = sms / 2;
   if (clusters > tiles) clusters = tiles;
-  kern<<<2 * clusters, kPThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmR, p);
+  launch_k(kern, dim3(2 * clusters), dim3(kPThreads), Cfg::kSmemBytes, stream, tmA, tmB, tmC, tmR, p);
   count_launch();
   return check_launch("gemm_pair_kernel");
 }

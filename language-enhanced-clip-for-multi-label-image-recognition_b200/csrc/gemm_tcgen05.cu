@@ -223,6 +223,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync();       // the prologue above overlapped the previous kernel's tail; no global access before this point
 
   if (warp == kWarpTma) {
     // ------------------------------- TMA producer -------------------------------
@@ -893,8 +894,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
     if (per_m < 1) return fail(LECB_ERR_ARG, "top-10 epilogue: too many row blocks (%d) for %d SMs", p.num_m_tiles, sms);
     grid = per_m * p.num_m_tiles;
   }
-  if (p.mt == 2) gemm_kernel<BN, BK, NB, kConv, kPairable ? 2 : 1><<<grid, kNumThreads, smem_bytes, stream>>>(tmA, tmB, tmC, tmR, p);
-  else kern<<<grid, kNumThreads, smem_bytes, stream>>>(tmA, tmB, tmC, tmR, p);
+  if (p.mt == 2) launch_k(gemm_kernel<BN, BK, NB, kConv, kPairable ? 2 : 1>, dim3(grid), dim3(kNumThreads), smem_bytes, stream, tmA, tmB, tmC, tmR, p);
+  else launch_k(kern, dim3(grid), dim3(kNumThreads), smem_bytes, stream, tmA, tmB, tmC, tmR, p);
   count_launch();
   return check_launch("gemm_kernel");
 }
@@ -1049,6 +1050,7 @@ extern "C" int lecb_gemm_bf16(const void* A, const void* W, const float* bias, c
 //   so slots a CTA never touches for a row block drop out of the merge).
 namespace lecb {
 __global__ void __launch_bounds__(256) topk_partial_fill_kernel(float* __restrict__ v, int* __restrict__ i, int64_t n) {
+  pdl_grid_sync();
   for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     v[t] = -INFINITY;
     i[t] = -1;
@@ -1090,8 +1092,7 @@ extern "C" int lecb_gemm_topk10(const void* A_hilo, const void* bank, int64_t M,
   st = encode_tiled_2d(&tmB, bank, static_cast<uint64_t>(N), static_cast<uint64_t>(K), BN, BK);
   if (st) return st;
   const int64_t nfill = M * slots * 10;
-  topk_partial_fill_kernel<<<static_cast<unsigned>((nfill + 255) / 256 < 1024 ? (nfill + 255) / 256 : 1024), 256, 0,
-                             static_cast<cudaStream_t>(stream)>>>(part_val, part_idx, nfill);
+  launch_k(topk_partial_fill_kernel, dim3(static_cast<unsigned>((nfill + 255) / 256 < 1024 ? (nfill + 255) / 256 : 1024)), dim3(256), 0, static_cast<cudaStream_t>(stream), part_val, part_idx, nfill);
   count_launch();
   st = check_launch("topk_partial_fill_kernel");
   if (st) return st;

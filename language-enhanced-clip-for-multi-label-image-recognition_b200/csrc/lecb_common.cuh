@@ -15,6 +15,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 // ------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL).  Every kernel of the library is launched with the programmatic-stream-
+// serialization attribute (lecb_host.h: launch_k), so its CTAs may be scheduled while the previous kernel of the stream
+// is still draining: everything before pdl_grid_sync() (barrier init, TMEM allocation, descriptor prefetch) overlaps that
+// tail.  griddepcontrol.wait returns once every prerequisite grid has completed and its memory is visible — no global
+// memory may be read OR written before it (the previous kernel may still be reading what this one overwrites);
+// launch_dependents then lets the NEXT kernel's CTAs start their own prologue as soon as resources free up.  Both are
+// no-ops for a launch without the attribute.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

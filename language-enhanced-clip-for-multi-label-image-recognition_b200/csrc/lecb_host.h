@@ -13,6 +13,25 @@ void count_launch(unsigned n = 1);
 int sm_count();                                       // SMs of the current device (cached per device)
 int check_launch(const char* what);                   // cudaGetLastError -> status
 
+// Every kernel launch of the library: cudaLaunchKernelEx with the programmatic-stream-serialization attribute (PDL), so the
+// kernel's prologue overlaps the tail of the previous kernel in the stream (each kernel calls pdl_grid_sync() before it
+// touches global memory: lecb_common.cuh).  LECB_NO_PDL=1 (read once) launches without the attribute.
+bool pdl_enabled();
+template <typename... P, typename... A>
+inline void launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kern, static_cast<A&&>(args)...);      // errors surface through check_launch()
+}
+
 // cudaFuncSetAttribute is a per-DEVICE setting: a `static DeviceOnce once; bool& done = once.flag();` at the call site keeps
 // one "configured" flag per device ordinal (a process that drives several GPUs configures each of them once).  A race
 // between host threads only repeats the idempotent attribute call.

@@ -53,6 +53,7 @@ template <bool kFastGamma>
 __global__ void __launch_bounds__(256)
 asl_fwd_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ grad,
                    float* __restrict__ loss_out, int64_t n, AslParams p) {
+  pdl_grid_sync();
   float acc = 0.f;
   const int64_t nvec = n / 4;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(kRankWarps * 32)
 ranking_fwd_bwd_kernel(const float* __restrict__ ypred, const float* __restrict__ ytrue, const float* __restrict__ wt,
                        float* __restrict__ grad, float* __restrict__ loss_out, int64_t B, int K, float scale, float margin,
                        float inv_batch) {
+  pdl_grid_sync();
   extern __shared__ float sm[];                  // per warp: [K] scaled score of list entry, [K] its target, [K] its column;
                                                  // then (co-occurrence, K <= kRankSmemWtK) the pair weights, transposed
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -279,6 +281,7 @@ template <int CH>
 __global__ void __launch_bounds__(kRankWarps * 32)
 kl_softmax_fwd_bwd_kernel(const float* __restrict__ x, const float* __restrict__ xm, float* __restrict__ grad,
                           float* __restrict__ loss_out, int64_t B, int K, float weight, float inv_batch) {
+  pdl_grid_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float acc = 0.f;
   const int64_t row_step = static_cast<int64_t>(gridDim.x) * kRankWarps;
@@ -372,6 +375,7 @@ __global__ void __launch_bounds__(kRankWarps * 32)
 resample_bce_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ freq_inv,
                     const float* __restrict__ init_bias, float* __restrict__ grad, float* __restrict__ loss_out,
                     float* __restrict__ sums, int64_t B, int K, ResampleParams p) {
+  pdl_grid_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float acc0 = 0.f, accw = 0.f;
   float c_w = p.loss_weight, c_0 = 0.f;          // gradient coefficients of the weighted / unweighted mean
@@ -456,9 +460,9 @@ static int launch_resample(const float* x, const float* y, const float* freq_inv
   if (blocks > cap) blocks = cap;
   const int chunks = (K + 31) / 32;
   if (chunks <= 3)
-    resample_bce_kernel<3, kMode><<<static_cast<unsigned>(blocks), kRankWarps * 32, 0, s>>>(x, y, freq_inv, init_bias, grad, loss, sums, B, K, p);
+    launch_k(resample_bce_kernel<3, kMode>, dim3(static_cast<unsigned>(blocks)), dim3(kRankWarps * 32), 0, s, x, y, freq_inv, init_bias, grad, loss, sums, B, K, p);
   else
-    resample_bce_kernel<8, kMode><<<static_cast<unsigned>(blocks), kRankWarps * 32, 0, s>>>(x, y, freq_inv, init_bias, grad, loss, sums, B, K, p);
+    launch_k(resample_bce_kernel<8, kMode>, dim3(static_cast<unsigned>(blocks)), dim3(kRankWarps * 32), 0, s, x, y, freq_inv, init_bias, grad, loss, sums, B, K, p);
   count_launch();
   return check_launch("resample_bce_kernel");
 }
@@ -474,7 +478,7 @@ static int launch_ranking(const float* logits, const float* targets, const float
   if (blocks > cap) blocks = cap;
   const float inv_b = 1.0f / static_cast<float>(B);
 #define LECB_RANK_CASE(CH)                                                                                        \
-  ranking_fwd_bwd_kernel<CH, kCooc><<<static_cast<unsigned>(blocks), kRankWarps * 32, smem, s>>>(logits, targets, wt, grad, \
+  launch_k(ranking_fwd_bwd_kernel<CH, kCooc>, dim3(static_cast<unsigned>(blocks)), dim3(kRankWarps * 32), smem, s, logits, targets, wt, grad, \
                                                                                                 loss, B, K, scale, margin, inv_b)
   if (chunks <= 1) LECB_RANK_CASE(1);
   else if (chunks <= 2) LECB_RANK_CASE(2);
@@ -507,9 +511,9 @@ extern "C" int lecb_asl_fwd_bwd(const float* logits, const float* targets, float
   if (blocks < 1) blocks = 1;
   if (blocks > cap) blocks = cap;
   if (gamma_pos == 1.0f && gamma_neg == 2.0f)
-    asl_fwd_bwd_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, s>>>(logits, targets, grad, loss, n, p);
+    launch_k(asl_fwd_bwd_kernel<true>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s, logits, targets, grad, loss, n, p);
   else
-    asl_fwd_bwd_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, s>>>(logits, targets, grad, loss, n, p);
+    launch_k(asl_fwd_bwd_kernel<false>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s, logits, targets, grad, loss, n, p);
   count_launch();
   return check_launch("asl_fwd_bwd_kernel");
 }
@@ -547,9 +551,9 @@ extern "C" int lecb_kl_softmax_fwd_bwd(const float* logits, const float* logits_
   const float inv_b = 1.0f / static_cast<float>(B);
   const int chunks = (K + 31) / 32;
   if (chunks <= 3)
-    kl_softmax_fwd_bwd_kernel<3><<<static_cast<unsigned>(blocks), kRankWarps * 32, 0, s>>>(logits, logits_target, grad, loss, B, K, weight, inv_b);
+    launch_k(kl_softmax_fwd_bwd_kernel<3>, dim3(static_cast<unsigned>(blocks)), dim3(kRankWarps * 32), 0, s, logits, logits_target, grad, loss, B, K, weight, inv_b);
   else
-    kl_softmax_fwd_bwd_kernel<8><<<static_cast<unsigned>(blocks), kRankWarps * 32, 0, s>>>(logits, logits_target, grad, loss, B, K, weight, inv_b);
+    launch_k(kl_softmax_fwd_bwd_kernel<8>, dim3(static_cast<unsigned>(blocks)), dim3(kRankWarps * 32), 0, s, logits, logits_target, grad, loss, B, K, weight, inv_b);
   count_launch();
   return check_launch("kl_softmax_fwd_bwd_kernel");
 }

@@ -26,6 +26,7 @@ struct TensorList {
 
 // blockIdx.y = tensor, blockIdx.x strides over its elements
 __global__ void __launch_bounds__(256) ema_update_kernel(const TensorList tl, float momentum, float one_minus) {
+  pdl_grid_sync();
   const int t = blockIdx.y;
   const float* __restrict__ live = tl.src[t];
   float* __restrict__ twin = tl.dst[t];
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(256) ema_update_kernel(const TensorList tl, fl
 }
 
 __global__ void __launch_bounds__(256) pack_kernel(const TensorList tl, float* __restrict__ flat) {
+  pdl_grid_sync();
   const int t = blockIdx.y;
   const float* __restrict__ src = tl.src[t];
   const long long n = tl.n[t], off = tl.off[t];
@@ -45,6 +47,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const TensorList tl, float* _
 }
 
 __global__ void __launch_bounds__(256) unpack_scale_kernel(const TensorList tl, const float* __restrict__ flat, float scale) {
+  pdl_grid_sync();
   const int t = blockIdx.y;
   float* __restrict__ dst = tl.dst[t];
   const long long n = tl.n[t], off = tl.off[t];
@@ -56,6 +59,7 @@ __global__ void __launch_bounds__(256) unpack_scale_kernel(const TensorList tl, 
 // zero, which reproduces torch's first step (buf <- g) without a step counter — so the launch is CUDA-graph replayable.
 __global__ void __launch_bounds__(256)
 sgd_step_kernel(const TensorList tl, const float* __restrict__ flat, float grad_scale, float lr, float momentum, float weight_decay) {
+  pdl_grid_sync();
   const int t = blockIdx.y;
   float* __restrict__ p = tl.dst[t];
   float* __restrict__ buf = tl.aux[t];
@@ -112,7 +116,7 @@ extern "C" int lecb_ema_update(const float* const* live, float* const* twin, con
   int st = fill_list(tl, live, twin, nullptr, n, count, "lecb_ema_update", &mx);
   if (st) return st;
   for (int i = 0; i < count; ++i) LECB_CHECK_ARG(tl.src[i] && tl.dst[i], "lecb_ema_update: tensor %d is null", i);
-  ema_update_kernel<<<list_grid(mx, count), 256, 0, static_cast<cudaStream_t>(stream)>>>(tl, momentum, one_minus_momentum);
+  launch_k(ema_update_kernel, dim3(list_grid(mx, count)), dim3(256), 0, static_cast<cudaStream_t>(stream), tl, momentum, one_minus_momentum);
   count_launch();
   return check_launch("ema_update_kernel");
 }
@@ -123,7 +127,7 @@ extern "C" int lecb_pack_f32(const float* const* src, const long long* n, int co
   long long mx = 0;
   int st = fill_list(tl, src, nullptr, nullptr, n, count, "lecb_pack_f32", &mx);
   if (st) return st;
-  pack_kernel<<<list_grid(mx, count), 256, 0, static_cast<cudaStream_t>(stream)>>>(tl, flat);
+  launch_k(pack_kernel, dim3(list_grid(mx, count)), dim3(256), 0, static_cast<cudaStream_t>(stream), tl, flat);
   count_launch();
   return check_launch("pack_kernel");
 }
@@ -136,7 +140,7 @@ extern "C" int lecb_unpack_scale_f32(const float* flat, float* const* dst, const
   int st = fill_list(tl, nullptr, dst, nullptr, n, count, "lecb_unpack_scale_f32", &mx);
   if (st) return st;
   for (int i = 0; i < count; ++i) LECB_CHECK_ARG(tl.dst[i], "lecb_unpack_scale_f32: tensor %d is null", i);
-  unpack_scale_kernel<<<list_grid(mx, count), 256, 0, static_cast<cudaStream_t>(stream)>>>(tl, flat, scale);
+  launch_k(unpack_scale_kernel, dim3(list_grid(mx, count)), dim3(256), 0, static_cast<cudaStream_t>(stream), tl, flat, scale);
   count_launch();
   return check_launch("unpack_scale_kernel");
 }
@@ -151,7 +155,7 @@ extern "C" int lecb_sgd_step(const float* flat_grad, float* const* params, float
   if (st) return st;
   for (int i = 0; i < count; ++i)
     LECB_CHECK_ARG(tl.dst[i] && (momentum == 0.f || tl.aux[i]), "lecb_sgd_step: tensor %d is null", i);
-  sgd_step_kernel<<<list_grid(mx, count), 256, 0, static_cast<cudaStream_t>(stream)>>>(tl, flat_grad, grad_scale, lr, momentum,
+  launch_k(sgd_step_kernel, dim3(list_grid(mx, count)), dim3(256), 0, static_cast<cudaStream_t>(stream), tl, flat_grad, grad_scale, lr, momentum,
                                                                                       weight_decay);
   count_launch();
   return check_launch("sgd_step_kernel");

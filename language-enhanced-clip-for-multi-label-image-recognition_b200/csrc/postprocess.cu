@@ -16,6 +16,7 @@ constexpr int kFuseMaxK = 128;
 __global__ void __launch_bounds__(kFuseWarps * 32)
 block_fuse_kernel(const float* __restrict__ data, const float* __restrict__ sims, int sims_ld, const float* __restrict__ base,
                   float* __restrict__ out, int NB, int K, int mode, float threshold, float weight) {
+  pdl_grid_sync();
   __shared__ float s_max[kFuseWarps][kFuseMaxK];
   __shared__ float s_min[kFuseWarps][kFuseMaxK];
   const int b = blockIdx.x;
@@ -93,6 +94,7 @@ block_fuse_kernel(const float* __restrict__ data, const float* __restrict__ sims
 // out[b,:] = pred[b,:] + w * pred[b,:] @ P   (P [K,K] row-major).  One CTA per image, pred row in smem.
 __global__ void __launch_bounds__(128)
 cooc_adjust_kernel(const float* __restrict__ pred, const float* __restrict__ P, float* __restrict__ out, int K, float w) {
+  pdl_grid_sync();
   __shared__ float sp[kFuseMaxK];
   const int b = blockIdx.x;
   for (int k = threadIdx.x; k < K; k += blockDim.x) sp[k] = pred[static_cast<int64_t>(b) * K + k];
@@ -114,7 +116,7 @@ extern "C" int lecb_block_fuse(const float* data, const float* sims, int sims_ld
   LECB_CHECK_ARG(B > 0 && NB > 0 && K > 1 && K <= kFuseMaxK, "lecb_block_fuse: need B, NB > 0 and 1 < K <= 128 (K=%d)", K);
   LECB_CHECK_ARG(mode >= 0 && mode <= 2, "lecb_block_fuse: mode must be 0 (plain), 1 (fuse) or 2 (fuse6)");
   LECB_CHECK_ARG(mode == 0 || (sims != nullptr && sims_ld > 0), "lecb_block_fuse: modes 1 and 2 need the similarity scores");
-  block_fuse_kernel<<<B, kFuseWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(data, sims, sims_ld, base, out, NB, K, mode,
+  launch_k(block_fuse_kernel, dim3(B), dim3(kFuseWarps * 32), 0, static_cast<cudaStream_t>(stream), data, sims, sims_ld, base, out, NB, K, mode,
                                                                                 threshold, weight);
   count_launch();
   return check_launch("block_fuse_kernel");
@@ -123,7 +125,7 @@ extern "C" int lecb_block_fuse(const float* data, const float* sims, int sims_ld
 extern "C" int lecb_cooc_adjust(const float* pred, const float* P, float* out, int B, int K, float weight, void* stream) {
   LECB_CHECK_ARG(pred && P && out, "lecb_cooc_adjust: null pointer");
   LECB_CHECK_ARG(B > 0 && K > 0 && K <= kFuseMaxK, "lecb_cooc_adjust: need 0 < K <= 128 (K=%d)", K);
-  cooc_adjust_kernel<<<B, 128, 0, static_cast<cudaStream_t>(stream)>>>(pred, P, out, K, weight);
+  launch_k(cooc_adjust_kernel, dim3(B), dim3(128), 0, static_cast<cudaStream_t>(stream), pred, P, out, K, weight);
   count_launch();
   return check_launch("cooc_adjust_kernel");
 }

@@ -9,6 +9,7 @@ namespace lecb {
 
 __global__ void __launch_bounds__(256)
 split_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int64_t n) {
+  pdl_grid_sync();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float v = x[i];
@@ -38,6 +39,7 @@ __device__ __forceinline__ void topk_insert(float (&val)[kTopK], int (&idx)[kTop
 __global__ void __launch_bounds__(256)
 topk10_kernel(const float* __restrict__ sim, int64_t ld, int N, float* __restrict__ out_val,
               int* __restrict__ out_idx) {
+  pdl_grid_sync();
   __shared__ float s_val[256 * kTopK];
   __shared__ int s_idx[256 * kTopK];
   __shared__ float r_val[8];
@@ -100,6 +102,7 @@ topk10_kernel(const float* __restrict__ sim, int64_t ld, int N, float* __restric
 __global__ void __launch_bounds__(256)
 topk10_merge_kernel(const float* __restrict__ part_val, const int* __restrict__ part_idx, int slots, float* __restrict__ out_val,
                     int* __restrict__ out_idx) {
+  pdl_grid_sync();
   extern __shared__ uint8_t sm_raw[];
   const int b = blockIdx.x, t = threadIdx.x;
   const int n = slots * kTopK;
@@ -167,6 +170,7 @@ topk10_merge_kernel(const float* __restrict__ part_val, const int* __restrict__ 
 template <typename TBank>
 __global__ void __launch_bounds__(256)
 gather_mean_kernel(const TBank* __restrict__ bank, const int* __restrict__ idx, float* __restrict__ out, int D) {
+  pdl_grid_sync();
   const int b = blockIdx.x;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float s = 0.f;
@@ -189,6 +193,7 @@ using namespace lecb;
 // [rows, 2D] = [hi | lo]: the A operand of lecb_gemm_topk10
 __global__ void __launch_bounds__(256)
 split_f16_hilo_kernel(const float* __restrict__ x, __half* __restrict__ out, int64_t rows, int D) {
+  pdl_grid_sync();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= rows * D) return;
   const int64_t r = i / D;
@@ -202,7 +207,7 @@ split_f16_hilo_kernel(const float* __restrict__ x, __half* __restrict__ out, int
 extern "C" int lecb_split_f16_hilo(const float* x, void* out, int64_t rows, int D, void* stream) {
   LECB_CHECK_ARG(x && out && rows > 0 && D > 0, "lecb_split_f16_hilo: bad argument");
   const int64_t n = rows * D;
-  split_f16_hilo_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(split_f16_hilo_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       x, static_cast<__half*>(out), rows, D);
   count_launch();
   return check_launch("split_f16_hilo_kernel");
@@ -210,7 +215,7 @@ extern "C" int lecb_split_f16_hilo(const float* x, void* out, int64_t rows, int 
 
 extern "C" int lecb_split_f16(const float* x, void* hi, void* lo, int64_t n, void* stream) {
   LECB_CHECK_ARG(x && hi && lo && n > 0, "lecb_split_f16: bad argument");
-  split_f16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(split_f16_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       x, static_cast<__half*>(hi), static_cast<__half*>(lo), n);
   count_launch();
   return check_launch("split_f16_kernel");
@@ -219,7 +224,7 @@ extern "C" int lecb_split_f16(const float* x, void* hi, void* lo, int64_t n, voi
 extern "C" int lecb_topk10(const float* sim, int64_t ld, int B, int N, float* out_val, int* out_idx, void* stream) {
   LECB_CHECK_ARG(sim && out_val && out_idx, "lecb_topk10: null pointer");
   LECB_CHECK_ARG(B > 0 && N >= kTopK && ld >= N, "lecb_topk10: need N >= 10 and ld >= N (N=%d)", N);
-  topk10_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(sim, ld, N, out_val, out_idx);
+  launch_k(topk10_kernel, dim3(B), dim3(256), 0, static_cast<cudaStream_t>(stream), sim, ld, N, out_val, out_idx);
   count_launch();
   return check_launch("topk10_kernel");
 }
@@ -239,7 +244,7 @@ extern "C" int lecb_topk10_merge(const float* part_val, const int* part_idx, int
       big_smem[dev] = true;
     }
   }
-  topk10_merge_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(part_val, part_idx, slots, out_val, out_idx);
+  launch_k(topk10_merge_kernel, dim3(B), dim3(256), smem, static_cast<cudaStream_t>(stream), part_val, part_idx, slots, out_val, out_idx);
   count_launch();
   return check_launch("topk10_merge_kernel");
 }
@@ -248,8 +253,8 @@ extern "C" int lecb_gather_mean10(const void* bank, int bank_is_f16, const int* 
                                   void* stream) {
   LECB_CHECK_ARG(bank && idx && out && B > 0 && D > 0, "lecb_gather_mean10: bad argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (bank_is_f16) gather_mean_kernel<__half><<<B, 256, 0, s>>>(static_cast<const __half*>(bank), idx, out, D);
-  else gather_mean_kernel<float><<<B, 256, 0, s>>>(static_cast<const float*>(bank), idx, out, D);
+  if (bank_is_f16) launch_k(gather_mean_kernel<__half>, dim3(B), dim3(256), 0, s, static_cast<const __half*>(bank), idx, out, D);
+  else launch_k(gather_mean_kernel<float>, dim3(B), dim3(256), 0, s, static_cast<const float*>(bank), idx, out, D);
   count_launch();
   return check_launch("gather_mean_kernel");
 }

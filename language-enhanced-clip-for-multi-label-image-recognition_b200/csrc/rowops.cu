@@ -18,6 +18,7 @@ template <int CO>
 __global__ void __launch_bounds__(128) stem_conv1_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias,
                                                          __nv_bfloat16* __restrict__ out, int B, int H, int W) {
+  pdl_grid_sync();
   // One thread = TWO horizontally adjacent output pixels x CO channels: the 5x3x3 input patch is shared and
   // every 128-bit weight broadcast from shared memory feeds 8 FMAs (the kernel is FMA-issue bound).
   __shared__ __align__(16) float sw[27 * CO];   // [tap(ci,ky,kx)][co]
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(128) stem_conv1_kernel(const float* __restrict
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) avgpool2_kernel(const __nv_bfloat16* __restrict__ x,
                                                        __nv_bfloat16* __restrict__ out, int B, int H, int W, int C) {
+  pdl_grid_sync();
   const int HO = H / 2, WO = W / 2, CV = C / 8;
   const int64_t total = static_cast<int64_t>(B) * HO * WO * CV;
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
@@ -126,6 +128,7 @@ __global__ void __launch_bounds__(256) avgpool2_kernel(const __nv_bfloat16* __re
 __global__ void __launch_bounds__(128) token_mean_kernel(const __nv_bfloat16* __restrict__ x,
                                                          __nv_bfloat16* __restrict__ out_bf16,
                                                          float* __restrict__ out_f32, int P, int C) {
+  pdl_grid_sync();
   const int b = blockIdx.y;
   const int c2 = blockIdx.x * blockDim.x + threadIdx.x;   // pair of channels
   if (c2 * 2 >= C) return;
@@ -153,6 +156,7 @@ __global__ void __launch_bounds__(128) token_mean_kernel(const __nv_bfloat16* __
 template <typename TIn, typename TOut, int kVecPerLane>
 __global__ void __launch_bounds__(256) l2norm_kernel(const TIn* __restrict__ x, TOut* __restrict__ y, int64_t rows,
                                                      int D) {
+  pdl_grid_sync();
   constexpr int kElemsPerVec = 16 / sizeof(TIn);
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -213,6 +217,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
                                                             float* __restrict__ y_f32, float* __restrict__ mean_out,
                                                             float* __restrict__ rstd_out, int64_t rows, int D,
                                                             float eps) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -285,11 +290,11 @@ extern "C" int lecb_stem_conv1(const float* x, const float* w, const float* bias
   if (Cout == 32 && !cuda_core_stem)      // the real CLIP ResNets (width 64): tensor-core implicit GEMM
     return launch_stem_conv1_tc(x, 0, w, bias, nullptr, nullptr, out, B, H, W, s);
   if (Cout == 32)
-    stem_conv1_kernel<32><<<grid, 128, 0, s>>>(x, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W);
+    launch_k(stem_conv1_kernel<32>, dim3(grid), dim3(128), 0, s, x, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W);
   else if (Cout == 48)
-    stem_conv1_kernel<48><<<grid, 128, 0, s>>>(x, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W);
+    launch_k(stem_conv1_kernel<48>, dim3(grid), dim3(128), 0, s, x, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W);
   else if (Cout == 8)
-    stem_conv1_kernel<8><<<grid, 128, 0, s>>>(x, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W);
+    launch_k(stem_conv1_kernel<8>, dim3(grid), dim3(128), 0, s, x, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W);
   else
     return fail(LECB_ERR_UNSUPPORTED, "lecb_stem_conv1: Cout=%d (supported: 8, 32, 48)", Cout);
   count_launch();
@@ -311,7 +316,7 @@ extern "C" int lecb_avgpool2x2(const void* x, void* out, int B, int H, int W, in
   LECB_CHECK_ARG(B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0,
                  "lecb_avgpool2x2: need even H, W and C %% 8 == 0 (H=%d W=%d C=%d)", H, W, C);
   const int64_t total = static_cast<int64_t>(B) * (H / 2) * (W / 2) * (C / 8);
-  avgpool2_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(avgpool2_kernel, dim3(grid_for(total, 256, 16)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), B, H, W, C);
   count_launch();
   return check_launch("avgpool2_kernel");
@@ -321,7 +326,7 @@ extern "C" int lecb_token_mean(const void* x, void* out_bf16, float* out_f32, in
   LECB_CHECK_ARG(x && (out_bf16 || out_f32), "lecb_token_mean: null pointer");
   LECB_CHECK_ARG(B > 0 && P > 0 && C > 0 && C % 2 == 0, "lecb_token_mean: bad shape");
   dim3 grid((C / 2 + 127) / 128, B);
-  token_mean_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(token_mean_kernel, dim3(grid), dim3(128), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out_bf16), out_f32, P, C);
   count_launch();
   return check_launch("token_mean_kernel");
@@ -335,10 +340,10 @@ static int launch_l2norm(const void* x, void* y, int64_t rows, int D, cudaStream
   const int grid = grid_for(rows, 8, 16);
   const TIn* xi = static_cast<const TIn*>(x);
   TOut* yo = static_cast<TOut*>(y);
-  if (per_lane <= 1) l2norm_kernel<TIn, TOut, 1><<<grid, 256, 0, s>>>(xi, yo, rows, D);
-  else if (per_lane <= 2) l2norm_kernel<TIn, TOut, 2><<<grid, 256, 0, s>>>(xi, yo, rows, D);
-  else if (per_lane <= 4) l2norm_kernel<TIn, TOut, 4><<<grid, 256, 0, s>>>(xi, yo, rows, D);
-  else if (per_lane <= 8) l2norm_kernel<TIn, TOut, 8><<<grid, 256, 0, s>>>(xi, yo, rows, D);
+  if (per_lane <= 1) launch_k(l2norm_kernel<TIn, TOut, 1>, dim3(grid), dim3(256), 0, s, xi, yo, rows, D);
+  else if (per_lane <= 2) launch_k(l2norm_kernel<TIn, TOut, 2>, dim3(grid), dim3(256), 0, s, xi, yo, rows, D);
+  else if (per_lane <= 4) launch_k(l2norm_kernel<TIn, TOut, 4>, dim3(grid), dim3(256), 0, s, xi, yo, rows, D);
+  else if (per_lane <= 8) launch_k(l2norm_kernel<TIn, TOut, 8>, dim3(grid), dim3(256), 0, s, xi, yo, rows, D);
   else return fail(LECB_ERR_UNSUPPORTED, "lecb_l2norm_rows: D=%d too wide", D);
   count_launch();
   return check_launch("l2norm_kernel");
@@ -363,9 +368,9 @@ extern "C" int lecb_layernorm_fwd(const float* x, const float* gamma, const floa
   const int grid = grid_for(rows, 8, 16);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* yb = static_cast<__nv_bfloat16*>(y_bf16);
-  if (per_lane <= 2) layernorm_fwd_kernel<2><<<grid, 256, 0, s>>>(x, gamma, beta, yb, y_f32, mean, rstd, rows, D, eps);
-  else if (per_lane <= 4) layernorm_fwd_kernel<4><<<grid, 256, 0, s>>>(x, gamma, beta, yb, y_f32, mean, rstd, rows, D, eps);
-  else if (per_lane <= 8) layernorm_fwd_kernel<8><<<grid, 256, 0, s>>>(x, gamma, beta, yb, y_f32, mean, rstd, rows, D, eps);
+  if (per_lane <= 2) launch_k(layernorm_fwd_kernel<2>, dim3(grid), dim3(256), 0, s, x, gamma, beta, yb, y_f32, mean, rstd, rows, D, eps);
+  else if (per_lane <= 4) launch_k(layernorm_fwd_kernel<4>, dim3(grid), dim3(256), 0, s, x, gamma, beta, yb, y_f32, mean, rstd, rows, D, eps);
+  else if (per_lane <= 8) launch_k(layernorm_fwd_kernel<8>, dim3(grid), dim3(256), 0, s, x, gamma, beta, yb, y_f32, mean, rstd, rows, D, eps);
   else return fail(LECB_ERR_UNSUPPORTED, "lecb_layernorm_fwd: D=%d too wide", D);
   count_launch();
   return check_launch("layernorm_fwd_kernel");

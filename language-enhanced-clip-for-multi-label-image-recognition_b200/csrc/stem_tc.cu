@@ -78,6 +78,9 @@ stem_conv1_tc_kernel(const void* __restrict__ xin, const float* __restrict__ w27
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  // the prologue read only the layer's own constants (packed weights, bias: written at engine construction, many kernels
+  // ago); the pixels may come from the previous kernel (crop + resize) and `out` may still be read by it
+  pdl_grid_sync();
   const uint32_t idesc = make_idesc_f16(kStemCo, true);
   uint32_t phase = 0;
   const int py = t / kTileW, px = t % kTileW;
@@ -298,10 +301,10 @@ int launch_stem_conv1_tc(const void* x, int x_is_u8, const float* w, const float
     nrm.std[c] = stdv ? stdv[c] : 1.f;
   }
   if (x_is_u8)
-    stem_conv1_tc_kernel<true><<<grid, 128, 0, s>>>(x, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W, tiles_x, tiles_y,
+    launch_k(stem_conv1_tc_kernel<true>, dim3(grid), dim3(128), 0, s, x, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W, tiles_x, tiles_y,
                                                     static_cast<int>(tiles), nrm);
   else
-    stem_conv1_tc_kernel<false><<<grid, 128, 0, s>>>(x, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W, tiles_x, tiles_y,
+    launch_k(stem_conv1_tc_kernel<false>, dim3(grid), dim3(128), 0, s, x, w, bias, static_cast<__nv_bfloat16*>(out), B, H, W, tiles_x, tiles_y,
                                                      static_cast<int>(tiles), nrm);
   count_launch();
   return check_launch("stem_conv1_tc_kernel");

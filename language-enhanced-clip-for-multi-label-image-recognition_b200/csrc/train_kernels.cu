@@ -22,6 +22,7 @@ __device__ __forceinline__ float qgelu_grad(float v) {
 
 __global__ void __launch_bounds__(256)
 quick_gelu_fwd_kernel(const uint4* __restrict__ v, uint4* __restrict__ u, int64_t nvec) {
+  pdl_grid_sync();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const uint4 a = __ldg(v + i);
@@ -40,6 +41,7 @@ quick_gelu_fwd_kernel(const uint4* __restrict__ v, uint4* __restrict__ u, int64_
 // dv = du * f'(v), all bf16
 __global__ void __launch_bounds__(256)
 quick_gelu_bwd_kernel(const uint4* __restrict__ du, const uint4* __restrict__ v, uint4* __restrict__ dv, int64_t nvec) {
+  pdl_grid_sync();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const uint4 g = __ldg(du + i), a = __ldg(v + i);
@@ -65,6 +67,7 @@ __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dx_in,
                      float* __restrict__ dx_f32, __nv_bfloat16* __restrict__ dx_bf16, int64_t rows, int D) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -120,6 +123,7 @@ constexpr int kPitch = kDh + 2;
 __global__ void __launch_bounds__(256)
 causal_attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                        __nv_bfloat16* __restrict__ dqkv, int L, int W, float scale) {
+  pdl_grid_sync();
   extern __shared__ uint8_t smem_raw[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);
   __nv_bfloat16* sK = sQ + kLMaxB * kPitch;
@@ -242,6 +246,7 @@ causal_attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat1
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 l2norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int64_t rows, int D) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
@@ -272,6 +277,7 @@ head_aggregate_bwd_kernel(const float* __restrict__ dots, int ldn, const float* 
                           const uint8_t* __restrict__ row_mask, const float* __restrict__ grad_local,
                           float* __restrict__ d_dots, int B, int P, int K, int n_txt, float logit_scale,
                           float spatial_scale) {
+  pdl_grid_sync();
   __shared__ float s_m[kAggWarps][kJ * 32];
   __shared__ float s_s[kAggWarps][kJ * 32];
   __shared__ float s_a[kAggWarps][kJ * 32];
@@ -467,6 +473,7 @@ template <typename TB>
 __global__ void __launch_bounds__(256)
 tn_gemm_small_kernel(const float* __restrict__ a, int lda, const TB* __restrict__ b, float* __restrict__ out, int R,
                      int J, int D, float alpha, int accumulate, int a_vec, int b_vec) {
+  pdl_grid_sync();
   constexpr bool kBf16 = sizeof(TB) == 2;
   constexpr int kBPer = kBf16 ? 2 : 4;           // 16-byte vectors of b per thread and chunk (64 x 64 elements)
   constexpr int kBElems = kBf16 ? 8 : 4;         // elements per vector
@@ -580,6 +587,7 @@ using namespace lecb;
 namespace lecb {
 __global__ void __launch_bounds__(256)
 residual_relu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ z, float* __restrict__ out, int64_t n) {
+  pdl_grid_sync();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
     out[i] = x[i] + fmaxf(z[i], 0.f);
 }
@@ -587,6 +595,7 @@ residual_relu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ 
 template <typename TZ>
 __global__ void __launch_bounds__(256)
 relu_bwd_kernel(const float* __restrict__ dy, const TZ* __restrict__ z, __nv_bfloat16* __restrict__ dz, int64_t n) {
+  pdl_grid_sync();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     float zi;
     if constexpr (sizeof(TZ) == 2) zi = __bfloat162float(z[i]);
@@ -598,7 +607,7 @@ relu_bwd_kernel(const float* __restrict__ dy, const TZ* __restrict__ z, __nv_bfl
 
 extern "C" int lecb_residual_relu_fwd(const float* x, const float* z, float* out, int64_t n, void* stream) {
   LECB_CHECK_ARG(x && z && out && n > 0, "lecb_residual_relu_fwd: bad argument");
-  lecb::residual_relu_fwd_kernel<<<ew_grid((n + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, z, out, n);
+  launch_k(lecb::residual_relu_fwd_kernel, dim3(ew_grid((n + 7) / 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, z, out, n);
   count_launch();
   return check_launch("residual_relu_fwd_kernel");
 }
@@ -607,17 +616,17 @@ extern "C" int lecb_relu_bwd(const float* dy, const void* z, int z_is_bf16, void
   LECB_CHECK_ARG(dy && z && dz_bf16 && n > 0, "lecb_relu_bwd: bad argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (z_is_bf16)
-    lecb::relu_bwd_kernel<__nv_bfloat16><<<ew_grid((n + 7) / 8), 256, 0, s>>>(dy, static_cast<const __nv_bfloat16*>(z),
+    launch_k(lecb::relu_bwd_kernel<__nv_bfloat16>, dim3(ew_grid((n + 7) / 8)), dim3(256), 0, s, dy, static_cast<const __nv_bfloat16*>(z),
                                                                              static_cast<__nv_bfloat16*>(dz_bf16), n);
   else
-    lecb::relu_bwd_kernel<float><<<ew_grid((n + 7) / 8), 256, 0, s>>>(dy, static_cast<const float*>(z), static_cast<__nv_bfloat16*>(dz_bf16), n);
+    launch_k(lecb::relu_bwd_kernel<float>, dim3(ew_grid((n + 7) / 8)), dim3(256), 0, s, dy, static_cast<const float*>(z), static_cast<__nv_bfloat16*>(dz_bf16), n);
   count_launch();
   return check_launch("relu_bwd_kernel");
 }
 
 extern "C" int lecb_quick_gelu_fwd(const void* v, void* u, int64_t n, void* stream) {
   LECB_CHECK_ARG(v && u && n > 0 && n % 8 == 0, "lecb_quick_gelu_fwd: need n %% 8 == 0");
-  quick_gelu_fwd_kernel<<<ew_grid(n / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(quick_gelu_fwd_kernel, dim3(ew_grid(n / 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const uint4*>(v), static_cast<uint4*>(u), n / 8);
   count_launch();
   return check_launch("quick_gelu_fwd_kernel");
@@ -625,7 +634,7 @@ extern "C" int lecb_quick_gelu_fwd(const void* v, void* u, int64_t n, void* stre
 
 extern "C" int lecb_quick_gelu_bwd(const void* du, const void* v, void* dv, int64_t n, void* stream) {
   LECB_CHECK_ARG(du && v && dv && n > 0 && n % 8 == 0, "lecb_quick_gelu_bwd: need n %% 8 == 0");
-  quick_gelu_bwd_kernel<<<ew_grid(n / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(quick_gelu_bwd_kernel, dim3(ew_grid(n / 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const uint4*>(du), static_cast<const uint4*>(v), static_cast<uint4*>(dv), n / 8);
   count_launch();
   return check_launch("quick_gelu_bwd_kernel");
@@ -642,9 +651,9 @@ extern "C" int lecb_layernorm_bwd(const float* dy, const float* x, const float* 
   const int grid = static_cast<int>(blocks > cap ? cap : blocks);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* db = static_cast<__nv_bfloat16*>(dx_bf16);
-  if (per_lane <= 2) layernorm_bwd_kernel<2><<<grid, 256, 0, s>>>(dy, x, gamma, mean, rstd, dx_in, dx_f32, db, rows, D);
-  else if (per_lane <= 4) layernorm_bwd_kernel<4><<<grid, 256, 0, s>>>(dy, x, gamma, mean, rstd, dx_in, dx_f32, db, rows, D);
-  else if (per_lane <= 8) layernorm_bwd_kernel<8><<<grid, 256, 0, s>>>(dy, x, gamma, mean, rstd, dx_in, dx_f32, db, rows, D);
+  if (per_lane <= 2) launch_k(layernorm_bwd_kernel<2>, dim3(grid), dim3(256), 0, s, dy, x, gamma, mean, rstd, dx_in, dx_f32, db, rows, D);
+  else if (per_lane <= 4) launch_k(layernorm_bwd_kernel<4>, dim3(grid), dim3(256), 0, s, dy, x, gamma, mean, rstd, dx_in, dx_f32, db, rows, D);
+  else if (per_lane <= 8) launch_k(layernorm_bwd_kernel<8>, dim3(grid), dim3(256), 0, s, dy, x, gamma, mean, rstd, dx_in, dx_f32, db, rows, D);
   else return fail(LECB_ERR_UNSUPPORTED, "lecb_layernorm_bwd: D=%d too wide", D);
   count_launch();
   return check_launch("layernorm_bwd_kernel");
@@ -664,7 +673,7 @@ extern "C" int lecb_causal_attn_bwd(const void* qkv, const void* dout, void* dqk
     configured = true;
   }
   dim3 grid(heads, N);
-  causal_attn_bwd_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(causal_attn_bwd_kernel, dim3(grid), dim3(256), smem, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(dout), static_cast<__nv_bfloat16*>(dqkv),
       L, W, 1.0f / sqrtf(static_cast<float>(kDh)));
   count_launch();
@@ -674,7 +683,7 @@ extern "C" int lecb_causal_attn_bwd(const void* qkv, const void* dout, void* dqk
 extern "C" int lecb_l2norm_bwd(const float* x, const float* dy, float* dx, int64_t rows, int D, void* stream) {
   LECB_CHECK_ARG(x && dy && dx && rows > 0 && D > 0, "lecb_l2norm_bwd: bad argument");
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
-  l2norm_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, dy, dx, rows, D);
+  launch_k(l2norm_bwd_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), x, dy, dx, rows, D);
   count_launch();
   return check_launch("l2norm_bwd_kernel");
 }
@@ -689,7 +698,7 @@ extern "C" int lecb_head_aggregate_bwd(const float* dots, int ldn, const float* 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int kj = (K + 31) / 32;
 #define LECB_AGGB(J)                                                                                             \
-  head_aggregate_bwd_kernel<J><<<B, kAggWarps * 32, 0, s>>>(dots, ldn, row_sumsq, row_mask, grad_local, d_dots, B, P, \
+  launch_k(head_aggregate_bwd_kernel<J>, dim3(B), dim3(kAggWarps * 32), 0, s, dots, ldn, row_sumsq, row_mask, grad_local, d_dots, B, P, \
                                                             K, n_txt, logit_scale, spatial_scale)
   if (kj == 1) LECB_AGGB(1);
   else if (kj == 2) LECB_AGGB(2);
@@ -708,10 +717,10 @@ extern "C" int lecb_tn_gemm_small(const float* a, int lda, const void* b, int b_
   const int a_vec = (lda % 4 == 0) && (reinterpret_cast<uintptr_t>(a) & 15) == 0;
   const int b_vec = (D % (b_is_bf16 ? 8 : 4) == 0) && (reinterpret_cast<uintptr_t>(b) & 15) == 0;
   if (b_is_bf16)
-    tn_gemm_small_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(a, lda, static_cast<const __nv_bfloat16*>(b), out, R, J, D, alpha,
+    launch_k(tn_gemm_small_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, a, lda, static_cast<const __nv_bfloat16*>(b), out, R, J, D, alpha,
                                                              accumulate, a_vec, b_vec);
   else
-    tn_gemm_small_kernel<float><<<grid, 256, 0, s>>>(a, lda, static_cast<const float*>(b), out, R, J, D, alpha, accumulate, a_vec, b_vec);
+    launch_k(tn_gemm_small_kernel<float>, dim3(grid), dim3(256), 0, s, a, lda, static_cast<const float*>(b), out, R, J, D, alpha, accumulate, a_vec, b_vec);
   count_launch();
   return check_launch("tn_gemm_small_kernel");
 }

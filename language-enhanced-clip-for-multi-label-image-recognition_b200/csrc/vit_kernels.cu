@@ -11,6 +11,7 @@ namespace lecb {
 // conv1.weight [width,3,p,p], M:247), columns >= 3*p*p are zero.  One thread = 8 consecutive columns.
 __global__ void __launch_bounds__(256)
 patchify_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int H, int W, int p, int Kpad) {
+  pdl_grid_sync();
   const int gw = W / p, gh = H / p;
   const int octs = Kpad / 8;
   const int64_t total = static_cast<int64_t>(B) * gh * gw * octs;
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(256)
 vit_embed_ln_kernel(const __nv_bfloat16* __restrict__ emb, const float* __restrict__ cls, const float* __restrict__ pos,
                     const float* __restrict__ g, const float* __restrict__ bta, float* __restrict__ out, int64_t rows,
                     int T, int D, float eps) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -107,6 +109,7 @@ vit_embed_ln_kernel(const __nv_bfloat16* __restrict__ emb, const float* __restri
 __global__ void __launch_bounds__(256)
 copy_cols_kernel(const __nv_bfloat16* __restrict__ src, int64_t ld_src, int col0, __nv_bfloat16* __restrict__ dst,
                  int64_t ld_dst, int64_t rows, int cols) {
+  pdl_grid_sync();
   const int vecs = cols / 8;
   const int64_t total = rows * vecs;
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
@@ -132,7 +135,7 @@ extern "C" int lecb_patchify(const float* x, void* out, int B, int H, int W, int
   LECB_CHECK_ARG(B > 0 && patch > 0 && H % patch == 0 && W % patch == 0, "lecb_patchify: H=%d W=%d not multiples of patch=%d", H, W, patch);
   LECB_CHECK_ARG(Kpad % 8 == 0 && Kpad >= 3 * patch * patch, "lecb_patchify: Kpad=%d must be a multiple of 8 and >= 3*patch^2", Kpad);
   const int64_t total = static_cast<int64_t>(B) * (H / patch) * (W / patch) * (Kpad / 8);
-  patchify_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(patchify_kernel, dim3(grid_for(total, 256, 16)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       x, static_cast<__nv_bfloat16*>(out), B, H, W, patch, Kpad);
   count_launch();
   return check_launch("patchify_kernel");
@@ -147,9 +150,9 @@ extern "C" int lecb_vit_embed_ln(const void* emb, const float* cls, const float*
   const unsigned grid = grid_for(rows * 32, 256, 8);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const __nv_bfloat16* e = static_cast<const __nv_bfloat16*>(emb);
-  if (per_lane <= 2) vit_embed_ln_kernel<2><<<grid, 256, 0, s>>>(e, cls, pos, gamma, beta, out, rows, T, D, eps);
-  else if (per_lane <= 4) vit_embed_ln_kernel<4><<<grid, 256, 0, s>>>(e, cls, pos, gamma, beta, out, rows, T, D, eps);
-  else if (per_lane <= 8) vit_embed_ln_kernel<8><<<grid, 256, 0, s>>>(e, cls, pos, gamma, beta, out, rows, T, D, eps);
+  if (per_lane <= 2) launch_k(vit_embed_ln_kernel<2>, dim3(grid), dim3(256), 0, s, e, cls, pos, gamma, beta, out, rows, T, D, eps);
+  else if (per_lane <= 4) launch_k(vit_embed_ln_kernel<4>, dim3(grid), dim3(256), 0, s, e, cls, pos, gamma, beta, out, rows, T, D, eps);
+  else if (per_lane <= 8) launch_k(vit_embed_ln_kernel<8>, dim3(grid), dim3(256), 0, s, e, cls, pos, gamma, beta, out, rows, T, D, eps);
   else return fail(LECB_ERR_UNSUPPORTED, "lecb_vit_embed_ln: D=%d too wide", D);
   count_launch();
   return check_launch("vit_embed_ln_kernel");
@@ -160,7 +163,7 @@ extern "C" int lecb_copy_cols(const void* src, int64_t ld_src, int col0, void* d
   LECB_CHECK_ARG(src && dst, "lecb_copy_cols: null pointer");
   LECB_CHECK_ARG(rows > 0 && cols > 0 && cols % 8 == 0 && col0 % 8 == 0 && ld_src % 8 == 0 && ld_dst % 8 == 0,
                  "lecb_copy_cols: cols, col0 and leading dimensions must be multiples of 8");
-  copy_cols_kernel<<<grid_for(rows * (cols / 8), 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(copy_cols_kernel, dim3(grid_for(rows * (cols / 8), 256, 16)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(src), ld_src, col0, static_cast<__nv_bfloat16*>(dst), ld_dst, rows, cols);
   count_launch();
   return check_launch("copy_cols_kernel");

@@ -44,6 +44,7 @@ struct NormParams {
 
 __global__ void __launch_bounds__(256)
 resize_h_kernel(const uint8_t* __restrict__ img, int H, int W, int S, const int* __restrict__ plan, uint8_t* __restrict__ tmp) {
+  pdl_grid_sync();
   const int* rec = plan + blockIdx.y * kWinRec;
   const int top = rec[0], left = rec[1], height = rec[2], pad_top = rec[4], pad_bottom = rec[5];
   const int* bounds = plan + rec[6];
@@ -72,6 +73,7 @@ resize_h_kernel(const uint8_t* __restrict__ img, int H, int W, int S, const int*
 __global__ void __launch_bounds__(256)
 resize_v_kernel(int S, const int* __restrict__ plan, const uint8_t* __restrict__ tmp, uint8_t* __restrict__ out_u8,
                 float* __restrict__ out_f32, NormParams nrm) {
+  pdl_grid_sync();
   const int* rec = plan + blockIdx.y * kWinRec;
   const int* bounds = plan + rec[9];
   const int* coeffs = plan + rec[10];
@@ -190,11 +192,11 @@ extern "C" int lecb_crop_resize_u8(const uint8_t* img, int H, int W, const int* 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int bx = (S * S + 255) / 256 < 64 ? (S * S + 255) / 256 : 64;
   const dim3 grid(bx > 0 ? bx : 1, n);
-  resize_h_kernel<<<grid, 256, 0, s>>>(img, H, W, S, plan, tmp);
+  launch_k(resize_h_kernel, dim3(grid), dim3(256), 0, s, img, H, W, S, plan, tmp);
   count_launch();
   int st = check_launch("resize_h_kernel");
   if (st) return st;
-  resize_v_kernel<<<grid, 256, 0, s>>>(S, plan, tmp, out_u8, out_f32, nrm);
+  launch_k(resize_v_kernel, dim3(grid), dim3(256), 0, s, S, plan, tmp, out_u8, out_f32, nrm);
   count_launch();
   return check_launch("resize_v_kernel");
 }

@@ -95,7 +95,13 @@ def test_train_step_matches_reference(ev, loss_name):
         err = np.abs(got.cpu().numpy() - gref).max() / scale
         cos = float((got.cpu().flatten() @ torch.from_numpy(gref).flatten()) / (got.cpu().norm() * np.linalg.norm(gref)))
         print(f"[train{sfx}] grad {pname}: max err / max ref = {err:.4f}, cosine = {cos:.5f}")
-        assert err < 5e-2 and cos > 0.999, (pname, err, cos)
+        # ASL is smooth: 5 % of the largest reference entry.  The ranking loss is piecewise linear (U:85-93): a logit that
+        # differs from the reference's by the bf16-level 7e-3 flips every hinge within that distance of the margin, and each
+        # flip moves dlogits by a whole unit; on top of that two runs of the backward itself differ by up to 1.8 % of max
+        # (fp32 atomics feeding bf16 roundings).  Measured over repeated runs: 2.7-5.0 % (ranking), 1-2.5 % (ASL);
+        # the direction (cosine) is the stable criterion and keeps the same gate for both
+        gate = 8e-2 if loss_name == "ranking" else 5e-2
+        assert err < gate and cos > 0.999, (pname, err, cos)
 
 
 def test_caption_bank_builder_matches_oracle(tmp_path):
