@@ -14,43 +14,70 @@ namespace lecb {
 constexpr int kDh = 64;
 
 // grid (heads/8, B), 256 threads: warp = head.  Dynamic smem: 8 * (P+1) floats (scores / probs).
+// Eight lanes share one patch row (lane & 7 = 16-byte chunk of the head's 128-byte row, lane >> 3 = patch slot), so a warp-wide
+// load fetches four complete rows, every lane keeps only its 8 query / 8 output values (round 1 / 2: 64 query registers per lane
+// held the kernel at 16 warps per SM, and with one full row per lane it ran at the load latency: 0.37 of the HBM peak), and
+// sixteen rows per warp are in flight in both passes.
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 t;
+  t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
+}
+
 __global__ void __launch_bounds__(256)
 attnpool_query0_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ kmat,
                        const __nv_bfloat16* __restrict__ vmat, __nv_bfloat16* __restrict__ out, int P, int C,
                        float qscale) {
   pdl_grid_sync();
   extern __shared__ float s_scores[];
+  constexpr int kU = 4;                          // 4 x 4 patch rows per warp per step
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = lane >> 3, chunk = lane & 7;
   const int b = blockIdx.y;
   const int h = blockIdx.x * 8 + warp;
   float* sc = s_scores + warp * (P + 1);
-  const float* qp = q + static_cast<int64_t>(b) * C + h * kDh;
-  float qr[kDh];
-#pragma unroll
-  for (int d = 0; d < kDh; ++d) qr[d] = __ldg(qp + d) * qscale;
-  const __nv_bfloat16* kb = kmat + static_cast<int64_t>(b) * P * C + h * kDh;
-  // pass 1: lane-parallel over patches, each lane does a full 64-dim dot (8 x 16-byte loads)
+  float q8[8];
+  {
+    const float4* qp = reinterpret_cast<const float4*>(q + static_cast<int64_t>(b) * C + h * kDh + chunk * 8);
+    const float4 a = __ldg(qp), c = __ldg(qp + 1);
+    q8[0] = a.x * qscale; q8[1] = a.y * qscale; q8[2] = a.z * qscale; q8[3] = a.w * qscale;
+    q8[4] = c.x * qscale; q8[5] = c.y * qscale; q8[6] = c.z * qscale; q8[7] = c.w * qscale;
+  }
+  // pass 1: scores.  Row p of this warp's head: 128 bytes at kb + p*C; lane reads its 16-byte chunk of rows slot, slot+4, ...
+  const __nv_bfloat16* kb = kmat + static_cast<int64_t>(b) * P * C + h * kDh + chunk * 8;
   float ssum = 0.f, smax = -INFINITY;
-  for (int p = lane; p < P; p += 32) {
-    const uint4* kp = reinterpret_cast<const uint4*>(kb + static_cast<int64_t>(p) * C);
-    float s = 0.f;
+  for (int p0 = 0; p0 < P; p0 += 4 * kU) {
+    uint4 raw[kU];
 #pragma unroll
-    for (int v = 0; v < kDh / 8; ++v) {
-      const uint4 u = __ldg(kp + v);
-      float2 f;
-      f = unpack_bf16(u.x); s = fmaf(qr[8 * v + 0], f.x, s); s = fmaf(qr[8 * v + 1], f.y, s);
-      f = unpack_bf16(u.y); s = fmaf(qr[8 * v + 2], f.x, s); s = fmaf(qr[8 * v + 3], f.y, s);
-      f = unpack_bf16(u.z); s = fmaf(qr[8 * v + 4], f.x, s); s = fmaf(qr[8 * v + 5], f.y, s);
-      f = unpack_bf16(u.w); s = fmaf(qr[8 * v + 6], f.x, s); s = fmaf(qr[8 * v + 7], f.y, s);
+    for (int u = 0; u < kU; ++u) {
+      const int p = p0 + 4 * u + slot;
+      raw[u] = p < P ? __ldg(reinterpret_cast<const uint4*>(kb + static_cast<int64_t>(p) * C)) : make_uint4(0u, 0u, 0u, 0u);
     }
-    sc[p] = s;
-    ssum += s;
-    smax = fmaxf(smax, s);
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int p = p0 + 4 * u + slot;
+      float f[8];
+      unpack8(raw[u], f);
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s = fmaf(q8[i], f[i], s);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (p < P && chunk == 0) {                  // one lane per row keeps the statistics
+        sc[p] = s;
+        ssum += s;
+        smax = fmaxf(smax, s);
+      }
+    }
   }
   ssum = warp_sum(ssum);
   smax = warp_max(smax);
   const float s_mean = ssum / static_cast<float>(P);      // score of the mean token (key = mean of keys)
   smax = fmaxf(smax, s_mean);
+  __syncwarp();
   float den = 0.f;
   for (int p = lane; p < P; p += 32) {
     const float e = __expf(sc[p] - smax);
@@ -61,38 +88,52 @@ attnpool_query0_kernel(const float* __restrict__ q, const __nv_bfloat16* __restr
   const float e_mean = __expf(s_mean - smax);
   den += e_mean;
   __syncwarp();
-  // pass 2: lanes over the 64 dims (2 each), loop over patches
-  const __nv_bfloat16* vb = vmat + static_cast<int64_t>(b) * P * C + h * kDh + 2 * lane;
-  float o0 = 0.f, o1 = 0.f, m0 = 0.f, m1 = 0.f;
-  // eight row loads in flight per lane: the loop is a chain of dependent FMAs behind one 128-byte load per patch, and with
-  // 16 warps per SM the load latency, not HBM, set the pace (1.8 TB/s before)
-  int p = 0;
-  for (; p + 8 <= P; p += 8) {
-    uint32_t raw[8];
+  // pass 2: probability-weighted sum and plain sum (the mean token's value) of the value rows, same row -> lane mapping
+  const __nv_bfloat16* vb = vmat + static_cast<int64_t>(b) * P * C + h * kDh + chunk * 8;
+  float o[8], m[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) raw[j] = __ldg(reinterpret_cast<const uint32_t*>(vb + static_cast<int64_t>(p + j) * C));
+  for (int i = 0; i < 8; ++i) {
+    o[i] = 0.f;
+    m[i] = 0.f;
+  }
+  for (int p0 = 0; p0 < P; p0 += 4 * kU) {
+    uint4 raw[kU];
+    float a[kU];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float2 f = unpack_bf16(raw[j]);
-      const float a = sc[p + j];
-      o0 = fmaf(a, f.x, o0);
-      o1 = fmaf(a, f.y, o1);
-      m0 += f.x;
-      m1 += f.y;
+    for (int u = 0; u < kU; ++u) {
+      const int p = p0 + 4 * u + slot;
+      const bool in = p < P;
+      raw[u] = in ? __ldg(reinterpret_cast<const uint4*>(vb + static_cast<int64_t>(p) * C)) : make_uint4(0u, 0u, 0u, 0u);
+      a[u] = in ? sc[p] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      float f[8];
+      unpack8(raw[u], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        o[i] = fmaf(a[u], f[i], o[i]);
+        m[i] += f[i];
+      }
     }
   }
-  for (; p < P; ++p) {
-    const float2 f = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(vb + static_cast<int64_t>(p) * C)));
-    const float a = sc[p];
-    o0 = fmaf(a, f.x, o0);
-    o1 = fmaf(a, f.y, o1);
-    m0 += f.x;
-    m1 += f.y;
-  }
   const float invP = 1.0f / static_cast<float>(P), invd = 1.0f / den;
-  o0 = (o0 + e_mean * m0 * invP) * invd;
-  o1 = (o1 + e_mean * m1 * invP) * invd;
-  reinterpret_cast<uint32_t*>(out + static_cast<int64_t>(b) * C + h * kDh)[lane] = pack_bf16(o0, o1);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {                   // sum over the four patch slots
+    o[i] += __shfl_xor_sync(0xffffffffu, o[i], 8);
+    o[i] += __shfl_xor_sync(0xffffffffu, o[i], 16);
+    m[i] += __shfl_xor_sync(0xffffffffu, m[i], 8);
+    m[i] += __shfl_xor_sync(0xffffffffu, m[i], 16);
+    o[i] = (o[i] + e_mean * m[i] * invP) * invd;
+  }
+  if (slot == 0) {
+    uint4 u;
+    u.x = pack_bf16(o[0], o[1]);
+    u.y = pack_bf16(o[2], o[3]);
+    u.z = pack_bf16(o[4], o[5]);
+    u.w = pack_bf16(o[6], o[7]);
+    *reinterpret_cast<uint4*>(out + static_cast<int64_t>(b) * C + h * kDh + chunk * 8) = u;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -143,7 +143,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_grid_sync();       // prologue done while the previous kernel drained; no global access before this point
+  pdl_wait();            // prologue done while the previous kernel drained; no global access before this point
+  const bool one_item = static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) >= p.total_items;
+  if (one_item) pdl_trigger();             // at most one work item: it is the last one (else: the producer, below)
 
   if (warp == 4) {
     // ------------------------------- TMA producer -------------------------------
@@ -152,6 +154,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++it) {
         int q0, h, b, n_sub, n_kv;
         decode(w, q0, h, b, n_sub, n_kv);
+        if (!one_item && w + static_cast<int>(gridDim.x) >= p.total_items) pdl_trigger();      // last item of a longer run
         const int qb = it & 1;
         mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&q_full[qb], kAtTileBytes);
@@ -249,16 +252,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     // P = exp2(S*sc - msc) -> bf16 K-major operand block in shared memory; returns the row sum.  The second
     // 32-column TMEM load is in flight while the first half is exponentiated; `wait_bar` (P block free) is
     // taken just before the first store so that wait hides behind the first half's math.
-    auto write_p_impl = [&](auto mask_tag, uint32_t tS, uint32_t tP, float msc, int lim, uint64_t* wait_bar,
+    // kHalf (ragged blocks only): no row of this warp sees a key of the second 32-column half — those 32 exponentials per
+    // row are skipped and the half of P is written as zeros
+    auto write_p_impl = [&](auto mask_tag, auto half_tag, uint32_t tS, uint32_t tP, float msc, int lim, uint64_t* wait_bar,
                             uint32_t wait_parity) {
       constexpr bool kMask = decltype(mask_tag)::value;
+      constexpr bool kHalf = decltype(half_tag)::value;
       float sum = 0.f;
       uint32_t ra[32], rb[32], pk[32];
       tmem_ld_32x32(tS, ra);
       tmem_ld_wait();
-      tmem_ld_32x32(tS + 32u, rb);
+      if constexpr (!kHalf) tmem_ld_32x32(tS + 32u, rb);
+      if (kHalf) {
 #pragma unroll
-      for (int c2 = 0; c2 < 2; ++c2) {
+        for (int i = 16; i < 32; ++i) pk[i] = 0u;
+      }
+#pragma unroll
+      for (int c2 = 0; c2 < (kHalf ? 1 : 2); ++c2) {
         uint32_t(&r)[32] = c2 ? rb : ra;
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
@@ -270,7 +280,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
           sum += e0 + e1;
           pk[c2 * 16 + i / 2] = pack_bf16(e0, e1);
         }
-        if (c2 == 0) tmem_ld_wait();
+        if (c2 == 0 && !kHalf) tmem_ld_wait();
       }
       if (wait_bar != nullptr) mbar_wait(wait_bar, wait_parity);      // PV of sub-block jj-2 has consumed this P buffer
       tmem_st_32x32(tP, pk);
@@ -280,8 +290,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     // the mask test costs two extra instructions per score: only the ragged last block / causal diagonal pays it
     auto write_p = [&](uint32_t tS, uint32_t tP, float msc, bool need_mask, int lim, uint64_t* wait_bar,
                        uint32_t wait_parity) {
-      return need_mask ? write_p_impl(std::true_type{}, tS, tP, msc, lim, wait_bar, wait_parity)
-                       : write_p_impl(std::false_type{}, tS, tP, msc, lim, wait_bar, wait_parity);
+      // ragged last block (T = 1 + patches is never a multiple of 64: 17 live keys of 64 at ViT-B/16 @448, ONE at ViT-L/14) and the
+      // causal diagonal: warp-uniform choice of the half-block variant
+      if (need_mask && __reduce_max_sync(0xffffffffu, lim) < 32)
+        return write_p_impl(std::true_type{}, std::true_type{}, tS, tP, msc, lim, wait_bar, wait_parity);
+      return need_mask ? write_p_impl(std::true_type{}, std::false_type{}, tS, tP, msc, lim, wait_bar, wait_parity)
+                       : write_p_impl(std::false_type{}, std::false_type{}, tS, tP, msc, lim, wait_bar, wait_parity);
     };
 
     int sc = 0;
@@ -291,9 +305,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       const int qi = q0 + row;
       const int limit = p.causal ? min(p.T - 1, qi) : p.T - 1;       // last key index this row may see
       float m = -INFINITY, l = 0.f;
+      // ragged last query tile (17 live rows of 128 at T = 785, one at T = 1025; rows 77.. of the text tower): a warp whose 32 rows
+      // are all past q_rows keeps the barrier protocol — it is paced by s_full, so it can never run a phase ahead of the live
+      // warps — but does none of the softmax work; its rows of P / O hold garbage that is never stored (MMA rows are independent)
+      const bool warp_live = q0 + warp * 32 < p.q_rows;
       for (int jj = 0; jj < n_sub; ++jj) {
         const int g = sc + jj, bf = g & 1;
         const uint32_t par = (g >> 1) & 1;
+        if (!warp_live) {
+          mbar_wait(&s_full[bf], par);
+          if (lane == 0) {
+            mbar_arrive(&p_full[bf]);
+            mbar_arrive(&s_free[bf]);
+          }
+          continue;
+        }
         const int kv0 = jj * kAtSub;
         const bool need_mask = (kv0 + kAtSub > p.T) || (p.causal && kv0 + kAtSub - 1 > q0);
         const int lim = limit - kv0;             // columns c <= lim are visible
@@ -334,8 +360,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&s_free[bf]);
-          mbar_arrive(&p_full[bf]);
+          mbar_arrive(&p_full[bf]);        // before s_free: once s_free completes (and the next S of this buffer can be issued, which
+          mbar_arrive(&s_free[bf]);        // is what paces a warp without live rows) every p_full arrival of the sub-block is in
         }
       }
       // all PV MMAs of the item done -> O complete (the last two sub-blocks' commits cover every earlier MMA)

@@ -22,12 +22,14 @@ int fail(int status, const char* fmt, ...) {
 
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-bool pdl_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("LECB_NO_PDL");
-    return !(e != nullptr && e[0] != '\0' && e[0] != '0');
+int pdl_mode() {
+  static const int mode = [] {
+    const char* off = getenv("LECB_NO_PDL");
+    if (off != nullptr && off[0] != '\0' && off[0] != '0') return 0;
+    const char* m = getenv("LECB_PDL_MODE");
+    return (m != nullptr && m[0] >= '0' && m[0] <= '4') ? m[0] - '0' : 1;
   }();
-  return on;
+  return mode;
 }
 
 int sm_count() {

@@ -185,7 +185,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   cluster_sync_all();              // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_grid_sync();       // prologue done while the previous kernel drained; no global access before this point
+  pdl_wait();            // prologue done while the previous kernel drained; no global access before this point
+  if (my_tiles <= 1) pdl_trigger();        // at most one work item: it is the last one (else: the producer, below)
 
   if (warp == kPWarpTma) {
     // ------------------------------- TMA producer (both CTAs) -------------------------------
@@ -195,6 +196,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int ti = 0; ti < my_tiles; ++ti) {
         int m_pair, n_blk;
         tile_coords(ti, m_pair, n_blk);
+        if (ti + 1 == my_tiles && my_tiles > 1) pdl_trigger();         // last work item of a longer run (lecb_common.cuh)
         const int64_t m0 = (static_cast<int64_t>(m_pair) * 2 + rank) * kPM;         // this CTA's first row
         int pw0 = 0, ph0 = 0, pn0 = 0;
         if (kConv) {

@@ -223,7 +223,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_grid_sync();       // the prologue above overlapped the previous kernel's tail; no global access before this point
+  pdl_wait();            // the prologue above overlapped the previous kernel's tail; no global access before this point
+  if (my_tiles <= MT) pdl_trigger();       // at most one work item: it is the last one (else: the producer, below)
 
   if (warp == kWarpTma) {
     // ------------------------------- TMA producer -------------------------------
@@ -237,6 +238,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int ti = 0; ti < my_tiles; ti += MT) {
         int m_blk, n_blk;
         tile_coords(ti, m_blk, n_blk);
+        if (ti + MT >= my_tiles && my_tiles > MT) pdl_trigger();       // last work item of a longer run (lecb_common.cuh)
         if (kConv && p.halo) {
           const int tx = m_blk % p.tiles_x;
           const int ty = (m_blk / p.tiles_x) % p.tiles_y;

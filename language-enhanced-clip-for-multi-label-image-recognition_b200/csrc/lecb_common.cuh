@@ -20,13 +20,26 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 // is still draining: everything before pdl_grid_sync() (barrier init, TMEM allocation, descriptor prefetch) overlaps that
 // tail.  griddepcontrol.wait returns once every prerequisite grid has completed and its memory is visible — no global
 // memory may be read OR written before it (the previous kernel may still be reading what this one overwrites);
-// launch_dependents then lets the NEXT kernel's CTAs start their own prologue as soon as resources free up.  Both are
-// no-ops for a launch without the attribute.
+// launch_dependents then lets the NEXT kernel's CTAs start their own prologue as soon as resources free up (the dependent
+// grid is launched once every CTA of this one has executed it or exited).  Both are no-ops for a launch without the
+// attribute.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pdl_grid_sync() {
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() {
+#ifndef LECB_PDL_NO_TRIGGER
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
 }
+// the row kernels: wait, then let the next kernel in at once
+__device__ __forceinline__ void pdl_grid_sync() {
+  pdl_wait();
+  pdl_trigger();
+}
+// The persistent tensor-core kernels (GEMM / conv, attention) trigger LATE: when a CTA starts its LAST work item, not at its
+// start.  Measured on the ViT-B/16 tower (profiles/r02_pdl_policy.txt): with the trigger at the start of a long GEMM the next
+// row kernel's CTAs become resident beside it for its whole run and the step is 3 % SLOWER than without PDL (24.6 vs 23.9
+// ms); with the late trigger the dependents arrive for the tail only.  Short kernels (one item per CTA: the prompt-tuning
+// step's GEMMs) start their last item at once, which keeps that step's gain (2.76 -> 2.58 ms).
 
 // ------------------------------------------------------------------------------------------
 // mbarrier

@@ -13,10 +13,17 @@ void count_launch(unsigned n = 1);
 int sm_count();                                       // SMs of the current device (cached per device)
 int check_launch(const char* what);                   // cudaGetLastError -> status
 
-// Every kernel launch of the library: cudaLaunchKernelEx with the programmatic-stream-serialization attribute (PDL), so the
-// kernel's prologue overlaps the tail of the previous kernel in the stream (each kernel calls pdl_grid_sync() before it
-// touches global memory: lecb_common.cuh).  LECB_NO_PDL=1 (read once) launches without the attribute.
-bool pdl_enabled();
+// Every kernel launch of the library: cudaLaunchKernelEx, with the programmatic-stream-serialization attribute (PDL) where it
+// pays, so the kernel's prologue overlaps the tail of the previous kernel in the stream (each kernel executes
+// griddepcontrol.wait before it touches global memory: lecb_common.cuh).  Measured policy (profiles/r02_pdl_policy.txt):
+//  * the tensor-core kernels (more than 48 KB of dynamic shared memory: GEMM / conv, attention) always carry the attribute;
+//  * a row kernel carries it only when its grid is small (<= 8 CTAs per SM: the prompt-tuning step, where launch latency is
+//    a fifth of every kernel).  Big row kernels launched early behind a GEMM ran the ViT-B step 2.5 % SLOWER than no PDL at
+//    all (24.7 vs 24.1 ms) and the RN101 step 2 % slower, wherever the primary's trigger sat; launched the ordinary way they
+//    cost nothing (23.9 ms).
+// LECB_PDL_MODE (read once): 1 = that policy (default), 0 = never (same as LECB_NO_PDL=1), 2 = row kernels only, 3 = tensor-core
+// kernels only, 4 = every kernel.
+int pdl_mode();
 template <typename... P, typename... A>
 inline void launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -28,7 +35,17 @@ inline void launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cud
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  const int mode = pdl_mode();
+  const bool heavy = smem > 48 * 1024;
+  bool on = false;
+  switch (mode) {
+    case 1: on = heavy || static_cast<unsigned long long>(grid.x) * grid.y * grid.z <= 8ull * static_cast<unsigned>(sm_count()); break;
+    case 2: on = !heavy; break;
+    case 3: on = heavy; break;
+    case 4: on = true; break;
+    default: break;
+  }
+  cfg.numAttrs = on ? 1 : 0;
   (void)cudaLaunchKernelEx(&cfg, kern, static_cast<A&&>(args)...);      // errors surface through check_launch()
 }
 

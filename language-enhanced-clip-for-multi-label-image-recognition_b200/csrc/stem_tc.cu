@@ -80,7 +80,7 @@ stem_conv1_tc_kernel(const void* __restrict__ xin, const float* __restrict__ w27
   const uint32_t tmem_base = tmem_slot;
   // the prologue read only the layer's own constants (packed weights, bias: written at engine construction, many kernels
   // ago); the pixels may come from the previous kernel (crop + resize) and `out` may still be read by it
-  pdl_grid_sync();
+  pdl_wait();
   const uint32_t idesc = make_idesc_f16(kStemCo, true);
   uint32_t phase = 0;
   const int py = t / kTileW, px = t % kTileW;
@@ -207,6 +207,7 @@ stem_conv1_tc_kernel(const void* __restrict__ xin, const float* __restrict__ w27
   Origin cur = tile_origin(blockIdx.x < static_cast<unsigned>(num_tiles) ? blockIdx.x : 0);
   if (static_cast<int>(blockIdx.x) < num_tiles) fetch(cur);
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    if (tile + static_cast<int>(gridDim.x) >= num_tiles) pdl_trigger();      // last tile of this CTA (late trigger: lecb_common.cuh)
     const int b = cur.b, ho0 = (cur.hi0 + 1) / 2, wo0 = (cur.wi0 + 1) / 2;
     // the previous iteration's readers of `patch` finished before its second __syncthreads
     stash(cur);

@@ -110,3 +110,25 @@ def test_attn_causal_bwd(n, l, heads):
         assert err <= scale * 2.0 ** -6, f"{name}: err {err:.4g} scale {scale:.4g}"
         if ref2 is not None:
             assert (got[:, sl] - ref2[:, sl]).abs().max().item() <= scale * 2.0 ** -6
+
+
+@pytest.mark.parametrize("b,p,heads", [(3, 196, 32), (2, 49, 16), (1, 7, 8), (2, 1024, 8)])
+def test_attnpool_query0_matches_torch(b, p, heads):
+    """CLIP AttentionPool2d reduced to its token-0 output (M:89-127 via T:413): one query per image and head against the P patch
+    keys plus the mean token, whose key / value are the means of the patch keys / values.  fp32 torch on the same bf16 K / V."""
+    from lecb200 import ops
+    c = heads * 64
+    g = torch.Generator(device="cpu").manual_seed(p * 31 + heads)
+    q = torch.randn((b, c), generator=g).cuda()
+    kmat = torch.randn((b * p, c), generator=g).cuda().bfloat16()
+    vmat = torch.randn((b * p, c), generator=g).cuda().bfloat16()
+    out = ops.attnpool_query0(q, kmat, vmat, b, p, heads)
+    torch.cuda.synchronize()
+    kf = kmat.float().view(b, p, heads, 64)
+    vf = vmat.float().view(b, p, heads, 64)
+    keys = torch.cat([kf.mean(1, keepdim=True), kf], 1)                       # mean token first (M:96)
+    vals = torch.cat([vf.mean(1, keepdim=True), vf], 1)
+    s = torch.einsum("bhd,bthd->bht", q.view(b, heads, 64), keys) / 8.0
+    ref = torch.einsum("bht,bthd->bhd", s.softmax(-1), vals).reshape(b, c)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2.0 ** -7 * max(1.0, ref.abs().max().item()), err          # bf16 output
