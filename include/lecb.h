@@ -13,7 +13,12 @@
  *   - returns 0 on success, a negative lecb_status otherwise; `lecb_last_error()` gives the
  *     thread-local message of the last failure on this host thread;
  *   - activations are row-major bf16 "pixel-major" matrices: NHWC images == [B*H*W, C] rows;
- *   - there is NO CPU fallback: without a CUDA device every compute call returns LECB_ERR_CUDA.
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns LECB_ERR_CUDA;
+ *   - launches use programmatic dependent launch (cudaLaunchKernelEx + the stream-serialization attribute) where it was
+ *     measured to pay — the tensor-core kernels always, row kernels with small grids — and every kernel executes
+ *     griddepcontrol.wait before its first global access, so ordinary stream order holds for the caller: work enqueued on
+ *     `stream` before a call is complete and visible to it, and its results to whatever follows.  Works under CUDA-graph
+ *     capture.  Environment LECB_NO_PDL=1 launches everything the ordinary way (LECB_PDL_MODE=0..4: experiment knob).
  */
 #ifndef LECB_H_
 #define LECB_H_
@@ -120,10 +125,10 @@ int lecb_causal_attn_fwd(const void* qkv, void* out, int N, int L, int W, int he
  * Only the first `q_rows` query rows of every sequence are computed and stored (q_rows == T: all of them;
  * q_rows == 1: the class token only, used by the dense last block); other rows of `out` are left untouched. */
 int lecb_attn_fwd(const void* qkv, void* out, int B, int T, int W, int heads, int q_rows, int causal, void* stream);
-/* The kernel is bound by the MUFU (one ex2 per score, 16 per clock and SM): every n-th score's exponential (n in {2, 3, 4};
- * 0 = none; default 4; sequences shorter than 256 tokens always use 0) is evaluated instead as 2^round(x) * cubic(x - round(x))
- * on the FMA pipe (relative error 7.7e-5, 4 % of half a bf16 ulp of the probability): +5-7 % at the ViT shapes.
- * lecb_set_attn_poly returns the previous setting. */
+/* Share of the softmax's exponentials evaluated on the FMA pipe instead of the MUFU: every n-th score (n in {2, 3, 4}; 0 = none;
+ * sequences shorter than 256 tokens always use 0) becomes 2^round(x) * cubic(x - round(x)) (relative error 7.7e-5, 4 % of half a
+ * bf16 ulp of the probability).  Default 0: it paid +5-7 % while the kernel still exponentiated the dead rows / columns of
+ * ragged tiles, and costs 3-4 % since it does not (DESIGN.md section 3 xviii).  lecb_set_attn_poly returns the previous setting. */
 int lecb_set_attn_poly(int n);
 
 /* ---- ViT visual tower row kernels (VisionTransformer.forward, M:259-276) ----

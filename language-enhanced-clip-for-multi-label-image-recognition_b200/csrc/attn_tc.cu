@@ -418,7 +418,10 @@ using namespace lecb;
 
 namespace lecb {
 static int g_attn_poly = -1;        // -1: not initialised (LECB_ATTN_POLY or the default), else 0 / 2 / 3 / 4
-constexpr int kAttnPolyDefault = 4;
+// Default 0 since the ragged-edge skipping (dead query warps, half key blocks): the MUFU is no longer the co-bottleneck it was, and
+// with every exponential on it the kernel is 3-4 % faster than with a quarter on the FMA pipe (456-462 vs 476-492 us per
+// ViT-B/16 layer, 499-508 vs 525-528 at ViT-L/14; before the skipping: 473 vs 449 — profiles/r02_attn_poly_ab.jsonl)
+constexpr int kAttnPolyDefault = 0;
 
 template <int kPoly>
 static int launch_attn(const CUtensorMap& tm, const AttnParams& p, int grid, cudaStream_t stream) {

@@ -40,4 +40,4 @@ for name, b, t, heads, causal in (("ViT-B/16@448", 128, 785, 12, False), ("ViT-L
         row[f"poly{m}"] = {"us": round(ms * 1e3, 1), "tflops": round(fl / ms / 1e9, 1),
                            "max_abs_dev_vs_mufu": float((outs[m] - outs[0]).abs().max())}
     print(json.dumps(row), flush=True)
-_lib.lib.lecb_set_attn_poly(4)
+_lib.lib.lecb_set_attn_poly(0)      # back to the default
