@@ -17,8 +17,13 @@ if os.path.exists(p):
     PEAK = json.load(open(p))["hbm_gbs"]
 
 
+ITERS_CAP = int(os.environ.get("LECB_ROWOPS_ITERS", "0"))      # > 0: few launches per kernel (the ncu pass)
+
+
 def timeit(fn, iters=20):
-    for _ in range(3):
+    if ITERS_CAP:
+        iters = min(iters, ITERS_CAP)
+    for _ in range(1 if ITERS_CAP else 3):
         fn()
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

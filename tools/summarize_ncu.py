@@ -9,6 +9,9 @@ import sys
 from collections import OrderedDict, defaultdict
 
 
+PCT = "dram__throughput.avg.pct_of_peak_sustained_elapsed"
+
+
 def short(name):
     m = re.search(r"lecb::(\w+)", name)
     base = m.group(1) if m else name.split("(")[0][-40:]
@@ -36,8 +39,8 @@ def main(src, dst):
         elif unit == "Gbyte":
             v *= 1e9
         k[name] = v
-    agg = defaultdict(lambda: {"launches": 0, "us": 0.0, "dram_read": 0.0, "dram_write": 0.0})
-    fam = defaultdict(lambda: {"launches": 0, "us": 0.0, "dram_read": 0.0, "dram_write": 0.0})
+    agg = defaultdict(lambda: {"launches": 0, "us": 0.0, "dram_read": 0.0, "dram_write": 0.0, "pct": 0.0, "pct_n": 0})
+    fam = defaultdict(lambda: {"launches": 0, "us": 0.0, "dram_read": 0.0, "dram_write": 0.0, "pct": 0.0, "pct_n": 0})
     for l in launches.values():
         for table, key in ((agg, short(l["kernel"])), (fam, re.sub(r"<.*", "", short(l["kernel"])))):
             a = table[key]
@@ -45,6 +48,9 @@ def main(src, dst):
             a["us"] += l.get("gpu__time_duration.sum", 0.0)
             a["dram_read"] += l.get("dram__bytes_read.sum", 0.0)
             a["dram_write"] += l.get("dram__bytes_write.sum", 0.0)
+            if PCT in l:                                  # optional fourth metric of the row-kernel pass
+                a["pct"] += l[PCT]
+                a["pct_n"] += 1
     total_us = sum(a["us"] for a in fam.values())
 
     def fin(t):
@@ -54,6 +60,8 @@ def main(src, dst):
             out[k] = {"launches": a["launches"], "us_total": round(a["us"], 1), "share_of_profiled_time": round(a["us"] / total_us, 4),
                       "dram_bytes_total": by, "dram_bytes_per_launch": by / a["launches"],
                       "dram_GBs_under_ncu": round(by / a["us"] / 1e3, 1) if a["us"] else None}
+            if a["pct_n"]:
+                out[k]["dram_throughput_pct_of_peak_mean"] = round(a["pct"] / a["pct_n"], 1)
         return out
 
     res = {"source": src, "note": "ncu replays each kernel cold-cache and serialised: shares and bytes are meaningful, absolute times are not bench values",
