@@ -1,4 +1,4 @@
-"""Compact table of the ncu raw pages exported on the GPU box (tools/gpu_call8.sh): python tools/ncu_compact.py gpurun_out/c8_*_raw.csv"""
+"""Compact table of the ncu raw pages exported on the GPU box (tools/gpu_calls/gpu_call8.sh): python tools/ncu_compact.py gpurun_out/c8_*_raw.csv"""
 import csv
 import sys
 
