@@ -13,10 +13,13 @@ PCT = "dram__throughput.avg.pct_of_peak_sustained_elapsed"
 
 
 def short(name):
-    m = re.search(r"lecb::(\w+)", name)
-    base = m.group(1) if m else name.split("(")[0][-40:]
-    t = re.search(r"<([^>]*)>", name)
-    return base + (f"<{t.group(1)}>" if t and "gemm" in base else "")
+    """'void lecb::gemm_kernel<128, 64, ...>(args)' or ncu's namespace-less 'void l2norm_kernel<float, float, 4>(args)' -> the
+    kernel's own name; template arguments are kept (GEMM instances and row-kernel variants are different kernels)."""
+    head = name.split("(")[0]
+    m = re.search(r"(\w+)\s*(<.*>)?\s*$", head)
+    if not m:
+        return head[-60:]
+    return m.group(1) + (m.group(2) or "")
 
 
 def main(src, dst):
