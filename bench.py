@@ -491,7 +491,7 @@ def bench_headline(cx, args):
             for _ in range(prof_steps):
                 model(images, if_test=True)
         table = kt.summary(prof_steps)
-        fam = ("lecb_gemm_bf16", "lecb_conv3x3_bf16", "lecb_bottleneck_tail")
+        fam = ("lecb_gemm_bf16", "lecb_gemm_bf16_dual", "lecb_conv3x3_bf16")
         gemm_ms = sum(table[n]["ms"] for n in fam if n in table)
         gemm_fl = sum(table[n]["flops"] for n in fam if n in table)
         gemm_n = sum(table[n]["launches"] for n in fam if n in table)

@@ -67,6 +67,16 @@ unsigned long long lecb_launch_count(void);
 int lecb_gemm_bf16(const void* A, const void* W, const float* bias, const void* residual, void* out,
                    float* row_sumsq, int64_t M, int N, int K, unsigned flags, void* stream);
 
+/* ---- the same GEMM over TWO A operands (K-concatenation without the concatenated tensor) ----------
+ * out[M,N] = epi( A1[M,K1] · W[:, :K1]^T + A2[M,K2] · W[:, K1:]^T + bias[N] ), W bf16 [N, K1+K2], bf16 output.
+ * Replaces the tail of a Bottleneck with a projection shortcut, M:46-52:
+ *   out = bn3(conv3(out)); identity = downsample(x); out += identity; out = relu(out)
+ * as ONE GEMM of [y | x_pooled] against [W3 | Wd] (eval BatchNorm folded, bias = b3 + bd): the [M,N] shortcut tensor is
+ * neither written nor read back as a residual.  k blocks [0, K1/64) are TMA-loaded from A1, the rest from A2.
+ * Requirements: K1 % 64 == 0, K2 % 64 == 0, N % 8 == 0, 16-byte aligned operands; flags: 0 or LECB_EPI_RELU. */
+int lecb_gemm_bf16_dual(const void* A1, int K1, const void* A2, int K2, const void* W, const float* bias, void* out,
+                        int64_t M, int N, unsigned flags, void* stream);
+
 /* ---- implicit-GEMM 3x3 convolution, stride 1, pad 1 (TMA im2col + tcgen05) ---------------------
  * x: NHWC bf16 [B,H,W,Cin]; w: bf16 [Cout][3][3][Cin] with eval-BatchNorm folded in; bias fp32 [Cout];
  * out: NHWC bf16 [B,H,W,Cout].  Replaces M:44 (Bottleneck conv2+bn2+relu) and M:174-175 (stem

@@ -19,6 +19,8 @@ SIGNATURES = {
     "lecb_launch_count": (C.c_ulonglong, []),
     "lecb_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int,
                                c_uint, c_void_p]),
+    "lecb_gemm_bf16_dual": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_uint,
+                                    c_void_p]),
     "lecb_conv3x3_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_uint, c_void_p]),
     "lecb_set_pair_gemm": (c_int, [c_int]),

@@ -64,6 +64,8 @@ struct PairParams {
   int num_n_tiles;     // ceil(N / 256)
   unsigned flags;
   int H, W, kb_per_tap;   // conv mode
+  int kb_split;           // > 0: two A operands (lecb_gemm_bf16_dual): k blocks >= kb_split come from A2, whose tensor map travels
+                          // in the residual slot (the mode has no residual)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -218,7 +220,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma2_load_im2col_4d(&tmA, &full[stage], sA + stage * kPABytes, cb * kPK, pw0 - 1, ph0 - 1, pn0,
                                 static_cast<uint16_t>(kx), static_cast<uint16_t>(ky));
           } else {
-            tma2_load_2d(&tmA, &full[stage], sA + stage * kPABytes, kb * kPK, static_cast<int>(m0));
+            const bool second = p.kb_split > 0 && kb >= p.kb_split;
+            tma2_load_2d(second ? &tmR : &tmA, &full[stage], sA + stage * kPABytes, (second ? kb - p.kb_split : kb) * kPK,
+                         static_cast<int>(m0));
           }
           tma2_load_2d(&tmB, &full[stage], sB + stage * kPBBytes, kb * kPK, n0);
           if (++stage == kStages) {
@@ -523,8 +527,11 @@ static int staging_buffers(int num_kb, bool has_res) {
 }
 
 int launch_pair_gemm(const void* A, const void* Wt, const float* bias, const void* residual, void* out, float* row_sumsq,
-                     int64_t M, int N, int K, unsigned flags, cudaStream_t stream) {
+                     int64_t M, int N, int K, unsigned flags, cudaStream_t stream, const void* A2, int K1) {
+  if (A2 != nullptr && (residual != nullptr || K1 <= 0 || K1 >= K || K1 % kPK != 0 || (flags & LECB_EPI_OUT_F32)))
+    return fail(LECB_ERR_ARG, "pair GEMM, dual-A mode: bad split K1=%d of K=%d, residual or fp32 output given", K1, K);
   PairParams p{};
+  p.kb_split = A2 != nullptr ? K1 / kPK : 0;
   p.bias = bias;
   p.residual = residual;
   p.row_sumsq = row_sumsq;
@@ -535,7 +542,7 @@ int launch_pair_gemm(const void* A, const void* Wt, const float* bias, const voi
   p.num_n_tiles = (N + kPN - 1) / kPN;
   p.flags = flags;
   CUtensorMap tmA, tmB, tmC, tmR;
-  int st = encode_tiled_2d(&tmA, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), kPM, kPK);
+  int st = encode_tiled_2d(&tmA, A, static_cast<uint64_t>(M), static_cast<uint64_t>(A2 != nullptr ? K1 : K), kPM, kPK);
   if (st) return st;
   st = encode_tiled_2d(&tmB, Wt, static_cast<uint64_t>(N), static_cast<uint64_t>(K), kPN / 2, kPK);
   if (st) return st;
@@ -546,6 +553,10 @@ int launch_pair_gemm(const void* A, const void* Wt, const float* bias, const voi
   tmR = tmC;
   if (residual != nullptr) {
     st = encode_tiled_2d_ex(&tmR, residual, static_cast<uint64_t>(M), static_cast<uint64_t>(N), kPM, ccols, esz);
+    if (st) return st;
+  }
+  if (A2 != nullptr) {                   // the second A operand rides in the residual slot
+    st = encode_tiled_2d(&tmR, A2, static_cast<uint64_t>(M), static_cast<uint64_t>(K - K1), kPM, kPK);
     if (st) return st;
   }
   // fp32 blocks carry half the columns: twice the blocks in flight for the same bytes

@@ -33,7 +33,7 @@ namespace lecb {
 bool pair_gemm_eligible(int64_t M, int N, int K, unsigned flags, bool has_sumsq_f32_out);
 bool pair_conv_eligible(int B, int H, int Wd, int Cin, int Cout, unsigned flags);
 int launch_pair_gemm(const void* A, const void* Wt, const float* bias, const void* residual, void* out, float* row_sumsq,
-                     int64_t M, int N, int K, unsigned flags, cudaStream_t stream);
+                     int64_t M, int N, int K, unsigned flags, cudaStream_t stream, const void* A2 = nullptr, int K1 = 0);
 int launch_pair_conv3x3(const void* x, const void* w, const float* bias, void* out, int B, int H, int Wd, int Cin, int Cout,
                         unsigned flags, cudaStream_t stream);
 
@@ -106,6 +106,9 @@ struct GemmParams {
   float* topk_val;    // fused per-row top-10 epilogue (caption retrieval, T:446): instead of storing the tile, every epilogue
   int* topk_idx;      // thread keeps the 10 largest values of its row over the n tiles this CTA processes and writes them
   int topk_slots;     // to slot blockIdx.x of [rows][topk_slots][10]; a merge kernel finishes (retrieval.cu)
+  int kb_split;       // > 0: TWO A operands (lecb_gemm_bf16_dual): k blocks [0, kb_split) come from A1 (tmA), the rest from A2
+                      // (which travels in the residual tensor-map slot: the mode has no residual) — the K-concatenated GEMM
+                      // [A1 | A2] . [W1 | W2]^T without ever materialising the concatenation
   int halo_single;    // tw == 8: ONE (th+2) x (tw+2) halo copy per stage.  The swizzle of a K-major operand is a function of
                       // the absolute shared-memory address bits (measured: a descriptor may start on any 128-byte row
                       // with base_offset 0), so tap (ky,kx) is just start = copy + (ky*(tw+2) + kx) * 128 with an
@@ -198,6 +201,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.kb_split > 0) tma_prefetch_desc(&tmR);
     for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -296,8 +300,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tma_load_im2col_4d(&tmA, &full[stage], sA_ring + stage * a_stride + Cfg::kABytes, cb * BK, pw1 - 1, ph1 - 1,
                                  pn1, static_cast<uint16_t>(kx), static_cast<uint16_t>(ky));
           } else {
-            const int a_col = p.hilo ? (kb & 1) * (p.num_kb >> 1) * BK + (kb >> 1) * BK : kb * BK;
-            tma_load_2d(&tmA, &full[stage], sA_ring + stage * a_stride, a_col, m_blk * kTileM);
+            const bool second = p.kb_split > 0 && kb >= p.kb_split;                 // dual-A mode: the tail of K is A2's
+            const int a_col = p.hilo ? (kb & 1) * (p.num_kb >> 1) * BK + (kb >> 1) * BK : (second ? kb - p.kb_split : kb) * BK;
+            tma_load_2d(second ? &tmR : &tmA, &full[stage], sA_ring + stage * a_stride, a_col, m_blk * kTileM);
           }
           if (!p.b_resident)
             tma_load_2d(&tmB, &full[stage], sB + stage * Cfg::kBBytes, (p.hilo ? (kb >> 1) : kb) * BK, n_blk * BN);
@@ -833,7 +838,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 template <int BN, int BK, int NB, bool kConv>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t stream,
+                       const CUtensorMap* tmA2 = nullptr) {
   using Cfg = GemmCfg<BN, BK, NB>;
   constexpr bool kPairable = kConv && BN == 128 && BK == 64 && NB == 2;      // the one instantiation of MT = 2
   static DeviceOnce once;                    // the attribute is per device: one flag per device ordinal
@@ -866,6 +872,10 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParam
       st = encode_tiled_2d_ex(&tmR, p.residual, static_cast<uint64_t>(p.M), static_cast<uint64_t>(p.N), kTileM, ccols, esz);
       if (st) return st;
     }
+  }
+  if (p.kb_split > 0) {                  // dual-A mode: the second A operand rides in the (otherwise unused) residual slot
+    if (tmA2 == nullptr || p.residual != nullptr) return fail(LECB_ERR_ARG, "dual-A GEMM: second operand missing or residual given");
+    tmR = *tmA2;
   }
   // Weight tiles that fit stay resident in shared memory for the CTA's lifetime (64-channel 3x3 convs: 9 x 8 KB;
   // the K <= 256 expand convs: 128 KB): the mainloop then streams only A tiles, which removes the W re-fetch from
@@ -912,13 +922,14 @@ static int pick_bn(int N) {
 // NB = number of 16 KB epilogue staging buffers: 4 when the K loop is short (the tile is epilogue/HBM-bound and
 // deeper residual prefetch + store overlap matters more than operand stages), else 2.
 template <bool kConv, int NB>
-static int dispatch_nb(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t s) {
+static int dispatch_nb(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t s,
+                       const CUtensorMap* tmA2 = nullptr) {
   if (BK == 64) {
     switch (BN) {
-      case 32: return launch_gemm<32, 64, NB, kConv>(tmA, tmB, p, s);
-      case 64: return launch_gemm<64, 64, NB, kConv>(tmA, tmB, p, s);
-      case 128: return launch_gemm<128, 64, NB, kConv>(tmA, tmB, p, s);
-      default: return launch_gemm<256, 64, NB, kConv>(tmA, tmB, p, s);
+      case 32: return launch_gemm<32, 64, NB, kConv>(tmA, tmB, p, s, tmA2);
+      case 64: return launch_gemm<64, 64, NB, kConv>(tmA, tmB, p, s, tmA2);
+      case 128: return launch_gemm<128, 64, NB, kConv>(tmA, tmB, p, s, tmA2);
+      default: return launch_gemm<256, 64, NB, kConv>(tmA, tmB, p, s, tmA2);
     }
   }
   return BN == 32 ? launch_gemm<32, 32, NB, kConv>(tmA, tmB, p, s) : launch_gemm<64, 32, NB, kConv>(tmA, tmB, p, s);
@@ -938,7 +949,8 @@ static int resident_ring(int BN, int BK, int num_kb, int nb) {
 }
 
 template <bool kConv>
-static int dispatch(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t s) {
+static int dispatch(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t s,
+                    const CUtensorMap* tmA2 = nullptr) {
   int nb = 2;
   if (!kConv) {
     if (p.num_kb <= 2) nb = 8;               // measured 6 / 8: equal
@@ -981,11 +993,11 @@ static int dispatch(int BN, int BK, const CUtensorMap& tmA, const CUtensorMap& t
   }
   if (kConv && nb == 1) return dispatch_nb<kConv, 1>(BN, BK, tmA, tmB, p, s);
   switch (nb) {
-    case 8: return dispatch_nb<kConv, 8>(BN, BK, tmA, tmB, p, s);
-    case 5: return dispatch_nb<kConv, 5>(BN, BK, tmA, tmB, p, s);
-    case 4: return dispatch_nb<kConv, 4>(BN, BK, tmA, tmB, p, s);
-    case 3: return dispatch_nb<kConv, 3>(BN, BK, tmA, tmB, p, s);
-    default: return dispatch_nb<kConv, 2>(BN, BK, tmA, tmB, p, s);
+    case 8: return dispatch_nb<kConv, 8>(BN, BK, tmA, tmB, p, s, tmA2);
+    case 5: return dispatch_nb<kConv, 5>(BN, BK, tmA, tmB, p, s, tmA2);
+    case 4: return dispatch_nb<kConv, 4>(BN, BK, tmA, tmB, p, s, tmA2);
+    case 3: return dispatch_nb<kConv, 3>(BN, BK, tmA, tmB, p, s, tmA2);
+    default: return dispatch_nb<kConv, 2>(BN, BK, tmA, tmB, p, s, tmA2);
   }
 }
 
@@ -1042,6 +1054,45 @@ extern "C" int lecb_gemm_bf16(const void* A, const void* W, const float* bias, c
   st = encode_tiled_2d(&tmB, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), BN, BK);
   if (st) return st;
   return dispatch<false>(BN, BK, tmA, tmB, p, static_cast<cudaStream_t>(stream));
+}
+
+// K-concatenated GEMM over two A operands (the projection shortcut of a bottleneck, M:44-52):
+//   out[M,N] = epi( A1[M,K1] . W[:, :K1]^T + A2[M,K2] . W[:, K1:]^T + bias ),   W = [W1 | W2] bf16 [N, K1+K2]
+// `out = relu(bn3(conv3(y)) + downsample(x))` is one GEMM with [y | x] against [W3 | Wd] and the summed folded biases: the
+// shortcut tensor (M x N bf16) is neither written nor read back as a residual.  bf16 output, K1 % 64 == K2 % 64 == 0.
+extern "C" int lecb_gemm_bf16_dual(const void* A1, int K1, const void* A2, int K2, const void* W, const float* bias, void* out,
+                                   int64_t M, int N, unsigned flags, void* stream) {
+  LECB_CHECK_ARG(A1 && A2 && W && out, "lecb_gemm_bf16_dual: null pointer");
+  LECB_CHECK_ARG(M > 0 && N > 0 && K1 > 0 && K2 > 0, "lecb_gemm_bf16_dual: empty problem M=%lld N=%d K1=%d K2=%d", (long long)M, N, K1, K2);
+  LECB_CHECK_ARG(K1 % 64 == 0 && K2 % 64 == 0, "lecb_gemm_bf16_dual: K1=%d and K2=%d must be multiples of 64", K1, K2);
+  LECB_CHECK_ARG(N % 8 == 0, "lecb_gemm_bf16_dual: N=%d must be a multiple of 8", N);
+  LECB_CHECK_ARG((flags & ~static_cast<unsigned>(LECB_EPI_RELU)) == 0, "lecb_gemm_bf16_dual: only LECB_EPI_RELU is supported (flags=0x%x)", flags);
+  LECB_CHECK_ARG(((reinterpret_cast<uintptr_t>(A1) | reinterpret_cast<uintptr_t>(A2) | reinterpret_cast<uintptr_t>(W) |
+                   reinterpret_cast<uintptr_t>(out)) & 15) == 0, "lecb_gemm_bf16_dual: operands must be 16-byte aligned");
+  const int K = K1 + K2;
+  if (pair_gemm_eligible(M, N, K, flags, false))
+    return launch_pair_gemm(A1, W, bias, nullptr, out, nullptr, M, N, K, flags, static_cast<cudaStream_t>(stream), A2, K1);
+  const int BK = 64;
+  const int BN = pick_bn(N);
+  GemmParams p{};
+  p.bias = bias;
+  p.out = out;
+  p.mt = 1;
+  p.M = M;
+  p.N = N;
+  p.num_kb = K / BK;
+  p.kb_split = K1 / BK;
+  p.num_m_tiles = static_cast<int>((M + kTileM - 1) / kTileM);
+  p.num_n_tiles = (N + BN - 1) / BN;
+  p.flags = flags;
+  CUtensorMap tmA, tmA2, tmB;
+  int st = encode_tiled_2d(&tmA, A1, static_cast<uint64_t>(M), static_cast<uint64_t>(K1), kTileM, BK);
+  if (st) return st;
+  st = encode_tiled_2d(&tmA2, A2, static_cast<uint64_t>(M), static_cast<uint64_t>(K2), kTileM, BK);
+  if (st) return st;
+  st = encode_tiled_2d(&tmB, W, static_cast<uint64_t>(N), static_cast<uint64_t>(K), BN, BK);
+  if (st) return st;
+  return dispatch<false>(BN, BK, tmA, tmB, p, static_cast<cudaStream_t>(stream), &tmA2);
 }
 
 // Similarity GEMM with the per-row top-10 fused into the epilogue (caption retrieval, T:444-446):

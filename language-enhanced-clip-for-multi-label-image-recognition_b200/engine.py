@@ -79,6 +79,11 @@ class VisualRN:
                 if (p + ".downsample.0.weight") in sd:
                     w, b = _fold_bn(sd, p + ".downsample.0.weight", p + ".downsample.1")
                     blk["ds"] = (_w1x1(w), b)
+                    # M:46-52 as ONE K-concatenated GEMM: relu([y | idn] . [W3 | Wd]^T + b3 + bd) — the shortcut tensor is never
+                    # written (ops.gemm_dual); needs 64-channel granularity on both operands, else the two-GEMM form below
+                    w3, b3 = blk["c3"]
+                    if w3.shape[1] % 64 == 0 and blk["ds"][0].shape[1] % 64 == 0 and not os.environ.get("LECB_NO_DUAL"):
+                        blk["c3ds"] = (torch.cat([w3, blk["ds"][0]], 1).contiguous(), (b3 + b).contiguous())
                 self.blocks.append(blk)
         ap = "visual.attnpool."
         self.proj = {n: (sd[ap + n + ".weight"].to(torch.bfloat16).contiguous(), sd[ap + n + ".bias"].float().contiguous())
@@ -118,6 +123,9 @@ class VisualRN:
             y = ops.avgpool2x2(y)
             idn = ops.avgpool2x2(x)
             h, w = h // 2, w // 2
+        if "c3ds" in blk:
+            out = ops.gemm_dual(y.view(b * h * w, -1), idn.view(b * h * w, -1), *blk["c3ds"], relu=True)
+            return out.view(b, h, w, -1)
         if "ds" in blk:
             idn = ops.gemm(idn.view(-1, c), *blk["ds"])
         out = ops.gemm(y.view(b * h * w, -1), *blk["c3"], residual=idn.view(b * h * w, -1), relu=True)

@@ -51,6 +51,26 @@ def gemm(a, w, bias=None, residual=None, relu=False, quick_gelu=False, out_f32=F
     return out
 
 
+def gemm_dual(a1, a2, w, bias=None, relu=False, out=None):
+    """out[M,N] = epi(a1[M,K1] @ w[:, :K1]^T + a2[M,K2] @ w[:, K1:]^T + bias): the K-concatenated GEMM [a1 | a2] @ w^T without
+    the concatenated tensor (lecb_gemm_bf16_dual; the projection-shortcut tail of a Bottleneck, M:46-52).  All bf16, bias fp32,
+    K1 and K2 multiples of 64."""
+    _need(a1, torch.bfloat16, "a1")
+    _need(a2, torch.bfloat16, "a2")
+    _need(w, torch.bfloat16, "w")
+    m, k1 = a1.shape
+    m2, k2 = a2.shape
+    n, k = w.shape
+    assert m == m2 and k == k1 + k2, (a1.shape, a2.shape, w.shape)
+    if bias is not None:
+        _need(bias, torch.float32, "bias")
+    if out is None:
+        out = torch.empty((m, n), device=a1.device, dtype=torch.bfloat16)
+    check(lib.lecb_gemm_bf16_dual(_ptr(a1), k1, _ptr(a2), k2, _ptr(w), _ptr(bias), _ptr(out), m, n, EPI_RELU if relu else 0,
+                                  _stream()), "lecb_gemm_bf16_dual")
+    return out
+
+
 def gemm_mul_quick_gelu_grad(a, w, v, out=None):
     """out[M,N] = (a[M,K] @ w[N,K]^T) * QuickGELU'(v[M,N]), all bf16: the c_proj data gradient and the QuickGELU backward
     (autograd of M:202-204, 226-227) in one launch; the product is rounded to bf16 once."""

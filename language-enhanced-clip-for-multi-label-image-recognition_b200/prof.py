@@ -18,6 +18,8 @@ ALGO_FLOP_SCALE = 1.0
 def _sig(name, a):
     if name == "lecb_gemm_bf16":
         return f"M={a[6]} N={a[7]} K={a[8]} flags={a[9]} res={int(bool(a[3]))}"
+    if name == "lecb_gemm_bf16_dual":
+        return f"M={a[7]} N={a[8]} K={a[1]}+{a[3]} flags={a[9]}"
     if name == "lecb_conv3x3_bf16":
         return f"B={a[4]} H={a[5]} W={a[6]} Cin={a[7]} Cout={a[8]}" + (" +pool" if a[9] & _lib.EPI_AVGPOOL2 else "")
     if name == "lecb_avgpool2x2":
@@ -32,6 +34,9 @@ def _work(name, a):
         out_b = 4 if flags & _lib.EPI_OUT_F32 else 2
         res_b = 0 if not a[3] else (4 if flags & _lib.EPI_RES_F32 else 2)
         return 2.0 * m * n * k, 2.0 * (m * k + n * k) + m * n * (out_b + res_b)
+    if name == "lecb_gemm_bf16_dual":                 # [A1 | A2] . W^T: both operands and W read once, bf16 out, no residual
+        k, m, n = a[1] + a[3], a[7], a[8]
+        return 2.0 * m * n * k, 2.0 * (m * k + n * k) + 2.0 * m * n
     if name == "lecb_conv3x3_bf16":
         b, h, w, ci, co = a[4], a[5], a[6], a[7], a[8]
         out_px = b * h * w / (4.0 if a[9] & _lib.EPI_AVGPOOL2 else 1.0)      # fused 2x2 average pool writes a quarter

@@ -53,6 +53,12 @@ def test_argument_errors_are_reported_without_a_gpu(built):
     # null pointers / bad shapes are rejected before any CUDA call
     st = lib.lecb_gemm_bf16(0, 0, 0, 0, 0, 0, 128, 64, 64, 0, 0)
     assert st == -1 and b"null" in lib.lecb_last_error()
+    st = lib.lecb_gemm_bf16_dual(0, 64, 0, 64, 0, 0, 0, 128, 64, 0, 0)
+    assert st == -1 and b"null" in lib.lecb_last_error()
+    st = lib.lecb_gemm_bf16_dual(16, 64, 16, 96, 16, 0, 16, 128, 64, 0, 0)              # K2 not a multiple of 64
+    assert st == -1 and b"multiples of 64" in lib.lecb_last_error()
+    st = lib.lecb_gemm_bf16_dual(16, 64, 16, 64, 16, 0, 16, 128, 64, _lib.EPI_QUICKGELU, 0)   # only ReLU is offered
+    assert st == -1 and b"LECB_EPI_RELU" in lib.lecb_last_error()
     st = lib.lecb_head_aggregate(1, 240, 0, 0, 1, 0, 0, 1, 1, 500, 3, 4.0, 50.0, 0)
     assert st == -1 and b"K" in lib.lecb_last_error()
     # the fused average pool needs even H and W (checked before any CUDA call); the planning query never launches

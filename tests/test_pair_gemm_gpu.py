@@ -177,3 +177,46 @@ def test_tn_gemm_small_matches_torch(r, j, d, lda, bf16):
     assert a_un.data_ptr() % 16 != 0 and b_un.data_ptr() % 16 != 0 and a_un.is_contiguous()
     got2 = ops.tn_gemm_small(a_un, b_un, j)
     assert torch.equal(got2, got)
+
+
+# (M, N, K1, K2): the four projection-shortcut tails of RN50 / RN101 (scaled-down M), one ragged M, one N tail; the first and the
+# last two run on the single-CTA kernel (K < 256 / N < 256), the others on the CTA-pair kernel
+DUAL_SHAPES = [(50176, 256, 64, 64), (38016, 512, 128, 256), (37888, 1024, 256, 512), (19200, 2048, 512, 1024),
+               (38000 + 77, 512, 256, 128), (20000, 320, 64, 192), (9000, 128, 64, 64), (4096, 64, 128, 64)]
+
+
+@pytest.mark.parametrize("m,n,k1,k2", DUAL_SHAPES)
+def test_dual_operand_gemm_equals_concatenated_gemm(m, n, k1, k2, pair_switch):
+    """lecb_gemm_bf16_dual (two A operands, K-concatenated: the Bottleneck tail M:46-52 as one GEMM) against fp32 torch and,
+    bit for bit, against lecb_gemm_bf16 on the materialised concatenation (same k-block order, same accumulation)."""
+    from lecb200 import ops
+    a1 = _rand((m, k1), 31).bfloat16()
+    a2 = _rand((m, k2), 32).bfloat16()
+    w = _rand((n, k1 + k2), 33, (k1 + k2) ** -0.5).bfloat16()
+    bias = _rand((n,), 34)
+    cat = torch.cat([a1, a2], 1).contiguous()
+    base = cat.float() @ w.float().t() + bias
+    for mode in (1, 0):
+        pair_switch(mode)
+        for relu in (True, False):
+            got = ops.gemm_dual(a1, a2, w, bias, relu=relu)
+            ref = ops.gemm(cat, w, bias, relu=relu)
+            torch.cuda.synchronize()
+            _check(got, base.relu() if relu else base, f"dual {m}x{n}x({k1}+{k2}) relu={relu} pair={mode}")
+            assert torch.equal(got, ref), f"dual vs concatenated differ by {(got.float() - ref.float()).abs().max().item()} (pair={mode})"
+    pair_switch(1)
+    # the reference's own form: conv3 + bn3, downsample, add, relu with the shortcut rounded to bf16 in between (two-GEMM path)
+    idn = ops.gemm(a2, w[:, k1:].contiguous(), None)
+    two = ops.gemm(a1, w[:, :k1].contiguous(), bias, residual=idn, relu=True)
+    one = ops.gemm_dual(a1, a2, w, bias, relu=True)
+    torch.cuda.synchronize()
+    _check(one, two.float(), "dual vs two-GEMM form")
+
+
+def test_dual_operand_gemm_argument_errors():
+    from lecb200 import _lib, ops
+    a1 = torch.zeros((256, 64), device="cuda", dtype=torch.bfloat16)
+    a2 = torch.zeros((256, 96), device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros((64, 160), device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(_lib.LecbError):
+        ops.gemm_dual(a1, a2, w)                 # K2 = 96 is not a multiple of 64
