@@ -21,10 +21,17 @@
 namespace lecb {
 
 constexpr int kStemCo = 32;
-constexpr int kStemK = 32;          // 27 taps + 5 zero columns
+constexpr int kStemK = 32;          // 27 taps + 2 bias columns (A = 1.0, W = bias as a bf16 hi / lo pair) + 3 zero columns
 constexpr int kTileH = 8, kTileW = 16;                    // output pixels per CTA tile (128 = TMEM lanes)
 constexpr int kPatchH = 2 * kTileH + 1, kPatchW = 2 * kTileW + 1;      // 17 x 33 input pixels
 constexpr int kPatchPitch = 100;                          // bf16 elements per patch row (33 * 3 = 99, even pitch: 4-byte rows)
+
+// max(x, 0) and round to bf16, two values per instruction (lo -> bits 0-15)
+__device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 
 struct StemNorm {
   float mean[3], std[3];
@@ -40,7 +47,6 @@ stem_conv1_tc_kernel(const void* __restrict__ xin, const float* __restrict__ w27
   __shared__ __nv_bfloat16 lut[kU8 ? 3 * 256 : 1];
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ uint32_t tmem_slot;
-  __shared__ float sbias[kStemCo];
   const int t = threadIdx.x;
   const int warp = t >> 5;
   const int HO = H / 2, WO = W / 2;
@@ -52,6 +58,10 @@ stem_conv1_tc_kernel(const void* __restrict__ xin, const float* __restrict__ w27
     if (k < 27) {
       const int ky = k / 9, kx = (k % 9) / 3, ci = k % 3;
       v = w27[(ci * 9 + ky * 3 + kx) * kStemCo + co];
+    } else if (k == 27) {
+      v = bias[co];                                                        // rounded to bf16 below: the "hi" half
+    } else if (k == 28) {
+      v = bias[co] - __bfloat162float(__float2bfloat16(bias[co]));        // the "lo" half: hi + lo = bias to 2^-17 relative
     }
     const uint32_t off = swizzled_chunk_offset(co, k / 8, 64) + (k % 8) * 2;
     *reinterpret_cast<__nv_bfloat16*>(sW + off) = __float2bfloat16(v);
@@ -64,7 +74,6 @@ stem_conv1_tc_kernel(const void* __restrict__ xin, const float* __restrict__ w27
       lut[i] = __float2bfloat16(v);
     }
   }
-  if (t < kStemCo) sbias[t] = bias[t];
   if (t == 0) {
     mbar_init(&mma_bar, 1);
     fence_barrier_init();
@@ -172,6 +181,21 @@ stem_conv1_tc_kernel(const void* __restrict__ xin, const float* __restrict__ w27
           const int cc0 = 4 * lane - shift;                              // row byte of this lane's first byte (may be < 0)
           const uint32_t w4 = words[kU8 ? it : 0];
           __nv_bfloat16* prow = patch + r * kPatchPitch;
+          if (row_ok && !edge_cols) {
+            // interior row of an interior tile (block-uniform x warp-uniform condition): every column is a pixel of the image,
+            // so only the two ends of the 99-byte window need a range test; the channel of byte k is (ci0 + k) mod 3 with ONE
+            // division per lane and row (4 = 1 mod 3)
+            const int q = ((cc0 + 3) * 171) >> 9;                          // (cc0 + 3) / 3, cc0 >= -3
+            const int ci0 = cc0 + 3 - 3 * q;                               // cc0 mod 3 (floor)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              int ci = ci0 + k;
+              ci -= ci >= 3 ? 3 : 0;                                       // ci0 + k <= 5
+              const __nv_bfloat16 val = lut[ci * 256 + ((w4 >> (8 * k)) & 0xffu)];
+              if (static_cast<unsigned>(cc0 + k) < static_cast<unsigned>(kPatchW * 3)) prow[cc0 + k] = val;
+            }
+            continue;
+          }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int cc = cc0 + k;
@@ -219,8 +243,11 @@ stem_conv1_tc_kernel(const void* __restrict__ xin, const float* __restrict__ w27
     // ---- this thread's im2col row: three runs of 9 consecutive patch elements (ky = 0, 1, 2) ----
     {
       uint16_t v[kStemK];
+      // the folded-BN bias rides through the MMA: columns 27 / 28 of every A row are 1.0 against the bias's bf16 (hi, lo) pair in
+      // W — the accumulator leaves TMEM with the bias already added, and the epilogue is one cvt.relu per channel pair
+      v[27] = v[28] = 0x3F80;
 #pragma unroll
-      for (int k = 27; k < kStemK; ++k) v[k] = 0;
+      for (int k = 29; k < kStemK; ++k) v[k] = 0;
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         // element offset (2py+ky)*100 + 6px is even: five aligned 32-bit words cover the nine values
@@ -267,10 +294,10 @@ stem_conv1_tc_kernel(const void* __restrict__ xin, const float* __restrict__ w27
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint4 u;
-        u.x = pack_bf16(fmaxf(__uint_as_float(r[c * 8 + 0]) + sbias[c * 8 + 0], 0.f), fmaxf(__uint_as_float(r[c * 8 + 1]) + sbias[c * 8 + 1], 0.f));
-        u.y = pack_bf16(fmaxf(__uint_as_float(r[c * 8 + 2]) + sbias[c * 8 + 2], 0.f), fmaxf(__uint_as_float(r[c * 8 + 3]) + sbias[c * 8 + 3], 0.f));
-        u.z = pack_bf16(fmaxf(__uint_as_float(r[c * 8 + 4]) + sbias[c * 8 + 4], 0.f), fmaxf(__uint_as_float(r[c * 8 + 5]) + sbias[c * 8 + 5], 0.f));
-        u.w = pack_bf16(fmaxf(__uint_as_float(r[c * 8 + 6]) + sbias[c * 8 + 6], 0.f), fmaxf(__uint_as_float(r[c * 8 + 7]) + sbias[c * 8 + 7], 0.f));
+        u.x = pack_relu_bf16(__uint_as_float(r[c * 8 + 0]), __uint_as_float(r[c * 8 + 1]));
+        u.y = pack_relu_bf16(__uint_as_float(r[c * 8 + 2]), __uint_as_float(r[c * 8 + 3]));
+        u.z = pack_relu_bf16(__uint_as_float(r[c * 8 + 4]), __uint_as_float(r[c * 8 + 5]));
+        u.w = pack_relu_bf16(__uint_as_float(r[c * 8 + 6]), __uint_as_float(r[c * 8 + 7]));
         op[c] = u;
       }
     }
