@@ -5,6 +5,8 @@
 //  * pairwise ranking hinge (U:85-93) and its co-occurrence weighted form (U:95-110): one warp per row over the
 //    compacted list of non-zero targets, no [B,K,K] temporary.
 //  * the EMA consistency KL terms of T:809-813 (log_softmax / softmax / KLDivLoss batchmean) fwd + bwd.
+#include <stdlib.h>
+
 #include "lecb_common.cuh"
 #include "lecb_host.h"
 
@@ -22,8 +24,50 @@ __device__ __forceinline__ float pow_gamma(float base, float g) {
   return powf(base, g);
 }
 
-template <bool kFastGamma>
+// MUFU approximations with flush-to-zero: the plain intrinsics (__expf / __logf / __fdividef without -ftz) wrap every MUFU in a
+// denormal fix-up (compare, predicated scale, predicated undo: 3-4 extra instructions each), and none of the arguments below can
+// be denormal where it matters (1 + e >= 1, probabilities are clamped to eps first)
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// kLean (host-checked: gamma_pos = 1, gamma_neg = 2, thresh_neg <= thresh_pos so that a target is never positive AND negative,
+// eps a normal number): branch-free, one logarithm on the selected probability, four MUFU operations per element.  Same
+// expressions as the general form below, which stays for every other parameter set.
+template <bool kFastGamma, bool kLean>
 __device__ __forceinline__ void asl_elem(float x, float y, const AslParams& p, float& loss, float& grad) {
+  if (kLean) {
+    const float e = ex2_ftz(x * -1.4426950408889634f);
+    const float s = rcp_ftz(1.0f + e);                                  // e = +inf -> 0
+    const float oms = 1.0f - s;
+    const float sneg_raw = oms + p.clip;
+    const bool has_clip = p.clip > 0.f;
+    const bool clipped = has_clip && sneg_raw > 1.0f;
+    const float sneg = has_clip ? fminf(sneg_raw, 1.0f) : oms;
+    const bool pos = y > p.thresh_pos, neg = y < p.thresh_neg;          // mutually exclusive here
+    const float sel = pos ? s : sneg;                                   // p_t of a live element
+    const float lg = 0.6931471805599453f * lg2_ftz(fmaxf(sel, p.eps));
+    const float base = 1.0f - sel;
+    const float w = pos ? base : base * base;                           // (1 - p_t)^gamma, gamma = 1 / 2
+    const float dneg = (!clipped && sneg >= p.eps) ? -s * oms * rcp_ftz(sneg) : 0.f;     // d log(1 - s + clip) / dx
+    const float dpos = s >= p.eps ? oms : 0.f;                                            // d log(s) / dx
+    const float scale = (pos || neg) ? -w * p.inv_denom : 0.f;
+    loss = lg * scale;
+    grad = (pos ? dpos : dneg) * scale;
+    return;
+  }
   const float e = __expf(-x);
   const float s = __fdividef(1.0f, 1.0f + e);
   const float sneg_raw = 1.0f - s + p.clip;
@@ -49,7 +93,7 @@ __device__ __forceinline__ void asl_elem(float x, float y, const AslParams& p, f
   grad = -(dpos + dneg) * w * p.inv_denom;
 }
 
-template <bool kFastGamma>
+template <bool kFastGamma, bool kLean>
 __global__ void __launch_bounds__(256)
 asl_fwd_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ grad,
                    float* __restrict__ loss_out, int64_t n, AslParams p) {
@@ -66,14 +110,14 @@ asl_fwd_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, flo
     const float4 xb = __ldcs(x4 + i + stride), yb = __ldcs(y4 + i + stride);
     float4 ga, gb;
     float l;
-    asl_elem<kFastGamma>(xa.x, ya.x, p, l, ga.x); acc += l;
-    asl_elem<kFastGamma>(xa.y, ya.y, p, l, ga.y); acc += l;
-    asl_elem<kFastGamma>(xa.z, ya.z, p, l, ga.z); acc += l;
-    asl_elem<kFastGamma>(xa.w, ya.w, p, l, ga.w); acc += l;
-    asl_elem<kFastGamma>(xb.x, yb.x, p, l, gb.x); acc += l;
-    asl_elem<kFastGamma>(xb.y, yb.y, p, l, gb.y); acc += l;
-    asl_elem<kFastGamma>(xb.z, yb.z, p, l, gb.z); acc += l;
-    asl_elem<kFastGamma>(xb.w, yb.w, p, l, gb.w); acc += l;
+    asl_elem<kFastGamma, kLean>(xa.x, ya.x, p, l, ga.x); acc += l;
+    asl_elem<kFastGamma, kLean>(xa.y, ya.y, p, l, ga.y); acc += l;
+    asl_elem<kFastGamma, kLean>(xa.z, ya.z, p, l, ga.z); acc += l;
+    asl_elem<kFastGamma, kLean>(xa.w, ya.w, p, l, ga.w); acc += l;
+    asl_elem<kFastGamma, kLean>(xb.x, yb.x, p, l, gb.x); acc += l;
+    asl_elem<kFastGamma, kLean>(xb.y, yb.y, p, l, gb.y); acc += l;
+    asl_elem<kFastGamma, kLean>(xb.z, yb.z, p, l, gb.z); acc += l;
+    asl_elem<kFastGamma, kLean>(xb.w, yb.w, p, l, gb.w); acc += l;
     if (grad) {
       __stcs(reinterpret_cast<float4*>(grad) + i, ga);
       __stcs(reinterpret_cast<float4*>(grad) + i + stride, gb);
@@ -83,15 +127,15 @@ asl_fwd_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, flo
     const float4 xv = __ldcs(x4 + i), yv = __ldcs(y4 + i);
     float4 g;
     float l;
-    asl_elem<kFastGamma>(xv.x, yv.x, p, l, g.x); acc += l;
-    asl_elem<kFastGamma>(xv.y, yv.y, p, l, g.y); acc += l;
-    asl_elem<kFastGamma>(xv.z, yv.z, p, l, g.z); acc += l;
-    asl_elem<kFastGamma>(xv.w, yv.w, p, l, g.w); acc += l;
+    asl_elem<kFastGamma, kLean>(xv.x, yv.x, p, l, g.x); acc += l;
+    asl_elem<kFastGamma, kLean>(xv.y, yv.y, p, l, g.y); acc += l;
+    asl_elem<kFastGamma, kLean>(xv.z, yv.z, p, l, g.z); acc += l;
+    asl_elem<kFastGamma, kLean>(xv.w, yv.w, p, l, g.w); acc += l;
     if (grad) __stcs(reinterpret_cast<float4*>(grad) + i, g);
   }
   for (int64_t t = nvec * 4 + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += stride) {
     float l, g;
-    asl_elem<kFastGamma>(x[t], y[t], p, l, g);
+    asl_elem<kFastGamma, kLean>(x[t], y[t], p, l, g);
     acc += l;
     if (grad) grad[t] = g;
   }
@@ -323,15 +367,16 @@ kl_softmax_fwd_bwd_kernel(const float* __restrict__ x, const float* __restrict__
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int k = c * 32 + lane;
-      ea[c] = k < K ? __expf(a[c] - amax) : 0.f;          // kept: p and q below are these over the row sums
-      em[c] = k < K ? __expf(m[c] - mmax) : 0.f;
+      // (flush-to-zero MUFU forms, see asl_elem: the arguments are <= 0 and a term below 2^-126 of the row maximum is nothing)
+      ea[c] = k < K ? ex2_ftz((a[c] - amax) * 1.4426950408889634f) : 0.f;          // kept: p and q below are these over the row sums
+      em[c] = k < K ? ex2_ftz((m[c] - mmax) * 1.4426950408889634f) : 0.f;
       asum += ea[c];
       msum += em[c];
     }
     asum = warp_sum(asum);
     msum = warp_sum(msum);
-    const float la = __logf(asum), lm = __logf(msum);
-    const float ra = __fdividef(1.0f, asum), rm = __fdividef(1.0f, msum);
+    const float la = 0.6931471805599453f * lg2_ftz(asum), lm = 0.6931471805599453f * lg2_ftz(msum);      // sums in [1, K]
+    const float ra = rcp_ftz(asum), rm = rcp_ftz(msum);
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int k = c * 32 + lane;
@@ -510,10 +555,14 @@ extern "C" int lecb_asl_fwd_bwd(const float* logits, const float* targets, float
   const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
   if (blocks < 1) blocks = 1;
   if (blocks > cap) blocks = cap;
-  if (gamma_pos == 1.0f && gamma_neg == 2.0f)
-    launch_k(asl_fwd_bwd_kernel<true>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s, logits, targets, grad, loss, n, p);
+  static const bool no_lean = getenv("LECB_ASL_GENERAL") != nullptr;      // A/B and cross-check switch
+  const bool fast_gamma = gamma_pos == 1.0f && gamma_neg == 2.0f;
+  if (fast_gamma && thresh_neg <= thresh_pos && eps >= 1e-30f && !no_lean)
+    launch_k(asl_fwd_bwd_kernel<true, true>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s, logits, targets, grad, loss, n, p);
+  else if (fast_gamma)
+    launch_k(asl_fwd_bwd_kernel<true, false>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s, logits, targets, grad, loss, n, p);
   else
-    launch_k(asl_fwd_bwd_kernel<false>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s, logits, targets, grad, loss, n, p);
+    launch_k(asl_fwd_bwd_kernel<false, false>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s, logits, targets, grad, loss, n, p);
   count_launch();
   return check_launch("asl_fwd_bwd_kernel");
 }

@@ -36,6 +36,45 @@ def test_losses_match_reference():
         np.testing.assert_array_equal(a.detach().cpu().numpy(), g["x"])       # no in-place scaling (U:86 quirk)
 
 
+def _asl_float64(x, y, gamma_neg, gamma_pos, clip, eps, tp, tn, partial):
+    """U:126-173 in float64 (focal weight outside the graph, U:162-170)."""
+    x = x.double().requires_grad_(True)
+    s = torch.sigmoid(x)
+    pos, neg = (y > tp).double(), (y < tn).double()
+    sneg = 1 - s
+    if clip > 0:
+        sneg = (sneg + clip).clamp(max=1)
+    loss = pos * torch.log(s.clamp(min=eps)) + neg * torch.log(sneg.clamp(min=eps))
+    with torch.no_grad():
+        pt = s * pos + sneg * neg
+        w = torch.pow(1 - pt, gamma_pos * pos + gamma_neg * neg)
+    loss = -(loss * w).sum() / (x.shape[0] if partial else x.numel())
+    loss.backward()
+    return loss.detach(), x.grad
+
+
+@pytest.mark.parametrize("tp,tn,gn", [(0.9, 0.9, 2.0), (0.9, -0.9, 2.0), (0.9, 0.9, 4.0), (0.3, 0.6, 2.0)])
+def test_asl_kernel_variants_match_float64(tp, tn, gn):
+    """The lean kernel (gamma 1 / 2, exclusive thresholds: flush-to-zero MUFU forms, one logarithm), the general fast-gamma kernel
+    (overlapping thresholds: a target both positive and negative) and the powf kernel against the float64 formula, with
+    saturated logits (sigmoid = 0 / 1 in fp32) and partial labels {-1, 0, 1} in the batch."""
+    from lecb200 import ops
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = torch.randn((4096, 80), generator=g) * 3
+    x[0, :8] = torch.tensor([-120.0, -90.0, -30.0, -17.0, 17.0, 30.0, 90.0, 120.0])
+    y = torch.randint(-1, 2, (4096, 80), generator=g).float()
+    y[1, :4] = torch.tensor([0.5, 0.45, 0.95, -0.95])
+    x, y = x.cuda(), y.cuda()
+    for partial in (False, True):
+        loss, grad = ops.asl_fwd_bwd(x, y, gamma_neg=gn, gamma_pos=1.0, clip=0.05, eps=1e-8, thresh_pos=tp, thresh_neg=tn,
+                                     partial=partial)
+        want_l, want_g = _asl_float64(x, y, gn, 1.0, 0.05, 1e-8, tp, tn, partial)
+        assert abs(loss.item() - want_l.item()) <= 2e-5 * max(1.0, abs(want_l.item())), (loss.item(), want_l.item())
+        scale = want_g.abs().max().item()
+        assert (grad.double() - want_g).abs().max().item() <= 2e-5 * scale
+        assert torch.isfinite(grad).all()
+
+
 def test_loss_kernels_scale():
     """Size-independent properties at a roofline-sized input: ASL of [2^18, 80] equals the mean of per-chunk
     losses; gradient rows only depend on their own row."""
