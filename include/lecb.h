@@ -170,7 +170,11 @@ int lecb_global_logits(const float* g_unit, const float* g_add, const float* tpo
                        float scale, void* stream);
 
 /* ---- asymmetric loss forward + backward (U:126-173): loss (scalar, device) and dloss/dlogits ----
- * partial != 0: -sum/B (dualcoop_loss, U:175-181); else -mean (ASL_loss, U:184-190). grad may be NULL. */
+ * partial != 0: -sum/B (dualcoop_loss, U:175-181); else -mean (ASL_loss, U:184-190). grad may be NULL.
+ * exp / log / reciprocal are the hardware approximations (ex2 / lg2 / rcp.approx.ftz: <= 2 ulp); against the float64 formula the
+ * loss agrees to 2e-5 relative and every gradient element to 2e-5 of the largest one (tests/test_train_gpu.py).  gamma_pos = 1,
+ * gamma_neg = 2 with thresh_neg <= thresh_pos (the two shipped call sites) run a branch-free variant with one logarithm per
+ * element; environment LECB_ASL_GENERAL=1 keeps the general variant for them as well. */
 int lecb_asl_fwd_bwd(const float* logits, const float* targets, float* grad, float* loss, int64_t B, int K,
                      float gamma_neg, float gamma_pos, float clip, float eps, float thresh_pos, float thresh_neg,
                      int partial, void* stream);
